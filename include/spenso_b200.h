@@ -1,0 +1,228 @@
+/* spenso_b200 — C ABI of the B200-native contraction engine.
+ *
+ * This is the drop-in boundary for spenso's concrete-data path.  The reference is Rust
+ * with no FFI on this path; a Rust shim implements
+ *   trait Contract            spenso/src/contraction.rs:32-35
+ *   Network::execute / ExecuteOp for NetworkStore   spenso/src/network.rs:1197-1241, 1244-1706
+ *   DataTensor / DenseTensor / SparseTensor storage spenso/src/tensors/data.rs:190-193,
+ *                                                    data/dense.rs:51-54, data/sparse.rs:48-53
+ * for a device-backed batched tensor by calling the entry points below.
+ *
+ * Conventions: plain pointers and sizes, opaque handles, int status returns
+ * (0 = ok), thread-local last-error string; no exceptions cross the boundary.  All
+ * device work is enqueued on the context's CUDA stream.  Complex data is interleaved
+ * (re, im) f64 — bit-compatible with spenso's Complex<f64>
+ * (spenso/src/algebra/complex.rs:55-58).  There is NO CPU execution path: every
+ * compute entry point fails with SPN_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef SPENSO_B200_H
+#define SPENSO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPN_VERSION 100
+#define SPN_MAX_ORDER 16            /* max indices per operand */
+#define SPN_MAX_OUT_ORDER 32        /* max indices of a pairwise result */
+
+/* ---- status codes (ContractionError, spenso/src/contraction.rs:20-30) ---------- */
+enum {
+  SPN_OK = 0,
+  SPN_ERR_EMPTY_SPARSE = 1, /* ContractionError::EmptySparse                        */
+  SPN_ERR_STRUCTURE = 2,    /* ContractionError::StructureError / merge invariants  */
+  SPN_ERR_DIMENSION = 3,    /* ContractionError::DimensionError                     */
+  SPN_ERR_OTHER = 4,        /* ContractionError::Other                              */
+  SPN_ERR_CUDA = 5,
+  SPN_ERR_NO_DEVICE = 6,
+  SPN_ERR_INVALID = 7,
+  SPN_ERR_JIT = 8
+};
+
+/* ---- index structure (R1-R3) ---------------------------------------------------- */
+/* LibraryRep, spenso/src/structure/representation.rs:583-620 */
+enum { SPN_REP_DUMMY = 0, SPN_REP_SELF_DUAL = 1, SPN_REP_INLINE_METRIC = 2, SPN_REP_DUALIZABLE = 3 };
+/* AbstractIndex, spenso/src/structure/abstract_index.rs:267-294 */
+enum { SPN_AIND_NORMAL = 0, SPN_AIND_DUALIZE = 1, SPN_AIND_DOUBLE = 2, SPN_AIND_DUMMY = 3, SPN_AIND_ADDED = 4 };
+
+/* Slot<LibraryRep, AbstractIndex>, spenso/src/structure/slot.rs:53-56 (16 bytes) */
+typedef struct spn_slot {
+  uint8_t rep_kind;  /* SPN_REP_*                                                    */
+  uint8_t aind_kind; /* SPN_AIND_*                                                   */
+  int16_t rep_id;    /* SelfDual(n)/InlineMetric(n): n; Dualizable(k): +k base, -k dual */
+  uint32_t dim;      /* Dimension::Concrete                                          */
+  uint64_t aind;     /* index payload; Double(a,b) packed (a<<16)|b                  */
+} spn_slot;
+
+/* MergeInfo, spenso/src/structure.rs:716-751 */
+enum { SPN_FIRST_BEFORE_SECOND = 0, SPN_SECOND_BEFORE_FIRST = 1, SPN_INTERLEAVED = 2 };
+
+/* Result of StructureContract::merge (spenso/src/structure/ordered.rs:594-919) plus the
+ * stride plan the kernels replay.  Plain data: comparable byte-for-byte.
+ *   out[o] = sum_k  sign(k) * A[offA(o) + kA(k)] * B[offB(o) + kB(k)]
+ *   o  = row-major index over out_dim[];  offX(o) = sum_d idx_d * out_stride_x[d]
+ *   k  = row-major index over k_dim[] (contracted dims in OTHER's order, last fastest)
+ *   sign(k) = XOR over contracted dims with k_metric[d] of (k_d > 0)      (Minkowski) */
+typedef struct spn_contract_plan {
+  uint32_t order_a, order_b, order_out, n_common;
+  uint32_t merge_kind;  /* SPN_FIRST_BEFORE_SECOND | SPN_SECOND_BEFORE_FIRST | SPN_INTERLEAVED */
+  uint32_t n_partition; /* == order_out unless an operand is scalar                     */
+  int64_t base_start, dual_start; /* of the result structure; -1 = none                */
+  uint64_t size_a, size_b, size_out, n_contracted;
+  spn_slot out_slots[SPN_MAX_OUT_ORDER];
+  uint8_t common_a[SPN_MAX_ORDER];
+  uint8_t common_b[SPN_MAX_ORDER];
+  uint8_t partition[SPN_MAX_OUT_ORDER]; /* 1 = slot comes from a (self)                 */
+  uint32_t out_dim[SPN_MAX_OUT_ORDER];
+  uint64_t out_stride_a[SPN_MAX_OUT_ORDER];
+  uint64_t out_stride_b[SPN_MAX_OUT_ORDER];
+  uint32_t k_dim[SPN_MAX_ORDER];
+  uint64_t k_stride_a[SPN_MAX_ORDER];
+  uint64_t k_stride_b[SPN_MAX_ORDER];
+  uint8_t k_metric[SPN_MAX_ORDER];
+  uint8_t k_pos_a[SPN_MAX_ORDER]; /* position in a of the d-th contracted pair          */
+  uint8_t k_pos_b[SPN_MAX_ORDER]; /* position in b                                     */
+} spn_contract_plan;
+
+const char* spn_last_error(void);
+int spn_version(void);
+
+/* PermutedStructure::from(Vec<Slot>) — ordered.rs:321-380.  out[i] = in[perm[i]]. */
+int spn_structure_canonicalize(const spn_slot* in, uint32_t n, spn_slot* out, int32_t* perm,
+                               int64_t* base_start, int64_t* dual_start);
+/* merge + MergeInfo + match_indices + strides — ordered.rs:594-919, structure.rs:435-460, 566-577.
+ * a and b must be canonically ordered. */
+int spn_plan_contract(const spn_slot* a, uint32_t na, const spn_slot* b, uint32_t nb, spn_contract_plan* out);
+
+/* ---- context --------------------------------------------------------------------- */
+typedef struct spn_ctx spn_ctx;
+int spn_ctx_create(int device, spn_ctx** out);
+void spn_ctx_destroy(spn_ctx* ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the legacy default stream */
+int spn_ctx_set_stream(spn_ctx* ctx, void* cuda_stream);
+int spn_ctx_synchronize(spn_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t spn_ctx_launch_count(const spn_ctx* ctx);
+int spn_ctx_sm_count(const spn_ctx* ctx);
+
+/* ---- tensors (S1) ---------------------------------------------------------------- */
+enum { SPN_F64 = 0, SPN_C64 = 1 };
+/* device layout of a batched tensor: [point][flat] (what n reference DenseTensors laid end to
+ * end look like) or [flat][point] */
+enum { SPN_POINT_MAJOR = 0, SPN_COMPONENT_MAJOR = 1 };
+enum { SPN_STORAGE_BATCHED = 0, SPN_STORAGE_SHARED_DENSE = 1, SPN_STORAGE_SHARED_SPARSE = 2 };
+
+typedef struct spn_tensor spn_tensor;
+
+/* Batched dense tensor: one DenseTensor<f64|Complex<f64>> per phase-space point, device resident.
+ * slots must be canonically ordered (use spn_structure_canonicalize). */
+int spn_tensor_batched(spn_ctx* ctx, const spn_slot* slots, uint32_t n, uint64_t n_points, int dtype, int layout,
+                       spn_tensor** out);
+/* same, over device memory owned by the caller (e.g. a torch tensor) */
+int spn_tensor_batched_wrap(spn_ctx* ctx, const spn_slot* slots, uint32_t n, uint64_t n_points, int dtype,
+                            int layout, void* device_ptr, spn_tensor** out);
+/* Shared (point-independent) tensors: DenseTensor / SparseTensor of Complex<f64>.  Host data in
+ * canonical row-major order; sparse entries keyed by canonical flat index. */
+int spn_tensor_shared_dense(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const double* reim, spn_tensor** out);
+int spn_tensor_shared_sparse(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const uint64_t* flat,
+                             const double* reim, uint64_t nnz, spn_tensor** out);
+void spn_tensor_free(spn_tensor* t);
+
+uint32_t spn_tensor_order(const spn_tensor* t);
+int spn_tensor_slots(const spn_tensor* t, spn_slot* out);
+uint64_t spn_tensor_size(const spn_tensor* t);     /* elements per point */
+uint64_t spn_tensor_n_points(const spn_tensor* t); /* 1 for shared */
+int spn_tensor_storage(const spn_tensor* t);
+int spn_tensor_dtype(const spn_tensor* t);
+int spn_tensor_layout(const spn_tensor* t);
+uint64_t spn_tensor_nnz(const spn_tensor* t);
+void* spn_tensor_device_ptr(const spn_tensor* t);
+
+/* host <-> device; host data is [point][flat] interleaved re/im regardless of the device layout */
+int spn_tensor_upload(spn_tensor* t, const void* host, uint64_t first_point, uint64_t n_points);
+/* same, without the final stream synchronisation: `host` must stay valid (and should be pinned)
+ * until the context's stream has passed this point */
+int spn_tensor_upload_async(spn_tensor* t, const void* host, uint64_t first_point, uint64_t n_points);
+int spn_tensor_download(const spn_tensor* t, void* host, uint64_t first_point, uint64_t n_points);
+/* sparse shared tensors: entries sorted by flat index */
+int spn_tensor_sparse_entries(const spn_tensor* t, uint64_t* flat, double* reim);
+
+/* ---- pairwise ops (the Contract trait and friends) -------------------------------- */
+/* a.contract(&b): contraction.rs:126-227.  Result storage: batched dense if either operand is
+ * batched; else shared — Dense unless both are Sparse (contraction.rs:219-224). */
+int spn_tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out);
+/* element-wise: algebra/add_assign.rs, sub_assign.rs, neg.rs, scalar_mul.rs */
+int spn_tensor_add(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, int subtract, spn_tensor** out);
+int spn_tensor_neg(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+int spn_tensor_scalar_mul(spn_ctx* ctx, const spn_tensor* a, double re, double im, spn_tensor** out);
+int spn_tensor_conj(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+/* Trace::internal_contract — contraction/trace.rs:12-83; slots may contain one repeated pair per call */
+int spn_tensor_trace(spn_ctx* ctx, const spn_slot* slots_with_repeats, uint32_t n, const spn_tensor* a,
+                     spn_tensor** out);
+/* sum over the point axis (Monte-Carlo partial sum); out_device receives 2*size f64 on device */
+int spn_tensor_reduce_points(spn_ctx* ctx, const spn_tensor* a, double* out_device);
+
+/* ---- networks (N1) --------------------------------------------------------------- */
+/* NetworkOp, spenso/src/network/graph.rs (Sum/Neg/Product/Power/Function) */
+enum { SPN_OP_PRODUCT = 3, SPN_OP_SUM = 4, SPN_OP_NEG = 5, SPN_OP_POWER = 6, SPN_OP_CONJ = 7 };
+/* built-in library tensors, spenso-hep-lib/src/lib.rs:27-387 (argument order bis i, bis j[, mink mu]) */
+enum {
+  SPN_LIB_GAMMA_WEYL = 0, SPN_LIB_GAMMA_DIRAC = 1, SPN_LIB_GAMMA0_WEYL = 2, SPN_LIB_GAMMA5_WEYL = 3,
+  SPN_LIB_PROJM_WEYL = 4, SPN_LIB_PROJP_WEYL = 5, SPN_LIB_METRIC = 6
+};
+enum { SPN_EXEC_FUSED = 0 /* one JIT-specialised sm_100a kernel per network */,
+       SPN_EXEC_STEPWISE = 1 /* one pairwise kernel per contraction, intermediates in HBM */ };
+
+typedef struct spn_net spn_net;
+int spn_net_create(spn_ctx* ctx, spn_net** out);
+void spn_net_destroy(spn_net* net);
+/* leaves: return node ids (>= 0) or a negative status */
+/* per-point input tensor; slots in the caller's argument order (canonicalised internally, the
+ * bound data must be in CANONICAL order, like a reference DenseTensor) */
+int spn_net_leaf_batched(spn_net* net, const spn_slot* slots, uint32_t n, int dtype);
+/* the SAME per-point tensor under other index labels (what the reference gets by instantiating one
+ * shadowed tensor, e.g. a momentum K, with different abstract indices): `leaf` is a node returned by
+ * spn_net_leaf_batched; slots are in the same argument order, same representations and dimensions.
+ * No new input is created — both leaves read the input bound to the original. */
+int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t n);
+/* point-independent local tensor (Network::from_tensor): an existing shared tensor */
+int spn_net_leaf_shared(spn_net* net, const spn_tensor* shared);
+/* library tensor with concrete indices in argument order (NetworkLeaf::LibraryKey + get_lib_data,
+ * network/graph.rs:291-322).  For SPN_LIB_METRIC pass the two slots. */
+int spn_net_leaf_library(spn_net* net, int which, const spn_slot* slots, uint32_t n);
+/* user library tensor: sparse entries keyed by ARGUMENT-order flat index */
+int spn_net_leaf_library_custom(spn_net* net, const spn_slot* slots, uint32_t n, const uint64_t* flat,
+                                const double* reim, uint64_t nnz);
+int spn_net_leaf_scalar(spn_net* net, double re, double im);
+int spn_net_op(spn_net* net, int op, const int32_t* children, uint32_t n_children, int32_t power);
+int spn_net_set_root(spn_net* net, int node);
+/* Run the graph walk, merge and schedule ONCE (they are identical for every point), then build
+ * the device program. */
+int spn_net_compile(spn_net* net, int exec_mode);
+/* result structure (canonical) — valid after compile */
+uint32_t spn_net_result_order(const spn_net* net);
+int spn_net_result_slots(const spn_net* net, spn_slot* out);
+uint64_t spn_net_result_size(const spn_net* net);
+uint32_t spn_net_n_inputs(const spn_net* net);
+/* number of pairwise contractions in the schedule and (a,b) node pairs in execution order */
+int spn_net_schedule(const spn_net* net, int32_t* pairs, uint32_t cap);
+/* generated CUDA source of the fused kernel (NUL terminated; owned by net) */
+const char* spn_net_cuda_source(const spn_net* net);
+/* FP64 arithmetic instructions (DMUL/DADD/DFMA) per point of the compiled fused program */
+uint64_t spn_net_macs_per_point(const spn_net* net);
+/* bytes of per-point input the fused kernel actually reads (components multiplied by structural
+ * zeros of the shared tensors are never loaded) */
+uint64_t spn_net_input_bytes_per_point(const spn_net* net);
+/* Network::execute for all points: inputs[i] is the batched tensor bound to the i-th
+ * spn_net_leaf_batched (creation order).  out (optional) receives the per-point result tensor;
+ * sum_out_device (optional) receives sum over points (2*result_size f64, device memory).
+ * n_points == 0: all points of inputs[0]. */
+int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_inputs, spn_tensor* out,
+                    double* sum_out_device, uint64_t first_point, uint64_t n_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPENSO_B200_H */

@@ -1,0 +1,594 @@
+// C ABI (include/spenso_b200.h): context, device tensors and the pairwise ops
+// (Contract / add / sub / neg / scalar_mul / conj / trace / reduce).  Every compute entry point
+// launches the sm_100a kernels of kernels.cu; there is no host execution path.
+#include <cstring>
+#include <memory>
+
+#include "tensor.hpp"
+
+using namespace spn;
+
+static thread_local std::string g_err;
+void spn::set_error(const std::string& s) { g_err = s; }
+
+#define API_TRY try {
+#define API_CATCH                      \
+  }                                    \
+  catch (const Error& e) {             \
+    g_err = e.what();                  \
+    return e.code;                     \
+  }                                    \
+  catch (const std::exception& e) {    \
+    g_err = e.what();                  \
+    return SPN_ERR_OTHER;              \
+  }
+
+namespace spn {
+
+KTables build_k_tables(const spn_contract_plan& p) {
+  KTables t;
+  uint32_t nd = p.n_common;
+  uint64_t nk = p.n_contracted;
+  if (nd == 0) nk = 1;
+  t.off_a.resize(nk);
+  t.off_b.resize(nk);
+  t.sign.resize(nk);
+  std::vector<uint32_t> idx(nd, 0);
+  for (uint64_t k = 0; k < nk; ++k) {
+    long long oa = 0, ob = 0;
+    bool neg = false;
+    for (uint32_t d = 0; d < nd; ++d) {
+      oa += (long long)idx[d] * (long long)p.k_stride_a[d];
+      ob += (long long)idx[d] * (long long)p.k_stride_b[d];
+      if (p.k_metric[d] && idx[d] > 0) neg = !neg;
+    }
+    t.off_a[k] = (int)oa;
+    t.off_b[k] = (int)ob;
+    t.sign[k] = neg ? 1 : 0;
+    for (uint32_t d = nd; d-- > 0;) {  // odometer, last contracted dim fastest
+      if (++idx[d] < p.k_dim[d]) break;
+      idx[d] = 0;
+    }
+  }
+  return t;
+}
+
+DevOutMap out_map_of(const spn_contract_plan& p) {
+  DevOutMap m{};
+  m.order = (int)p.order_out;
+  for (uint32_t r = 0; r < p.order_out; ++r) {
+    m.dim[r] = p.out_dim[r];
+    m.sa[r] = (long long)p.out_stride_a[r];
+    m.sb[r] = (long long)p.out_stride_b[r];
+  }
+  m.size_out = p.size_out;
+  return m;
+}
+
+static void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  cuda_check(cudaMalloc(&p, bytes ? bytes : 16), "cudaMalloc");
+  return p;
+}
+
+spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, int dtype, int layout, void* wrap) {
+  auto t = std::make_unique<spn_tensor>();
+  t->ctx = ctx;
+  t->st = st;
+  t->storage = SPN_STORAGE_BATCHED;
+  t->dtype = dtype;
+  t->layout = layout;
+  t->n_points = n_points;
+  if (wrap) {
+    t->dptr = wrap;
+    t->owns = false;
+  } else {
+    t->dptr = dev_alloc(n_points * st.size() * t->elem_bytes());
+    t->owns = true;
+  }
+  return t.release();
+}
+
+static void upload_shared(spn_tensor* t) {
+  t->dptr = dev_alloc(t->host_dense.size() * sizeof(double2));
+  t->owns = true;
+  cuda_check(cudaMemcpyAsync(t->dptr, t->host_dense.data(), t->host_dense.size() * sizeof(double2),
+                             cudaMemcpyHostToDevice, t->ctx->stream),
+             "upload shared tensor");
+  cuda_check(cudaStreamSynchronize(t->ctx->stream), "upload shared tensor");
+}
+
+spn_tensor* new_shared_dense(spn_ctx* ctx, const Structure& st, const double2* data) {
+  auto t = std::make_unique<spn_tensor>();
+  t->ctx = ctx;
+  t->st = st;
+  t->storage = SPN_STORAGE_SHARED_DENSE;
+  t->host_dense.assign(data, data + st.size());
+  upload_shared(t.get());
+  return t.release();
+}
+spn_tensor* new_shared_sparse(spn_ctx* ctx, const Structure& st, const std::map<uint64_t, double2>& entries) {
+  auto t = std::make_unique<spn_tensor>();
+  t->ctx = ctx;
+  t->st = st;
+  t->storage = SPN_STORAGE_SHARED_SPARSE;
+  t->entries = entries;
+  t->host_dense.assign(st.size(), make_double2(0.0, 0.0));
+  for (auto& kv : entries) {
+    if (kv.first >= st.size()) throw Error(SPN_ERR_INVALID, "sparse flat index out of bounds");
+    t->host_dense[kv.first] = kv.second;
+  }
+  upload_shared(t.get());
+  return t.release();
+}
+
+template <class T>
+struct DevArray {
+  T* p = nullptr;
+  cudaStream_t s;
+  DevArray(const std::vector<T>& h, cudaStream_t stream) : s(stream) {
+    cuda_check(cudaMallocAsync((void**)&p, (h.size() ? h.size() : 1) * sizeof(T), s), "cudaMallocAsync");
+    if (!h.empty())
+      cuda_check(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s), "table upload");
+  }
+  ~DevArray() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+// ContractionError::EmptySparse (singlecontract.rs:153-159 and the other sparse-receiver kernels):
+// a sparse receiver with no stored entry facing a dense operand with no data.
+static void check_empty_sparse(const spn_tensor* a, const spn_tensor* b, int merge_kind) {
+  const spn_tensor* recv = merge_kind == SPN_SECOND_BEFORE_FIRST ? b : a;
+  const spn_tensor* oth = merge_kind == SPN_SECOND_BEFORE_FIRST ? a : b;
+  if (recv->sparse() && !oth->sparse() && recv->entries.empty() && oth->size() * oth->n_points == 0)
+    throw Error(SPN_ERR_EMPTY_SPARSE, "Sparse tensor is empty");
+}
+
+void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out) {
+  spn_contract_plan plan = plan_contract(a->st, b->st);
+  check_empty_sparse(a, b, (int)plan.merge_kind);
+  Structure rs = structure_of_plan_result(plan);
+  uint64_t n_points = 1;
+  if (a->batched() && b->batched()) {
+    if (a->n_points != b->n_points) throw Error(SPN_ERR_INVALID, "batched operands have different point counts");
+    n_points = a->n_points;
+  } else if (a->batched()) {
+    n_points = a->n_points;
+  } else if (b->batched()) {
+    n_points = b->n_points;
+  }
+  const bool any_batched = a->batched() || b->batched();
+  const int out_dtype = (a->dtype == SPN_F64 && b->dtype == SPN_F64) ? SPN_F64 : SPN_C64;
+  const int out_layout = a->batched() ? a->layout : (b->batched() ? b->layout : SPN_POINT_MAJOR);
+  std::unique_ptr<spn_tensor> res(new_batched(ctx, rs, n_points, out_dtype, out_layout, nullptr));
+  const bool point_fastest = out_layout == SPN_COMPONENT_MAJOR;
+  KTables kt = build_k_tables(plan);
+  DevOutMap map = out_map_of(plan);
+  if (kt.off_a.size() > (size_t)1 << 24) throw Error(SPN_ERR_INVALID, "contracted volume too large for the table path");
+
+  const bool a_sp = a->sparse(), b_sp = b->sparse();
+  if (a_sp != b_sp) {
+    // K2: one shared sparse operand -> CSR gather over the stored entries only
+    const spn_tensor* sp = a_sp ? a : b;
+    const spn_tensor* dn = a_sp ? b : a;
+    const auto& s_out = a_sp ? plan.out_stride_a : plan.out_stride_b;
+    const auto& d_out = a_sp ? plan.out_stride_b : plan.out_stride_a;
+    const auto& ks = a_sp ? kt.off_a : kt.off_b;
+    const auto& kd = a_sp ? kt.off_b : kt.off_a;
+    std::vector<int> row_ptr(plan.size_out + 1, 0), col;
+    std::vector<double2> val;
+    std::vector<unsigned char> sgn;
+    std::vector<uint32_t> idx(plan.order_out, 0);
+    for (uint64_t o = 0; o < plan.size_out; ++o) {
+      uint64_t offs = 0, offd = 0;
+      for (uint32_t r = 0; r < plan.order_out; ++r) {
+        offs += (uint64_t)idx[r] * s_out[r];
+        offd += (uint64_t)idx[r] * d_out[r];
+      }
+      for (size_t k = 0; k < ks.size(); ++k) {
+        auto it = sp->entries.find(offs + (uint64_t)ks[k]);
+        if (it == sp->entries.end()) continue;
+        col.push_back((int)(offd + (uint64_t)kd[k]));
+        val.push_back(it->second);
+        sgn.push_back(kt.sign[k]);
+      }
+      row_ptr[o + 1] = (int)col.size();
+      for (uint32_t r = plan.order_out; r-- > 0;) {
+        if (++idx[r] < plan.out_dim[r]) break;
+        idx[r] = 0;
+      }
+    }
+    DevArray<int> d_row(row_ptr, ctx->stream), d_col(col, ctx->stream);
+    DevArray<double2> d_val(val, ctx->stream);
+    DevArray<unsigned char> d_sgn(sgn, ctx->stream);
+    cuda_check(launch_contract_csr(dn->operand(), res->output(), d_row.p, d_col.p, d_val.p, d_sgn.p,
+                                   /*dense_is_first=*/a_sp ? 0 : 1, plan.size_out, col.size(), n_points,
+                                   point_fastest, ctx->stream),
+               "contract_csr_kernel");
+    ctx->launches++;
+  } else {
+    // K1/K5/K7 (and sparse x sparse over the densified shared copies; the structural/zero
+    // filter of the sparse result is applied below)
+    DevArray<int> d_ka(kt.off_a, ctx->stream), d_kb(kt.off_b, ctx->stream);
+    DevArray<unsigned char> d_ks(kt.sign, ctx->stream);
+    cuda_check(launch_contract_dense(map, a->operand(), b->operand(), res->output(), d_ka.p, d_kb.p, d_ks.p,
+                                     kt.off_a.size(), n_points, point_fastest, ctx->stream),
+               "contract_dense_kernel");
+    ctx->launches++;
+  }
+  if (any_batched) {
+    *out = res.release();
+    return;
+  }
+  // shared x shared: the result is itself a shared tensor (computed on the device with one point)
+  std::vector<double2> host(plan.size_out);
+  cuda_check(cudaMemcpyAsync(host.data(), res->dptr, host.size() * sizeof(double2), cudaMemcpyDeviceToHost,
+                             ctx->stream),
+             "download shared result");
+  cuda_check(cudaStreamSynchronize(ctx->stream), "download shared result");
+  if (a_sp && b_sp) {
+    // Sparse x Sparse -> Sparse (contraction.rs:222-224): an entry exists iff at least one pair of
+    // stored entries met (structural, integer work) AND the value is not exactly zero
+    // (singlecontract.rs:268, multicontract.rs:276).  Receiver without entries => empty result.
+    std::map<uint64_t, double2> ent;
+    const spn_tensor* recv = plan.merge_kind == SPN_SECOND_BEFORE_FIRST ? b : a;
+    if (!recv->entries.empty()) {
+      std::vector<uint32_t> idx(plan.order_out, 0);
+      for (uint64_t o = 0; o < plan.size_out; ++o) {
+        uint64_t offa = 0, offb = 0;
+        for (uint32_t r = 0; r < plan.order_out; ++r) {
+          offa += (uint64_t)idx[r] * plan.out_stride_a[r];
+          offb += (uint64_t)idx[r] * plan.out_stride_b[r];
+        }
+        bool met = false;
+        for (size_t k = 0; k < kt.off_a.size() && !met; ++k)
+          met = a->entries.count(offa + (uint64_t)kt.off_a[k]) && b->entries.count(offb + (uint64_t)kt.off_b[k]);
+        // exterior products keep every met pair, even exact zeros (exteriorproduct.rs:19-46)
+        if (met && (plan.n_common == 0 || host[o].x != 0.0 || host[o].y != 0.0)) ent[o] = host[o];
+        for (uint32_t r = plan.order_out; r-- > 0;) {
+          if (++idx[r] < plan.out_dim[r]) break;
+          idx[r] = 0;
+        }
+      }
+    }
+    *out = new_shared_sparse(ctx, rs, ent);
+  } else {
+    *out = new_shared_dense(ctx, rs, host.data());
+  }
+}
+
+void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out) {
+  const bool binary = op == EW_ADD || op == EW_SUB;
+  if (binary) {
+    if (a->st.order() != b->st.order() || a->size() != b->size())
+      throw Error(SPN_ERR_STRUCTURE, "element-wise op on tensors of different structure");
+    for (uint32_t i = 0; i < a->st.order(); ++i)
+      if (!slot_same(a->st.slots[i], b->st.slots[i]))
+        throw Error(SPN_ERR_STRUCTURE, "element-wise op on tensors of different structure");
+    if (a->batched() && b->batched() && a->n_points != b->n_points)
+      throw Error(SPN_ERR_INVALID, "batched operands have different point counts");
+  }
+  uint64_t n_points = a->batched() ? a->n_points : (binary && b->batched() ? b->n_points : 1);
+  const bool any_batched = a->batched() || (binary && b->batched());
+  int dtype = a->dtype;
+  if (binary && b->dtype == SPN_C64) dtype = SPN_C64;
+  if (op == EW_SCALE && s.y != 0.0) dtype = SPN_C64;
+  if (op == EW_SCALE && a->dtype == SPN_F64 && s.y == 0.0) dtype = SPN_F64;
+  const int layout = a->batched() ? a->layout : (binary && b->batched() ? b->layout : SPN_POINT_MAJOR);
+  std::unique_ptr<spn_tensor> res(new_batched(ctx, a->st, n_points, dtype, layout, nullptr));
+  DevOperand ob = binary ? b->operand() : a->operand();
+  cuda_check(launch_elementwise(op, a->operand(), ob, res->output(), s, a->size(), n_points,
+                                layout == SPN_COMPONENT_MAJOR, ctx->stream),
+             "elementwise_kernel");
+  ctx->launches++;
+  if (any_batched) {
+    *out = res.release();
+    return;
+  }
+  std::vector<double2> host(a->size());
+  cuda_check(cudaMemcpyAsync(host.data(), res->dptr, host.size() * sizeof(double2), cudaMemcpyDeviceToHost,
+                             ctx->stream),
+             "download shared result");
+  cuda_check(cudaStreamSynchronize(ctx->stream), "download shared result");
+  const bool keep_sparse = binary ? (a->sparse() && b->sparse()) : a->sparse();
+  if (keep_sparse) {
+    std::map<uint64_t, double2> ent;
+    for (auto& kv : a->entries) ent[kv.first] = host[kv.first];
+    if (binary)
+      for (auto& kv : b->entries) ent[kv.first] = host[kv.first];
+    *out = new_shared_sparse(ctx, a->st, ent);
+  } else {
+    *out = new_shared_dense(ctx, a->st, host.data());
+  }
+}
+
+}  // namespace spn
+
+// =================================================================================================
+extern "C" {
+
+const char* spn_last_error(void) { return g_err.c_str(); }
+int spn_version(void) { return SPN_VERSION; }
+
+int spn_structure_canonicalize(const spn_slot* in, uint32_t n, spn_slot* out, int32_t* perm, int64_t* base_start,
+                               int64_t* dual_start) {
+  API_TRY
+  std::vector<int32_t> p;
+  Structure st = canonicalize(std::vector<spn_slot>(in, in + n), &p);
+  for (uint32_t i = 0; i < n; ++i) {
+    out[i] = st.slots[i];
+    if (perm) perm[i] = p[i];
+  }
+  if (base_start) *base_start = st.base_start;
+  if (dual_start) *dual_start = st.dual_start;
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_plan_contract(const spn_slot* a, uint32_t na, const spn_slot* b, uint32_t nb, spn_contract_plan* out) {
+  API_TRY
+  if (na > SPN_MAX_ORDER || nb > SPN_MAX_ORDER) throw Error(SPN_ERR_INVALID, "operand order exceeds SPN_MAX_ORDER");
+  Structure A = structure_of_canonical(a, na), B = structure_of_canonical(b, nb);
+  *out = plan_contract(A, B);
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_ctx_create(int device, spn_ctx** out) {
+  API_TRY
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    throw Error(SPN_ERR_NO_DEVICE, std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                                       " (spenso_b200 has no CPU execution path)");
+  if (device < 0 || device >= count) throw Error(SPN_ERR_INVALID, "device index out of range");
+  cuda_check(cudaSetDevice(device), "cudaSetDevice");
+  auto c = std::make_unique<spn_ctx>();
+  c->device = device;
+  cuda_check(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "device attribute");
+  cuda_check(cudaFree(0), "context init");
+  *out = c.release();
+  return SPN_OK;
+  API_CATCH
+}
+void spn_ctx_destroy(spn_ctx* ctx) { delete ctx; }
+int spn_ctx_set_stream(spn_ctx* ctx, void* s) {
+  ctx->stream = (cudaStream_t)s;
+  return SPN_OK;
+}
+int spn_ctx_synchronize(spn_ctx* ctx) {
+  API_TRY
+  cuda_check(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  return SPN_OK;
+  API_CATCH
+}
+uint64_t spn_ctx_launch_count(const spn_ctx* ctx) { return ctx->launches; }
+int spn_ctx_sm_count(const spn_ctx* ctx) { return ctx->sm_count; }
+
+int spn_tensor_batched(spn_ctx* ctx, const spn_slot* slots, uint32_t n, uint64_t n_points, int dtype, int layout,
+                       spn_tensor** out) {
+  API_TRY
+  *out = new_batched(ctx, structure_of_canonical(slots, n), n_points, dtype, layout, nullptr);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_batched_wrap(spn_ctx* ctx, const spn_slot* slots, uint32_t n, uint64_t n_points, int dtype, int layout,
+                            void* device_ptr, spn_tensor** out) {
+  API_TRY
+  if (!device_ptr) throw Error(SPN_ERR_INVALID, "null device pointer");
+  *out = new_batched(ctx, structure_of_canonical(slots, n), n_points, dtype, layout, device_ptr);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_shared_dense(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const double* reim, spn_tensor** out) {
+  API_TRY
+  *out = new_shared_dense(ctx, structure_of_canonical(slots, n), reinterpret_cast<const double2*>(reim));
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_shared_sparse(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const uint64_t* flat, const double* reim,
+                             uint64_t nnz, spn_tensor** out) {
+  API_TRY
+  std::map<uint64_t, double2> ent;
+  for (uint64_t k = 0; k < nnz; ++k) ent[flat[k]] = make_double2(reim[2 * k], reim[2 * k + 1]);
+  *out = new_shared_sparse(ctx, structure_of_canonical(slots, n), ent);
+  return SPN_OK;
+  API_CATCH
+}
+void spn_tensor_free(spn_tensor* t) { delete t; }
+
+uint32_t spn_tensor_order(const spn_tensor* t) { return t->st.order(); }
+int spn_tensor_slots(const spn_tensor* t, spn_slot* out) {
+  for (uint32_t i = 0; i < t->st.order(); ++i) out[i] = t->st.slots[i];
+  return SPN_OK;
+}
+uint64_t spn_tensor_size(const spn_tensor* t) { return t->size(); }
+uint64_t spn_tensor_n_points(const spn_tensor* t) { return t->n_points; }
+int spn_tensor_storage(const spn_tensor* t) { return t->storage; }
+int spn_tensor_dtype(const spn_tensor* t) { return t->dtype; }
+int spn_tensor_layout(const spn_tensor* t) { return t->layout; }
+uint64_t spn_tensor_nnz(const spn_tensor* t) { return t->sparse() ? t->entries.size() : t->size(); }
+void* spn_tensor_device_ptr(const spn_tensor* t) { return t->dptr; }
+
+static void do_upload(spn_tensor* t, const void* host, uint64_t first_point, uint64_t n_points, bool sync) {
+  if (!t->batched()) throw Error(SPN_ERR_INVALID, "upload: shared tensors are immutable");
+  if (first_point + n_points > t->n_points) throw Error(SPN_ERR_INVALID, "upload: point range out of bounds");
+  spn_ctx* ctx = t->ctx;
+  const size_t eb = t->elem_bytes(), sz = t->size();
+  if (t->layout == SPN_POINT_MAJOR) {
+    cuda_check(cudaMemcpyAsync((char*)t->dptr + first_point * sz * eb, host, n_points * sz * eb,
+                               cudaMemcpyHostToDevice, ctx->stream),
+               "upload");
+  } else {
+    void* stage = nullptr;
+    cuda_check(cudaMallocAsync(&stage, n_points * sz * eb + 16, ctx->stream), "upload staging");
+    cuda_check(cudaMemcpyAsync(stage, host, n_points * sz * eb, cudaMemcpyHostToDevice, ctx->stream), "upload");
+    DevOperand src{stage, (long long)sz, 1, t->dtype == SPN_C64};
+    DevOut dst{(char*)t->dptr + first_point * eb, 1, (long long)t->n_points, t->dtype == SPN_C64};
+    cuda_check(launch_elementwise(EW_COPY, src, src, dst, make_double2(0, 0), sz, n_points, true, ctx->stream),
+               "layout transpose");
+    ctx->launches++;
+    cudaFreeAsync(stage, ctx->stream);
+  }
+  if (sync) cuda_check(cudaStreamSynchronize(ctx->stream), "upload");
+}
+
+int spn_tensor_upload(spn_tensor* t, const void* host, uint64_t first_point, uint64_t n_points) {
+  API_TRY
+  do_upload(t, host, first_point, n_points, true);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_upload_async(spn_tensor* t, const void* host, uint64_t first_point, uint64_t n_points) {
+  API_TRY
+  do_upload(t, host, first_point, n_points, false);
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_tensor_download(const spn_tensor* t, void* host, uint64_t first_point, uint64_t n_points) {
+  API_TRY
+  spn_ctx* ctx = t->ctx;
+  const size_t eb = t->elem_bytes(), sz = t->size();
+  if (!t->batched()) {
+    if (first_point != 0 || n_points != 1) throw Error(SPN_ERR_INVALID, "shared tensors have exactly one point");
+    std::memcpy(host, t->host_dense.data(), sz * sizeof(double2));
+    return SPN_OK;
+  }
+  if (first_point + n_points > t->n_points) throw Error(SPN_ERR_INVALID, "download: point range out of bounds");
+  if (t->layout == SPN_POINT_MAJOR) {
+    cuda_check(cudaMemcpyAsync(host, (const char*)t->dptr + first_point * sz * eb, n_points * sz * eb,
+                               cudaMemcpyDeviceToHost, ctx->stream),
+               "download");
+  } else {
+    void* stage = nullptr;
+    cuda_check(cudaMallocAsync(&stage, n_points * sz * eb + 16, ctx->stream), "download staging");
+    DevOperand src{(const char*)t->dptr + first_point * eb, 1, (long long)t->n_points, t->dtype == SPN_C64};
+    DevOut dst{stage, (long long)sz, 1, t->dtype == SPN_C64};
+    cuda_check(launch_elementwise(EW_COPY, src, src, dst, make_double2(0, 0), sz, n_points, false, ctx->stream),
+               "layout transpose");
+    ctx->launches++;
+    cuda_check(cudaMemcpyAsync(host, stage, n_points * sz * eb, cudaMemcpyDeviceToHost, ctx->stream), "download");
+    cudaFreeAsync(stage, ctx->stream);
+  }
+  cuda_check(cudaStreamSynchronize(ctx->stream), "download");
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_tensor_sparse_entries(const spn_tensor* t, uint64_t* flat, double* reim) {
+  API_TRY
+  if (!t->sparse()) throw Error(SPN_ERR_INVALID, "not a sparse tensor");
+  size_t k = 0;
+  for (auto& kv : t->entries) {
+    flat[k] = kv.first;
+    reim[2 * k] = kv.second.x;
+    reim[2 * k + 1] = kv.second.y;
+    ++k;
+  }
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out) {
+  API_TRY
+  tensor_contract(ctx, a, b, out);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_add(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, int subtract, spn_tensor** out) {
+  API_TRY
+  tensor_elementwise(ctx, subtract ? EW_SUB : EW_ADD, a, b, make_double2(0, 0), out);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_neg(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  tensor_elementwise(ctx, EW_NEG, a, a, make_double2(0, 0), out);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_scalar_mul(spn_ctx* ctx, const spn_tensor* a, double re, double im, spn_tensor** out) {
+  API_TRY
+  tensor_elementwise(ctx, EW_SCALE, a, a, make_double2(re, im), out);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_conj(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  tensor_elementwise(ctx, EW_CONJ, a, a, make_double2(0, 0), out);
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_tensor_trace(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  // `slots` is the index list of `a` as the caller sees it, with one repeated (slot, dual) pair:
+  // traces(), structure.rs:462-485.  The data of `a` is row major over `slots`.
+  if (n != a->st.order() && !(n > 0)) throw Error(SPN_ERR_INVALID, "trace: slot count mismatch");
+  int p0 = -1, p1 = -1;
+  for (uint32_t i = 0; i < n && p0 < 0; ++i)
+    for (uint32_t j = i + 1; j < n; ++j)
+      if (slot_same(dual_of(slots[j]), slots[i])) {
+        p0 = (int)i;
+        p1 = (int)j;
+        break;
+      }
+  if (p0 < 0) throw Error(SPN_ERR_STRUCTURE, "trace: no repeated slot");
+  std::vector<uint64_t> strides(n, 1);
+  for (uint32_t i = n; i-- > 1;) strides[i - 1] = strides[i] * slots[i].dim;
+  std::vector<spn_slot> rest;
+  std::vector<uint64_t> rest_strides;
+  for (uint32_t i = 0; i < n; ++i)
+    if ((int)i != p0 && (int)i != p1) {
+      rest.push_back(slots[i]);
+      rest_strides.push_back(strides[i]);
+    }
+  std::vector<int32_t> perm;
+  Structure rs = canonicalize(rest, &perm);
+  DevOutMap map{};
+  map.order = (int)rs.order();
+  if (map.order > kMaxOutOrder) throw Error(SPN_ERR_INVALID, "trace: order too large");
+  for (uint32_t r = 0; r < rs.order(); ++r) {
+    map.dim[r] = rs.slots[r].dim;
+    map.sa[r] = (long long)rest_strides[perm[r]];
+  }
+  map.size_out = rs.size();
+  uint64_t n_points = a->batched() ? a->n_points : 1;
+  std::unique_ptr<spn_tensor> res(new_batched(ctx, rs, n_points, a->dtype, a->layout, nullptr));
+  cuda_check(launch_trace(map, a->operand(), res->output(), (long long)(strides[p0] + strides[p1]), slots[p0].dim,
+                          has_metric(slots[p0]) ? 1 : 0, n_points, a->layout == SPN_COMPONENT_MAJOR, ctx->stream),
+             "trace_kernel");
+  ctx->launches++;
+  if (a->batched()) {
+    *out = res.release();
+    return SPN_OK;
+  }
+  std::vector<double2> host(rs.size());
+  cuda_check(cudaMemcpyAsync(host.data(), res->dptr, host.size() * sizeof(double2), cudaMemcpyDeviceToHost,
+                             ctx->stream),
+             "download shared result");
+  cuda_check(cudaStreamSynchronize(ctx->stream), "download shared result");
+  *out = new_shared_dense(ctx, rs, host.data());
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_tensor_reduce_points(spn_ctx* ctx, const spn_tensor* a, double* out_device) {
+  API_TRY
+  if (a->dtype != SPN_C64) throw Error(SPN_ERR_INVALID, "reduce_points expects a complex tensor");
+  const int n_blocks = ctx->sm_count * 4;
+  double2* partial = nullptr;
+  cuda_check(cudaMallocAsync((void**)&partial, (size_t)n_blocks * a->size() * sizeof(double2) + 16, ctx->stream),
+             "reduce scratch");
+  cuda_check(launch_reduce_points(a->operand(), a->size(), a->n_points, partial, n_blocks,
+                                  reinterpret_cast<double2*>(out_device), ctx->stream),
+             "reduce_points_kernel");
+  ctx->launches += 2;
+  cudaFreeAsync(partial, ctx->stream);
+  return SPN_OK;
+  API_CATCH
+}
+
+}  // extern "C"

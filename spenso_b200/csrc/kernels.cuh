@@ -1,0 +1,68 @@
+// Hand-written sm_100a kernels of the pairwise ("Contract trait") path and launch wrappers.
+// All kernels are HBM-bound streaming kernels over the point batch: no tensor cores (f64
+// complex, tiny contracted dimensions), 128-bit loads/stores of interleaved (re,im),
+// index tables of the shared operand staged in shared memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spn {
+
+// element (point p, flat f) of a device tensor lives at ptr[p*ps + f*fs] (in elements)
+struct DevOperand {
+  const void* ptr;
+  long long ps, fs;
+  int is_complex;
+};
+struct DevOut {
+  void* ptr;
+  long long ps, fs;
+  int is_complex;
+};
+
+constexpr int kMaxOutOrder = 32;
+
+// decomposition of the result index (row major over out_dim) into operand base offsets
+struct DevOutMap {
+  int order;
+  unsigned dim[kMaxOutOrder];
+  long long sa[kMaxOutOrder];
+  long long sb[kMaxOutOrder];
+  unsigned long long size_out;
+};
+
+// K1/K5/K7 (dense x dense, single / multi / exterior, any MergeInfo): contraction/singlecontract.rs:25-76,
+// multicontract.rs:25-78, exteriorproduct.rs.  koff_a/koff_b/ksign: device tables of the
+// contracted loop in the reference's enumeration order (n_k entries).
+cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand b, DevOut out,
+                                  const int* koff_a, const int* koff_b, const unsigned char* ksign,
+                                  unsigned long long n_k, unsigned long long n_points, bool point_fastest,
+                                  cudaStream_t stream);
+
+// K2 (dense(per point) x sparse(shared)): singlecontract.rs:78-196, multicontract.rs:80-200.
+// CSR over result elements: row o holds (offset into the dense operand, value, sign) for every
+// stored entry of the sparse fibre, in ascending fibre position.
+cudaError_t launch_contract_csr(DevOperand dense, DevOut out, const int* row_ptr, const int* col_off,
+                                const double2* val, const unsigned char* sign, int dense_is_first,
+                                unsigned long long size_out, unsigned long long nnz, unsigned long long n_points,
+                                bool point_fastest, cudaStream_t stream);
+
+// element-wise (algebra/add_assign.rs, sub_assign.rs, neg.rs, scalar_mul.rs; FUN_LIB conj)
+enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2, EW_SCALE = 3, EW_CONJ = 4, EW_COPY = 5, EW_RECIP = 6 };
+cudaError_t launch_elementwise(int op, DevOperand a, DevOperand b, DevOut out, double2 scalar,
+                               unsigned long long size, unsigned long long n_points, bool point_fastest,
+                               cudaStream_t stream);
+
+// K8 trace: out[o] = sum_i sign(i) a[base(o) + i*diag_stride]
+cudaError_t launch_trace(const DevOutMap& map, DevOperand a, DevOut out, long long diag_stride, unsigned dim,
+                         int metric, unsigned long long n_points, bool point_fastest, cudaStream_t stream);
+
+// K7 reduction over the point axis: out[c] = sum_p a[p][c] (deterministic two-stage tree)
+cudaError_t launch_reduce_points(DevOperand a, unsigned long long size, unsigned long long n_points,
+                                 double2* partial /* [n_blocks][size] */, int n_blocks, double2* out,
+                                 cudaStream_t stream);
+// second stage alone (used by the fused network kernel's per-block partial sums)
+cudaError_t launch_reduce_partials(const double2* partial, int n_blocks, unsigned long long size, double2* out,
+                                   cudaStream_t stream);
+
+}  // namespace spn

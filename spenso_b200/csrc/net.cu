@@ -1,0 +1,1085 @@
+// Network executor: the B200 replacement for Network::execute
+// (/root/reference/spenso/src/network.rs:1217-1241, 1244-1706) and the Product-op contraction
+// strategy (/root/reference/spenso/src/network/contract.rs:43-498).
+//
+// The reference walks the expression graph, merges structures and picks a pairwise contraction
+// order again for every phase-space point.  All of that is point independent, so here it runs
+// once (spn_net_compile) and produces a linear schedule of pairwise steps.  The schedule is then
+// executed for all points at once in one of two ways:
+//   SPN_EXEC_FUSED     the schedule is replayed symbolically (symbolic.hpp) into ONE straight-line
+//                      sm_100a kernel: thread = point, inputs read once with 128/256-bit loads,
+//                      every intermediate in registers, library constants folded into the code,
+//                      optional Monte-Carlo sum reduced per block.  Algorithmic HBM traffic only.
+//   SPN_EXEC_STEPWISE  one pairwise kernel (kernels.cu) per step with intermediates in HBM —
+//                      the literal device image of the reference's append-only NetworkStore.
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <array>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <set>
+#include <sstream>
+
+#include "library.hpp"
+#include "symbolic.hpp"
+#include "tensor.hpp"
+
+using namespace spn;
+
+namespace {
+
+enum { LEAF_BATCHED = 0, LEAF_CONST = 1, NODE_OP = 2 };
+
+struct Node {
+  int kind = LEAF_CONST;
+  int op = 0;  // SPN_OP_*
+  Structure st;
+  int input = -1;  // LEAF_BATCHED
+  int dtype = SPN_C64;
+  bool sparse = false;  // LEAF_CONST
+  std::vector<double2> dense;
+  std::map<uint64_t, double2> entries;
+  std::vector<int> children;
+  int power = 1;
+  // LEAF_BATCHED: slots as the caller wrote them + canonical permutation (canonical[i] = args[perm[i]])
+  std::vector<spn_slot> args;
+  std::vector<int32_t> perm;
+  // re-indexed view of another batched leaf: canonical flat index here -> canonical flat index of
+  // the bound input tensor (empty = identity)
+  std::vector<uint64_t> flat_map;
+};
+
+enum StepOp { ST_CONTRACT = 0, ST_ADD = 1, ST_NEG = 2, ST_CONJ = 3, ST_RECIP = 4 };
+struct Step {
+  int op, dst, a, b;
+};
+struct Value {
+  Structure st;
+  bool batched = false;
+  int leaf = -1;  // node id for leaf values
+};
+
+// ---- JIT: CUDA source -> cubin (NVRTC, sm_100a) -> cudaKernel_t -------------------------------
+struct JitKernel {
+  std::string source, name;
+  std::vector<char> cubin;
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kernel = nullptr;
+  int blocks_per_sm = 0;
+  int num_regs = 0;
+  ~JitKernel() {
+    if (lib) cudaLibraryUnload(lib);
+  }
+};
+
+uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) {
+    h ^= c;
+    h *= 1099511628211ull;
+  }
+  return h;
+}
+
+std::string cache_dir() {
+  if (const char* e = getenv("SPN_JIT_CACHE")) return e;
+  Dl_info info;
+  if (dladdr((void*)&fnv1a, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t s = p.find_last_of('/');
+    return (s == std::string::npos ? std::string(".") : p.substr(0, s)) + "/_jit_cache";
+  }
+  return "/tmp/spn_jit_cache";
+}
+
+const char* kJitArch = "--gpu-architecture=sm_100a";
+
+void jit_compile(JitKernel& k) {
+  int maj = 0, min = 0;
+  nvrtcVersion(&maj, &min);
+  std::string key = k.source + "|" + kJitArch + "|" + std::to_string(maj) + "." + std::to_string(min);
+  char hex[32];
+  std::snprintf(hex, sizeof hex, "%016llx", (unsigned long long)fnv1a(key));
+  const std::string dir = cache_dir();
+  const std::string path = dir + "/" + hex + ".cubin";
+  const bool use_cache = !getenv("SPN_JIT_NO_CACHE");
+  if (use_cache) {
+    std::ifstream f(path, std::ios::binary);
+    if (f) {
+      k.cubin.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
+      if (!k.cubin.empty()) return;
+    }
+  }
+  nvrtcProgram prog;
+  if (nvrtcCreateProgram(&prog, k.source.c_str(), (k.name + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
+    throw Error(SPN_ERR_JIT, "nvrtcCreateProgram failed");
+  const char* opts[] = {kJitArch, "-lineinfo", "--std=c++17", "--fmad=true", "-default-device"};
+  nvrtcResult r = nvrtcCompileProgram(prog, 5, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    nvrtcGetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    nvrtcGetProgramLog(prog, &log[0]);
+    nvrtcDestroyProgram(&prog);
+    throw Error(SPN_ERR_JIT, "nvrtc: " + log.substr(0, 2000));
+  }
+  size_t n = 0;
+  nvrtcGetCUBINSize(prog, &n);
+  k.cubin.resize(n);
+  nvrtcGetCUBIN(prog, k.cubin.data());
+  nvrtcDestroyProgram(&prog);
+  if (use_cache) {
+    mkdir(dir.c_str(), 0755);
+    std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+    std::ofstream f(tmp, std::ios::binary);
+    if (f) {
+      f.write(k.cubin.data(), (std::streamsize)k.cubin.size());
+      f.close();
+      rename(tmp.c_str(), path.c_str());
+      std::ofstream s(dir + "/" + hex + ".cu");
+      if (s) s << k.source;
+    }
+  }
+}
+
+void jit_load(JitKernel& k, int block) {
+  if (k.kernel) return;
+  cuda_check(cudaLibraryLoadData(&k.lib, k.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0),
+             "cudaLibraryLoadData (fused network kernel)");
+  cuda_check(cudaLibraryGetKernel(&k.kernel, k.lib, k.name.c_str()), "cudaLibraryGetKernel");
+  cudaFuncAttributes attr{};
+  if (cudaFuncGetAttributes(&attr, (const void*)k.kernel) == cudaSuccess) k.num_regs = attr.numRegs;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k.kernel, block, 0) != cudaSuccess || nb <= 0) {
+    cudaGetLastError();
+    nb = k.num_regs > 0 ? std::max(1, 65536 / (k.num_regs * block)) : 4;
+  }
+  k.blocks_per_sm = nb;
+}
+
+}  // namespace
+
+// =================================================================================================
+struct spn_net {
+  spn_ctx* ctx = nullptr;
+  std::vector<Node> nodes;
+  int root = -1;
+  uint32_t n_inputs = 0;
+  std::vector<int> input_nodes;
+  // compiled
+  bool compiled = false;
+  int exec_mode = SPN_EXEC_FUSED;
+  std::vector<Value> values;
+  std::vector<Step> steps;
+  std::vector<std::pair<int, int>> schedule;  // (node a, node b) of every pairwise contraction, -1 = intermediate
+  int result_value = -1;
+  // fused
+  Program prog;
+  std::vector<CE> result_el;
+  Program::Stats stats;
+  struct Variant {
+    std::unique_ptr<JitKernel> k;
+  };
+  std::map<std::string, Variant> variants;
+  std::string default_source;
+  // stepwise
+  std::vector<std::unique_ptr<spn_tensor>> const_tensors;  // per value id (leaf consts), lazily uploaded
+
+  static constexpr int kBlock = 128;
+  static constexpr uint64_t kMaxFusedElems = 1u << 16;
+
+  // ---- graph -> schedule ----------------------------------------------------------------------
+  int new_value(const Structure& st, bool batched, int leaf = -1) {
+    Value v;
+    v.st = st;
+    v.batched = batched;
+    v.leaf = leaf;
+    values.push_back(v);
+    return (int)values.size() - 1;
+  }
+  int emit(int op, int a, int b, Structure st) {  // by value: callers pass values[..].st, which new_value moves
+    bool batched = values[a].batched || (b >= 0 && values[b].batched);
+    int dst = new_value(st, batched);
+    steps.push_back({op, dst, a, b});
+    return dst;
+  }
+  int emit_contract(int a, int b) {
+    spn_contract_plan p = plan_contract(values[a].st, values[b].st);
+    int la = values[a].leaf, lb = values[b].leaf;
+    schedule.emplace_back(la, lb);
+    return emit(ST_CONTRACT, a, b, structure_of_plan_result(p));
+  }
+  static bool same_structure(const Structure& a, const Structure& b) {
+    if (a.order() != b.order()) return false;
+    for (uint32_t i = 0; i < a.order(); ++i)
+      if (!slot_same(a.slots[i], b.slots[i])) return false;
+    return true;
+  }
+  static uint32_t n_shared_indices(const Structure& a, const Structure& b) {
+    uint32_t n = 0;
+    for (auto& s : a.slots) {
+      spn_slot d = dual_of(s);
+      for (auto& t : b.slots)
+        if (slot_same(t, d)) {
+          ++n;
+          break;
+        }
+    }
+    return n;
+  }
+
+  // Product op: pairwise contraction order.  The reference picks the node of smallest degree and
+  // a neighbour (contract.rs:346-497); its order depends on third-party graph iteration order and
+  // values do not depend on it, so we are free to choose: contract the connected pair
+  // with the smallest result (ties: point-independent pairs first — they cost nothing per point —
+  // then fewest multiply-adds); unconnected factors (scalars first) are multiplied in last.
+  int schedule_product(std::vector<int> vals) {
+    if (vals.empty()) throw Error(SPN_ERR_INVALID, "empty product");
+    while (vals.size() > 1) {
+      size_t bi = 0, bj = 1;
+      bool found = false;
+      std::array<double, 3> best{};
+      for (size_t i = 0; i < vals.size(); ++i)
+        for (size_t j = i + 1; j < vals.size(); ++j) {
+          const Structure &A = values[vals[i]].st, &B = values[vals[j]].st;
+          uint32_t nc = n_shared_indices(A, B);
+          if (nc == 0) continue;
+          spn_contract_plan p = plan_contract(A, B);
+          bool free_pair = !values[vals[i]].batched && !values[vals[j]].batched;
+          std::array<double, 3> cost{(double)p.size_out, free_pair ? 0.0 : 1.0,
+                                     (double)p.size_out * (double)p.n_contracted};
+          if (!found || cost < best) {
+            best = cost;
+            bi = i;
+            bj = j;
+            found = true;
+          }
+        }
+      if (!found) {
+        // outer product of the two smallest factors
+        std::vector<size_t> idx(vals.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) {
+          return values[vals[x]].st.size() < values[vals[y]].st.size();
+        });
+        bi = std::min(idx[0], idx[1]);
+        bj = std::max(idx[0], idx[1]);
+      }
+      int r = emit_contract(vals[bi], vals[bj]);
+      vals[bi] = r;
+      vals.erase(vals.begin() + (long)bj);
+    }
+    return vals[0];
+  }
+
+  void flatten(int id, int op, std::vector<int>& out) {  // merge_ops, graph.rs:1002-1065
+    for (int c : nodes[id].children) {
+      if (nodes[c].kind == NODE_OP && nodes[c].op == op)
+        flatten(c, op, out);
+      else
+        out.push_back(c);
+    }
+  }
+
+  int build(int id, std::map<int, int>& memo) {
+    auto it = memo.find(id);
+    if (it != memo.end()) return it->second;
+    int v = -1;
+    if (nodes[(size_t)id].kind != NODE_OP) {
+      v = new_value(nodes[(size_t)id].st, nodes[(size_t)id].kind == LEAF_BATCHED, id);
+    } else {
+      // copy what we need: recursion may append nodes and move the vector
+      struct {
+        int op, power;
+        std::vector<int> children;
+      } n{nodes[(size_t)id].op, nodes[(size_t)id].power, nodes[(size_t)id].children};
+      switch (n.op) {
+        case SPN_OP_PRODUCT: {
+          std::vector<int> kids, vals;
+          flatten(id, SPN_OP_PRODUCT, kids);
+          if (kids.empty()) throw Error(SPN_ERR_INVALID, "empty product");
+          for (int c : kids) vals.push_back(build(c, memo));
+          v = schedule_product(vals);
+          break;
+        }
+        case SPN_OP_SUM: {  // network.rs:1342-1467
+          std::vector<int> kids;
+          flatten(id, SPN_OP_SUM, kids);
+          if (kids.empty()) throw Error(SPN_ERR_INVALID, "empty sum");
+          v = build(kids[0], memo);
+          for (size_t k = 1; k < kids.size(); ++k) {
+            int w = build(kids[k], memo);
+            if (!same_structure(values[v].st, values[w].st))
+              throw Error(SPN_ERR_STRUCTURE, values[v].st.order() == 0 || values[w].st.order() == 0
+                                                 ? "sum of a scalar and a tensor"
+                                                 : "sum of tensors of different structure");
+            v = emit(ST_ADD, v, w, values[v].st);
+          }
+          break;
+        }
+        case SPN_OP_NEG:
+          if (n.children.size() != 1) throw Error(SPN_ERR_INVALID, "neg takes one child");
+          v = build(n.children[0], memo);
+          v = emit(ST_NEG, v, -1, values[v].st);
+          break;
+        case SPN_OP_CONJ:  // FUN_LIB conj, spenso-hep-lib/src/lib.rs:511-520
+          if (n.children.size() != 1) throw Error(SPN_ERR_INVALID, "conj takes one child");
+          v = build(n.children[0], memo);
+          v = emit(ST_CONJ, v, -1, values[v].st);
+          break;
+        case SPN_OP_POWER: {  // network.rs:1526-1703
+          if (n.children.size() != 1) throw Error(SPN_ERR_INVALID, "power takes one child");
+          int c = build(n.children[0], memo);
+          const int pw = n.power, np = pw < 0 ? -pw : pw;
+          const bool is_scalar = values[c].st.order() == 0;
+          if (is_scalar) {
+            if (np == 0) {
+              v = c;  // the reference returns the scalar itself for a zero exponent
+              break;
+            }
+            v = c;
+            for (int k = 1; k < np; ++k) v = emit_contract(v, c);
+            if (pw < 0) v = emit(ST_RECIP, v, -1, values[v].st);
+            break;
+          }
+          if (pw == 0) {
+            v = const_scalar_value(make_double2(1.0, 0.0));
+            break;
+          }
+          if (pw == 1) {
+            v = c;
+            break;
+          }
+          int square = emit_contract(c, c);
+          if (np % 2 == 1) {
+            for (int k = 0; k < np / 2; ++k) square = emit_contract(square, square);
+            v = emit_contract(square, c);
+            if (pw < 0) {
+              if (values[v].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "negative exponent on a non-scalar");
+              v = emit(ST_RECIP, v, -1, values[v].st);
+            }
+          } else {
+            if (values[square].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "even power of a tensor is not a scalar");
+            v = square;
+            for (int k = 1; k < np / 2; ++k) v = emit_contract(v, square);
+            if (pw < 0) v = emit(ST_RECIP, v, -1, values[v].st);
+          }
+          break;
+        }
+        default: throw Error(SPN_ERR_INVALID, "unknown op");
+      }
+    }
+    memo[id] = v;
+    return v;
+  }
+  int const_scalar_value(double2 s) {
+    Node n;
+    n.kind = LEAF_CONST;
+    n.dense = {s};
+    nodes.push_back(n);
+    return new_value(Structure(), false, (int)nodes.size() - 1);
+  }
+
+  // ---- fused: replay the schedule symbolically ---------------------------------------------------
+  std::vector<CE> sym_leaf(const Value& v) {
+    const Node& n = nodes[v.leaf];
+    const uint64_t sz = n.st.size();
+    if (sz > kMaxFusedElems) throw Error(SPN_ERR_INVALID, "tensor too large for the fused executor; use SPN_EXEC_STEPWISE");
+    std::vector<CE> el(sz);
+    if (n.kind == LEAF_CONST) {
+      for (uint64_t f = 0; f < sz; ++f) el[f] = CE{rr_const(n.dense[f].x), rr_const(n.dense[f].y)};
+    } else {
+      // loads are created lazily at the first use (el holds placeholders resolved in sym_get)
+      for (uint64_t f = 0; f < sz; ++f) el[f] = CE{RR{-2, 1.0}, RR{-2, 1.0}};
+    }
+    return el;
+  }
+  struct SymT {
+    std::vector<CE> el;
+    int input = -1;  // >= 0: unresolved components are loads of this input
+    bool cplx = true;
+    const std::vector<uint64_t>* flat_map = nullptr;
+  };
+  CE sym_get(SymT& t, uint64_t f) {
+    CE& e = t.el[f];
+    if (e.re.var == -2) e = prog.load(t.input, t.flat_map && !t.flat_map->empty() ? (*t.flat_map)[f] : f, t.cplx);
+    return e;
+  }
+
+  void compile_fused() {
+    std::vector<SymT> sym(values.size());
+    for (size_t v = 0; v < values.size(); ++v) {
+      if (values[v].leaf < 0) continue;
+      const Node& n = nodes[values[v].leaf];
+      sym[v].el = sym_leaf(values[v]);
+      if (n.kind == LEAF_BATCHED) {
+        sym[v].input = n.input;
+        sym[v].cplx = n.dtype == SPN_C64;
+        sym[v].flat_map = &n.flat_map;
+      }
+    }
+    for (const Step& s : steps) {
+      SymT out;
+      const uint64_t sz = values[s.dst].st.size();
+      if (sz > kMaxFusedElems) throw Error(SPN_ERR_INVALID, "intermediate too large for the fused executor; use SPN_EXEC_STEPWISE");
+      out.el.resize(sz);
+      SymT& A = sym[s.a];
+      switch (s.op) {
+        case ST_CONTRACT: {
+          SymT& B = sym[s.b];
+          spn_contract_plan p = plan_contract(values[s.a].st, values[s.b].st);
+          KTables kt = build_k_tables(p);
+          std::vector<uint32_t> idx(p.order_out, 0);
+          std::vector<Term> tr, ti;
+          for (uint64_t o = 0; o < p.size_out; ++o) {
+            uint64_t offa = 0, offb = 0;
+            for (uint32_t r = 0; r < p.order_out; ++r) {
+              offa += (uint64_t)idx[r] * p.out_stride_a[r];
+              offb += (uint64_t)idx[r] * p.out_stride_b[r];
+            }
+            tr.clear();
+            ti.clear();
+            for (size_t k = 0; k < kt.off_a.size(); ++k) {
+              // peek: skip structurally zero constants without touching (= loading) the partner
+              const uint64_t fa = offa + (uint64_t)kt.off_a[k], fb = offb + (uint64_t)kt.off_b[k];
+              const CE& pa = A.el[fa];
+              const CE& pb = B.el[fb];
+              if ((pa.re.is_zero() && pa.im.is_zero()) || (pb.re.is_zero() && pb.im.is_zero())) continue;
+              CE a = sym_get(A, fa), b = sym_get(B, fb);
+              Program::push_cmul(tr, ti, a, b, kt.sign[k] ? -1.0 : 1.0);
+            }
+            out.el[o] = CE{prog.sum(tr), prog.sum(ti)};
+            for (uint32_t r = p.order_out; r-- > 0;) {
+              if (++idx[r] < p.out_dim[r]) break;
+              idx[r] = 0;
+            }
+          }
+          break;
+        }
+        case ST_ADD: {
+          SymT& B = sym[s.b];
+          for (uint64_t f = 0; f < sz; ++f) {
+            CE a = sym_get(A, f), b = sym_get(B, f);
+            std::vector<Term> tr, ti;
+            Program::push_rr(tr, a.re, 1.0);
+            Program::push_rr(tr, b.re, 1.0);
+            Program::push_rr(ti, a.im, 1.0);
+            Program::push_rr(ti, b.im, 1.0);
+            out.el[f] = CE{prog.sum(tr), prog.sum(ti)};
+          }
+          break;
+        }
+        case ST_NEG:
+          for (uint64_t f = 0; f < sz; ++f) {
+            CE a = sym_get(A, f);
+            out.el[f] = CE{rr_neg(a.re), rr_neg(a.im)};
+          }
+          break;
+        case ST_CONJ:
+          for (uint64_t f = 0; f < sz; ++f) {
+            CE a = sym_get(A, f);
+            out.el[f] = CE{a.re, rr_neg(a.im)};
+          }
+          break;
+        case ST_RECIP:
+          for (uint64_t f = 0; f < sz; ++f) out.el[f] = prog.reciprocal(sym_get(A, f));
+          break;
+      }
+      sym[s.dst] = std::move(out);
+    }
+    SymT& R = sym[result_value];
+    result_el.resize(R.el.size());
+    std::vector<int> roots;
+    for (uint64_t f = 0; f < R.el.size(); ++f) {
+      result_el[f] = sym_get(R, f);
+      roots.push_back(result_el[f].re.var);
+      roots.push_back(result_el[f].im.var);
+    }
+    stats = prog.eliminate_dead(roots);
+  }
+
+  // ---- fused: print the kernel -------------------------------------------------------------------
+  // variant key: per input 'p' (point major, 32-byte aligned: 256-bit loads allowed) / 'q' (point
+  // major, 16-byte aligned only) / 'c' (component major); then out: 'n' none, 'p', 'c'
+  // (+ 'r' = real output); then 's' when the sum over points is wanted
+  std::string gen_source(const std::string& variant, const std::string& kname) const {
+    const uint64_t size_out = result_el.size();
+    const char out_mode = variant[n_inputs];
+    const bool out_real = variant.find('r', n_inputs) != std::string::npos;
+    const bool want_sum = variant.back() == 's';
+    std::ostringstream o;
+    o << "// generated by spenso_b200 (net.cu): fused per-point network kernel, sm_100a\n";
+    o << "// inputs: " << n_inputs << ", result components: " << size_out << ", fp64 instr/point: " << stats.n_fp
+      << ", input bytes/point: " << stats.n_load_bytes << "\n";
+    o << "typedef unsigned long long ull;\n";
+    o << "__device__ __forceinline__ double2 ld16(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }\n";
+    o << "__device__ __forceinline__ double ld8(const double* p) { return __ldg(p); }\n";
+    o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
+         "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << kBlock << ") " << kname << "(";
+    for (uint32_t k = 0; k < n_inputs; ++k) o << "const double* __restrict__ in" << k << ", ull cs" << k << ", ";
+    o << "double* __restrict__ out, ull ocs, double2* __restrict__ block_sums, ull n_points) {\n";
+    if (want_sum)
+      for (uint64_t c = 0; c < size_out; ++c) o << "  double sr" << c << " = 0.0, si" << c << " = 0.0;\n";
+    o << "  for (ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << kBlock
+      << ") {\n";
+    // value names
+    std::vector<std::string> name((size_t)prog.n_vals);
+    auto vname = [&](int v) -> const std::string& { return name[(size_t)v]; };
+    auto signedv = [&](int v, int s) { return (s < 0 ? "-" : "") + vname(v); };
+    auto scaled = [&](double k, int v) {
+      if (k == 1.0) return vname(v);
+      if (k == -1.0) return "-" + vname(v);
+      return "(" + lit(k) + " * " + vname(v) + ")";
+    };
+    // 256-bit loads: pair (flat, flat+1) of a point-major complex input when flat is even, the
+    // tensor has an even number of components (=> 32-byte aligned) and both are live
+    std::set<std::pair<int, uint64_t>> live_loads;
+    for (auto& i : prog.ins)
+      if (i.op == I_LOADC) live_loads.insert({i.in, i.flat});
+    std::set<std::pair<int, uint64_t>> done_pair;
+    for (const Ins& i : prog.ins) {
+      switch (i.op) {
+        case I_LOADC: {
+          const Node& n = nodes[input_nodes[(size_t)i.in]];
+          const uint64_t sz = n.st.size();
+          std::string ln = "l" + std::to_string(i.dst);
+          name[(size_t)i.dst] = ln + ".x";
+          name[(size_t)i.dst + 1] = ln + ".y";
+          if (variant[(size_t)i.in] == 'p' || variant[(size_t)i.in] == 'q') {
+            const bool pairable = sz % 2 == 0 && variant[(size_t)i.in] == 'p';
+            const uint64_t base = i.flat & ~1ull;
+            if (pairable && live_loads.count({i.in, base}) && live_loads.count({i.in, base + 1})) {
+              if (!done_pair.count({i.in, base})) {
+                done_pair.insert({i.in, base});
+                // declare both halves now; the partner instruction only defines its names
+                int partner_dst = -1;
+                for (const Ins& j : prog.ins)
+                  if (j.op == I_LOADC && j.in == i.in && j.flat == (i.flat ^ 1ull)) partner_dst = j.dst;
+                std::string a = "l" + std::to_string(i.flat == base ? i.dst : partner_dst);
+                std::string b = "l" + std::to_string(i.flat == base ? partner_dst : i.dst);
+                o << "    double2 " << a << ", " << b << "; ld32(in" << i.in << " + (p * " << sz << "ull + " << base
+                  << "ull) * 2, " << a << ", " << b << ");\n";
+              }
+            } else {
+              o << "    const double2 " << ln << " = ld16(in" << i.in << " + (p * " << sz << "ull + " << i.flat
+                << "ull) * 2);\n";
+            }
+          } else {
+            o << "    const double2 " << ln << " = ld16(in" << i.in << " + (" << i.flat << "ull * cs" << i.in
+              << " + p) * 2);\n";
+          }
+          break;
+        }
+        case I_LOADR: {
+          const Node& n = nodes[input_nodes[(size_t)i.in]];
+          name[(size_t)i.dst] = "l" + std::to_string(i.dst);
+          if (variant[(size_t)i.in] != 'c')
+            o << "    const double l" << i.dst << " = ld8(in" << i.in << " + p * " << n.st.size() << "ull + " << i.flat
+              << "ull);\n";
+          else
+            o << "    const double l" << i.dst << " = ld8(in" << i.in << " + " << i.flat << "ull * cs" << i.in
+              << " + p);\n";
+          break;
+        }
+        case I_MUL:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          o << "    const double v" << i.dst << " = " << scaled(i.k, i.x) << " * " << vname(i.y) << ";\n";
+          break;
+        case I_FMA:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          o << "    const double v" << i.dst << " = fma(" << scaled(i.k, i.x) << ", " << vname(i.y) << ", "
+            << signedv(i.z, i.sz) << ");\n";
+          break;
+        case I_MULK:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          o << "    const double v" << i.dst << " = " << lit(i.k) << " * " << vname(i.x) << ";\n";
+          break;
+        case I_FMAK:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          if (i.k == 1.0)
+            o << "    const double v" << i.dst << " = " << signedv(i.z, i.sz) << " + " << vname(i.x) << ";\n";
+          else if (i.k == -1.0)
+            o << "    const double v" << i.dst << " = " << signedv(i.z, i.sz) << " - " << vname(i.x) << ";\n";
+          else
+            o << "    const double v" << i.dst << " = fma(" << lit(i.k) << ", " << vname(i.x) << ", "
+              << signedv(i.z, i.sz) << ");\n";
+          break;
+        case I_ADDK:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          o << "    const double v" << i.dst << " = " << signedv(i.z, i.sz) << " + " << lit(i.kc) << ";\n";
+          break;
+        case I_DIV:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          if (i.x < 0)
+            o << "    const double v" << i.dst << " = " << lit(i.k) << " / " << vname(i.y) << ";\n";
+          else
+            o << "    const double v" << i.dst << " = " << scaled(i.k, i.x) << " / " << vname(i.y) << ";\n";
+          break;
+      }
+    }
+    auto rr_expr = [&](const RR& r) -> std::string {
+      if (r.is_const()) return lit(r.coef);
+      return scaled(r.coef, r.var);
+    };
+    for (uint64_t c = 0; c < size_out; ++c) {
+      const std::string re = rr_expr(result_el[c].re), im = rr_expr(result_el[c].im);
+      if (want_sum) o << "    sr" << c << " += " << re << "; si" << c << " += " << im << ";\n";
+      if (out_mode == 'n') continue;
+      std::string idx = out_mode == 'p' ? "(p * " + std::to_string(size_out) + "ull + " + std::to_string(c) + "ull)"
+                                        : "(" + std::to_string(c) + "ull * ocs + p)";
+      if (out_real)
+        o << "    out[" << idx << "] = " << re << ";\n";
+      else
+        o << "    reinterpret_cast<double2*>(out)[" << idx << "] = make_double2(" << re << ", " << im << ");\n";
+    }
+    o << "  }\n";
+    if (want_sum) {
+      // per-block partial of the Monte-Carlo sum: fixed shuffle tree + fixed order over warps
+      o << "  __shared__ double2 ws[" << (kBlock / 32) << "];\n";
+      for (uint64_t c = 0; c < size_out; ++c) {
+        o << "  {\n    double a = sr" << c << ", b = si" << c << ";\n";
+        o << "    for (int off = 16; off > 0; off >>= 1) { a += __shfl_down_sync(0xffffffffu, a, off); b += "
+             "__shfl_down_sync(0xffffffffu, b, off); }\n";
+        o << "    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = make_double2(a, b);\n    __syncthreads();\n";
+        o << "    if (threadIdx.x == 0) {\n      double2 t = ws[0];\n      for (int w = 1; w < " << (kBlock / 32)
+          << "; ++w) { t.x += ws[w].x; t.y += ws[w].y; }\n      block_sums[(ull)blockIdx.x * " << size_out << "ull + " << c
+          << "ull] = t;\n    }\n    __syncthreads();\n  }\n";
+      }
+    }
+    o << "}\n";
+    return o.str();
+  }
+
+  JitKernel& get_variant(const std::string& variant) {
+    auto it = variants.find(variant);
+    if (it != variants.end()) return *it->second.k;
+    auto k = std::make_unique<JitKernel>();
+    // the kernel name carries a hash of the body so ncu listings identify the network
+    std::string probe = gen_source(variant, "K");
+    char nm[64];
+    std::snprintf(nm, sizeof nm, "spn_fused_net_%08x_%s", (unsigned)(fnv1a(probe) & 0xffffffffu), variant.c_str());
+    k->name = nm;
+    k->source = gen_source(variant, k->name);
+    jit_compile(*k);
+    JitKernel& ref = *k;
+    variants[variant].k = std::move(k);
+    return ref;
+  }
+  std::string default_variant(bool sum) const {
+    std::string v(n_inputs, 'p');
+    v += 'p';
+    if (sum) v += 's';
+    return v;
+  }
+};
+
+// =================================================================================================
+namespace {
+
+#define NET_TRY try {
+#define NET_CATCH(neg)                                 \
+  }                                                    \
+  catch (const Error& e) {                             \
+    spn::set_error(e.what());                          \
+    return (neg) ? -e.code : e.code;                   \
+  }                                                    \
+  catch (const std::exception& e) {                    \
+    spn::set_error(e.what());                          \
+    return (neg) ? -SPN_ERR_OTHER : SPN_ERR_OTHER;     \
+  }
+
+int add_const_leaf(spn_net* net, const Structure& st, const std::map<uint64_t, double2>& entries, bool sparse,
+                   const std::vector<double2>* dense) {
+  Node n;
+  n.kind = LEAF_CONST;
+  n.st = st;
+  n.sparse = sparse;
+  if (dense) {
+    n.dense = *dense;
+  } else {
+    n.dense.assign(st.size(), make_double2(0.0, 0.0));
+    for (auto& kv : entries) {
+      if (kv.first >= st.size()) throw Error(SPN_ERR_INVALID, "sparse flat index out of bounds");
+      n.dense[kv.first] = kv.second;
+    }
+  }
+  n.entries = entries;
+  net->nodes.push_back(std::move(n));
+  return (int)net->nodes.size() - 1;
+}
+
+void check_uncompiled(spn_net* net) {
+  if (net->compiled) throw Error(SPN_ERR_INVALID, "network is already compiled");
+}
+
+bool v_is_alias(const spn_net* net, const Node& n) {
+  return &n != &net->nodes[(size_t)net->input_nodes[(size_t)n.input]];
+}
+
+// stepwise execution: one pairwise kernel per step, intermediates in HBM
+void run_stepwise(spn_net* net, const spn_tensor* const* inputs, spn_tensor* out, double* sum_out) {
+  spn_ctx* ctx = net->ctx;
+  std::vector<const spn_tensor*> val(net->values.size(), nullptr);
+  std::vector<std::unique_ptr<spn_tensor>> owned(net->values.size());
+  // last use of every value, to free intermediates as early as the reference's store never does
+  std::vector<int> last_use(net->values.size(), -1);
+  for (size_t s = 0; s < net->steps.size(); ++s) {
+    last_use[(size_t)net->steps[s].a] = (int)s;
+    if (net->steps[s].b >= 0) last_use[(size_t)net->steps[s].b] = (int)s;
+  }
+  for (size_t v = 0; v < net->values.size(); ++v) {
+    const Value& V = net->values[v];
+    if (V.leaf < 0) continue;
+    const Node& n = net->nodes[(size_t)V.leaf];
+    if (n.kind == LEAF_BATCHED) {
+      if (v_is_alias(net, n)) {
+        if (!n.flat_map.empty())
+          throw Error(SPN_ERR_INVALID, "stepwise execution: re-indexed leaf with a different canonical order");
+        const spn_tensor* t = inputs[n.input];
+        owned[v].reset(new_batched(ctx, n.st, t->n_points, t->dtype, t->layout, t->dptr));
+        val[v] = owned[v].get();
+      } else {
+        val[v] = inputs[n.input];
+      }
+    } else {
+      if (!net->const_tensors[v])
+        net->const_tensors[v].reset(n.sparse ? new_shared_sparse(ctx, n.st, n.entries)
+                                             : new_shared_dense(ctx, n.st, n.dense.data()));
+      val[v] = net->const_tensors[v].get();
+    }
+  }
+  for (size_t s = 0; s < net->steps.size(); ++s) {
+    const Step& st = net->steps[s];
+    spn_tensor* r = nullptr;
+    switch (st.op) {
+      case ST_CONTRACT: tensor_contract(ctx, val[(size_t)st.a], val[(size_t)st.b], &r); break;
+      case ST_ADD: tensor_elementwise(ctx, EW_ADD, val[(size_t)st.a], val[(size_t)st.b], make_double2(0, 0), &r); break;
+      case ST_NEG: tensor_elementwise(ctx, EW_NEG, val[(size_t)st.a], val[(size_t)st.a], make_double2(0, 0), &r); break;
+      case ST_CONJ: tensor_elementwise(ctx, EW_CONJ, val[(size_t)st.a], val[(size_t)st.a], make_double2(0, 0), &r); break;
+      case ST_RECIP: tensor_elementwise(ctx, EW_RECIP, val[(size_t)st.a], val[(size_t)st.a], make_double2(0, 0), &r); break;
+    }
+    owned[(size_t)st.dst].reset(r);
+    val[(size_t)st.dst] = r;
+    for (int u : {st.a, st.b})
+      if (u >= 0 && last_use[(size_t)u] == (int)s && u != net->result_value) owned[(size_t)u].reset();
+  }
+  const spn_tensor* res = val[(size_t)net->result_value];
+  uint64_t n_points = out ? out->n_points : (res->batched() ? res->n_points : 1);
+  if (out) {
+    if (out->size() != res->size()) throw Error(SPN_ERR_STRUCTURE, "output tensor has the wrong size");
+    // copy (broadcasting a point-independent result over the points)
+    DevOperand src = res->operand();
+    cuda_check(launch_elementwise(EW_COPY, src, src, out->output(), make_double2(0, 0), res->size(), n_points,
+                                  out->layout == SPN_COMPONENT_MAJOR, ctx->stream),
+               "copy result");
+    ctx->launches++;
+  }
+  if (sum_out) {
+    if (!res->batched()) throw Error(SPN_ERR_INVALID, "sum over points of a point-independent result");
+    const int n_blocks = ctx->sm_count * 4;
+    double2* partial = nullptr;
+    cuda_check(cudaMallocAsync((void**)&partial, (size_t)n_blocks * res->size() * sizeof(double2) + 16, ctx->stream),
+               "reduce scratch");
+    cuda_check(launch_reduce_points(res->operand(), res->size(), res->n_points, partial, n_blocks,
+                                    reinterpret_cast<double2*>(sum_out), ctx->stream),
+               "reduce_points_kernel");
+    ctx->launches += 2;
+    cudaFreeAsync(partial, ctx->stream);
+  }
+  // intermediates are freed when `owned` goes out of scope; the stream is ordered, cudaFree syncs
+}
+
+}  // namespace
+
+extern "C" {
+
+int spn_net_create(spn_ctx* ctx, spn_net** out) {
+  NET_TRY
+  auto n = std::make_unique<spn_net>();
+  n->ctx = ctx;  // may be NULL: plan-only network (compile + inspect, no execution)
+  *out = n.release();
+  return SPN_OK;
+  NET_CATCH(false)
+}
+void spn_net_destroy(spn_net* net) { delete net; }
+
+int spn_net_leaf_batched(spn_net* net, const spn_slot* slots, uint32_t n, int dtype) {
+  NET_TRY
+  check_uncompiled(net);
+  Node nd;
+  nd.kind = LEAF_BATCHED;
+  nd.args.assign(slots, slots + n);
+  nd.st = canonicalize(nd.args, &nd.perm);
+  nd.input = (int)net->n_inputs++;
+  nd.dtype = dtype;
+  net->nodes.push_back(std::move(nd));
+  net->input_nodes.push_back((int)net->nodes.size() - 1);
+  return (int)net->nodes.size() - 1;
+  NET_CATCH(true)
+}
+int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t n) {
+  NET_TRY
+  check_uncompiled(net);
+  if (leaf < 0 || leaf >= (int)net->nodes.size() || net->nodes[(size_t)leaf].kind != LEAF_BATCHED)
+    throw Error(SPN_ERR_INVALID, "reindex: not a batched leaf");
+  const Node src = net->nodes[(size_t)leaf];
+  if (n != src.args.size()) throw Error(SPN_ERR_STRUCTURE, "reindex: wrong number of slots");
+  for (uint32_t i = 0; i < n; ++i)
+    if (slots[i].rep_kind != src.args[i].rep_kind || slots[i].rep_id != src.args[i].rep_id ||
+        slots[i].dim != src.args[i].dim)
+      throw Error(SPN_ERR_STRUCTURE, "reindex: representation or dimension differs from the original leaf");
+  Node nd;
+  nd.kind = LEAF_BATCHED;
+  nd.args.assign(slots, slots + n);
+  nd.st = canonicalize(nd.args, &nd.perm);
+  nd.input = src.input;
+  nd.dtype = src.dtype;
+  // canonical index tuple here -> argument order -> canonical tuple of the bound tensor
+  const uint64_t size = nd.st.size();
+  auto src_strides = src.st.strides();
+  std::vector<uint64_t> stride_of_arg(n, 0);  // stride in the bound tensor of argument position a
+  for (uint32_t c = 0; c < n; ++c) stride_of_arg[(size_t)src.perm[c]] = src_strides[c];
+  nd.flat_map.resize(size);
+  std::vector<uint32_t> idx(n, 0);
+  bool identity = src.flat_map.empty();
+  for (uint64_t f = 0; f < size; ++f) {
+    uint64_t g = 0;
+    for (uint32_t c = 0; c < n; ++c) g += (uint64_t)idx[c] * stride_of_arg[(size_t)nd.perm[c]];
+    if (!src.flat_map.empty()) g = src.flat_map[g];
+    nd.flat_map[f] = g;
+    identity = identity && g == f;
+    for (uint32_t c = n; c-- > 0;) {
+      if (++idx[c] < nd.st.slots[c].dim) break;
+      idx[c] = 0;
+    }
+  }
+  if (identity) nd.flat_map.clear();
+  net->nodes.push_back(std::move(nd));
+  return (int)net->nodes.size() - 1;
+  NET_CATCH(true)
+}
+int spn_net_leaf_shared(spn_net* net, const spn_tensor* shared) {
+  NET_TRY
+  check_uncompiled(net);
+  if (shared->batched()) throw Error(SPN_ERR_INVALID, "leaf_shared needs a shared tensor");
+  return add_const_leaf(net, shared->st, shared->entries, shared->sparse(), &shared->host_dense);
+  NET_CATCH(true)
+}
+int spn_net_leaf_library(spn_net* net, int which, const spn_slot* slots, uint32_t n) {
+  NET_TRY
+  check_uncompiled(net);
+  std::vector<spn_slot> args(slots, slots + n);
+  LibraryData d = builtin_library(which, args);
+  Structure st;
+  auto ent = instantiate_library(d, args, &st);
+  return add_const_leaf(net, st, ent, true, nullptr);
+  NET_CATCH(true)
+}
+int spn_net_leaf_library_custom(spn_net* net, const spn_slot* slots, uint32_t n, const uint64_t* flat,
+                                const double* reim, uint64_t nnz) {
+  NET_TRY
+  check_uncompiled(net);
+  std::vector<spn_slot> args(slots, slots + n);
+  LibraryData d;
+  uint64_t size = 1;
+  for (auto& s : args) size *= s.dim;
+  for (uint64_t k = 0; k < nnz; ++k) {
+    if (flat[k] >= size) throw Error(SPN_ERR_INVALID, "library entry out of bounds");
+    d.nz.push_back({flat[k], make_double2(reim[2 * k], reim[2 * k + 1])});
+  }
+  Structure st;
+  auto ent = instantiate_library(d, args, &st);
+  return add_const_leaf(net, st, ent, true, nullptr);
+  NET_CATCH(true)
+}
+int spn_net_leaf_scalar(spn_net* net, double re, double im) {
+  NET_TRY
+  check_uncompiled(net);
+  std::vector<double2> d{make_double2(re, im)};
+  return add_const_leaf(net, Structure(), {}, false, &d);
+  NET_CATCH(true)
+}
+int spn_net_op(spn_net* net, int op, const int32_t* children, uint32_t n_children, int32_t power) {
+  NET_TRY
+  check_uncompiled(net);
+  if (op < SPN_OP_PRODUCT || op > SPN_OP_CONJ) throw Error(SPN_ERR_INVALID, "unknown op");
+  Node nd;
+  nd.kind = NODE_OP;
+  nd.op = op;
+  nd.power = power;
+  for (uint32_t k = 0; k < n_children; ++k) {
+    if (children[k] < 0 || children[k] >= (int)net->nodes.size()) throw Error(SPN_ERR_INVALID, "child id out of range");
+    nd.children.push_back(children[k]);
+  }
+  net->nodes.push_back(std::move(nd));
+  return (int)net->nodes.size() - 1;
+  NET_CATCH(true)
+}
+int spn_net_set_root(spn_net* net, int node) {
+  NET_TRY
+  check_uncompiled(net);
+  if (node < 0 || node >= (int)net->nodes.size()) throw Error(SPN_ERR_INVALID, "root id out of range");
+  net->root = node;
+  return SPN_OK;
+  NET_CATCH(false)
+}
+
+int spn_net_compile(spn_net* net, int exec_mode) {
+  NET_TRY
+  check_uncompiled(net);
+  if (net->root < 0) throw Error(SPN_ERR_INVALID, "network has no root");
+  if (exec_mode != SPN_EXEC_FUSED && exec_mode != SPN_EXEC_STEPWISE) throw Error(SPN_ERR_INVALID, "unknown exec mode");
+  net->exec_mode = exec_mode;
+  std::map<int, int> memo;
+  net->result_value = net->build(net->root, memo);
+  net->const_tensors.resize(net->values.size());
+  if (exec_mode == SPN_EXEC_FUSED) {
+    net->compile_fused();
+    JitKernel& k = net->get_variant(net->default_variant(false));
+    net->default_source = k.source;
+  }
+  net->compiled = true;
+  return SPN_OK;
+  NET_CATCH(false)
+}
+
+uint32_t spn_net_result_order(const spn_net* net) {
+  return net->compiled ? net->values[(size_t)net->result_value].st.order() : 0;
+}
+int spn_net_result_slots(const spn_net* net, spn_slot* out) {
+  if (!net->compiled) return SPN_ERR_INVALID;
+  const Structure& st = net->values[(size_t)net->result_value].st;
+  for (uint32_t i = 0; i < st.order(); ++i) out[i] = st.slots[i];
+  return SPN_OK;
+}
+uint64_t spn_net_result_size(const spn_net* net) {
+  return net->compiled ? net->values[(size_t)net->result_value].st.size() : 0;
+}
+uint32_t spn_net_n_inputs(const spn_net* net) { return net->n_inputs; }
+int spn_net_schedule(const spn_net* net, int32_t* pairs, uint32_t cap) {
+  uint32_t c = 0;
+  for (auto& p : net->schedule) {
+    if (c < cap) {
+      pairs[2 * c] = p.first;
+      pairs[2 * c + 1] = p.second;
+    }
+    ++c;
+  }
+  return (int)c;
+}
+const char* spn_net_cuda_source(const spn_net* net) { return net->default_source.c_str(); }
+uint64_t spn_net_macs_per_point(const spn_net* net) { return net->stats.n_fp; }
+uint64_t spn_net_input_bytes_per_point(const spn_net* net) { return net->stats.n_load_bytes; }
+
+int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_inputs, spn_tensor* out,
+                    double* sum_out_device, uint64_t first_point, uint64_t n_points) {
+  NET_TRY
+  if (!net->compiled) throw Error(SPN_ERR_INVALID, "network is not compiled");
+  if (!net->ctx) throw Error(SPN_ERR_NO_DEVICE, "plan-only network (created without a context) cannot execute");
+  if (n_inputs != net->n_inputs) throw Error(SPN_ERR_INVALID, "wrong number of input tensors");
+  spn_ctx* ctx = net->ctx;
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < n_inputs; ++k) {
+    const spn_tensor* t = inputs[k];
+    const Node& n = net->nodes[(size_t)net->input_nodes[k]];
+    if (!t || !t->batched()) throw Error(SPN_ERR_INVALID, "network inputs must be batched tensors");
+    if (t->dtype != n.dtype) throw Error(SPN_ERR_INVALID, "input dtype differs from the leaf declaration");
+    if (!spn_net::same_structure(t->st, n.st)) throw Error(SPN_ERR_STRUCTURE, "input structure differs from the leaf declaration");
+    if (k == 0)
+      total = t->n_points;
+    else if (t->n_points != total)
+      throw Error(SPN_ERR_INVALID, "inputs have different point counts");
+  }
+  if (n_inputs == 0) total = out ? out->n_points : 1;
+  if (n_points == 0) n_points = total - std::min(first_point, total);
+  if (first_point + n_points > total) throw Error(SPN_ERR_INVALID, "point range out of bounds");
+  const uint64_t size_out = net->values[(size_t)net->result_value].st.size();
+  if (out) {
+    if (!out->batched()) throw Error(SPN_ERR_INVALID, "output must be a batched tensor");
+    if (out->size() != size_out) throw Error(SPN_ERR_STRUCTURE, "output tensor has the wrong size");
+    if (out->n_points != total) throw Error(SPN_ERR_INVALID, "output tensor has a different point count");
+  }
+  if (!out && !sum_out_device) throw Error(SPN_ERR_INVALID, "nothing to compute: no output and no sum requested");
+
+  if (net->exec_mode == SPN_EXEC_STEPWISE) {
+    if (first_point != 0 || n_points != total) throw Error(SPN_ERR_INVALID, "stepwise execution runs all points");
+    run_stepwise(net, inputs, out, sum_out_device);
+    return SPN_OK;
+  }
+
+  // ---- fused ----
+  std::string variant;
+  for (uint32_t k = 0; k < n_inputs; ++k) {
+    const spn_tensor* t = inputs[k];
+    if (t->layout == SPN_COMPONENT_MAJOR)
+      variant += 'c';
+    else
+      variant += (((uintptr_t)t->dptr + first_point * t->size() * t->elem_bytes()) % 32 == 0) ? 'p' : 'q';
+  }
+  variant += !out ? 'n' : (out->layout == SPN_COMPONENT_MAJOR ? 'c' : 'p');
+  if (out && out->dtype == SPN_F64) variant += 'r';
+  if (sum_out_device) variant += 's';
+  JitKernel& k = net->get_variant(variant);
+  jit_load(k, spn_net::kBlock);
+
+  if (n_points == 0) {
+    if (sum_out_device) cuda_check(cudaMemsetAsync(sum_out_device, 0, size_out * 16, ctx->stream), "memset");
+    return SPN_OK;
+  }
+  const uint64_t need = (n_points + spn_net::kBlock - 1) / spn_net::kBlock;
+  const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
+  const unsigned grid = (unsigned)std::min<uint64_t>(need, cap);
+
+  std::vector<const double*> in_ptr(n_inputs);
+  std::vector<unsigned long long> in_cs(n_inputs);
+  for (uint32_t i = 0; i < n_inputs; ++i) {
+    const spn_tensor* t = inputs[i];
+    const size_t eb = t->elem_bytes();
+    in_cs[i] = t->n_points;
+    in_ptr[i] = reinterpret_cast<const double*>(
+        (const char*)t->dptr + (t->layout == SPN_POINT_MAJOR ? first_point * t->size() * eb : first_point * eb));
+  }
+  double* out_ptr = nullptr;
+  unsigned long long ocs = 0;
+  if (out) {
+    const size_t eb = out->elem_bytes();
+    ocs = out->n_points;
+    out_ptr = reinterpret_cast<double*>(
+        (char*)out->dptr + (out->layout == SPN_POINT_MAJOR ? first_point * out->size() * eb : first_point * eb));
+  }
+  double2* partial = nullptr;
+  if (sum_out_device)
+    cuda_check(cudaMallocAsync((void**)&partial, (size_t)grid * size_out * sizeof(double2) + 16, ctx->stream),
+               "sum scratch");
+  unsigned long long np = n_points;
+  std::vector<void*> args;
+  for (uint32_t i = 0; i < n_inputs; ++i) {
+    args.push_back(&in_ptr[i]);
+    args.push_back(&in_cs[i]);
+  }
+  args.push_back(&out_ptr);
+  args.push_back(&ocs);
+  args.push_back(&partial);
+  args.push_back(&np);
+  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(spn_net::kBlock), args.data(), 0, ctx->stream),
+             "launch fused network kernel");
+  ctx->launches++;
+  if (sum_out_device) {
+    cuda_check(launch_reduce_partials(partial, (int)grid, size_out, reinterpret_cast<double2*>(sum_out_device),
+                                      ctx->stream),
+               "reduce_partials_kernel");
+    ctx->launches++;
+    cudaFreeAsync(partial, ctx->stream);
+  }
+  return SPN_OK;
+  NET_CATCH(false)
+}
+
+}  // extern "C"

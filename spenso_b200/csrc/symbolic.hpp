@@ -1,0 +1,281 @@
+// Per-point program of a fused network kernel.
+//
+// The network executor (net.cu) walks the contraction schedule ONCE and, instead of computing
+// numbers, records what every component of every intermediate tensor is as a function of the
+// per-point inputs.  Components are tracked as real quantities `coef * value` where `value` is an
+// SSA id (or a literal): multiplying by the library constants that dominate these networks
+// (gamma matrices: 0, +-1, +-i; metrics: +-1; colour generators: +-1/2, ...) therefore emits no
+// instruction at all — zeros vanish, signs and factors of i become operand modifiers/renames of
+// the next FMA.  What is left is a straight-line list of DMUL/DFMA/DADD over the components that
+// actually depend on the kinematics; net.cu prints it as the body of one CUDA kernel
+// (thread = phase-space point, every intermediate in registers, inputs read exactly once).
+//
+// The arithmetic this replaces is the reference's per-point kernels:
+//   spenso/src/contraction/{singlecontract,multicontract,exteriorproduct}.rs and
+//   spenso/src/algebra/{add_assign,neg,scalar_mul}.rs  (C[o] = sum_k s(k) A[..k] B[..k]),
+//   complex product spenso/src/algebra/complex/mul.rs:16-21.
+// FMA contraction and a different summation order are allowed by the 1e-12 parity tolerance.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace spn {
+
+// a real quantity: coef * value(var); var < 0 => the literal `coef`
+struct RR {
+  int var = -1;
+  double coef = 0.0;
+  bool is_const() const { return var < 0; }
+  bool is_zero() const { return var < 0 && coef == 0.0; }
+};
+inline RR rr_const(double c) { return RR{-1, c}; }
+inline RR rr_neg(RR a) { return RR{a.var, -a.coef}; }
+
+// one complex tensor component
+struct CE {
+  RR re, im;
+};
+
+enum InsOp : uint8_t {
+  I_LOADC,  // dst, dst+1 = re, im of input[in] component [flat]
+  I_LOADR,  // dst = real input[in] component [flat]
+  I_MUL,    // dst = k * x * y
+  I_FMA,    // dst = k * x * y + sz * z
+  I_MULK,   // dst = k * x
+  I_FMAK,   // dst = k * x + sz * z
+  I_ADDK,   // dst = sz * z + kc
+  I_DIV     // dst = k * x / y
+};
+
+struct Ins {
+  InsOp op;
+  int dst = -1, x = -1, y = -1, z = -1;
+  double k = 1.0, kc = 0.0;
+  int sz = 1;
+  int in = -1;         // loads: input index
+  uint64_t flat = 0;   // loads: component
+};
+
+struct Term {
+  double k;
+  int x, y;  // y < 0: linear term k*x ; x < 0 too: constant k
+};
+
+struct Program {
+  std::vector<Ins> ins;
+  int n_vals = 0;
+  // lazily created loads: (input, flat) -> value id of the real part
+  std::map<std::pair<int, uint64_t>, int> loaded;
+
+  int fresh(int n = 1) {
+    int v = n_vals;
+    n_vals += n;
+    return v;
+  }
+  CE load(int in, uint64_t flat, bool is_complex) {
+    auto key = std::make_pair(in, flat);
+    auto it = loaded.find(key);
+    int v;
+    if (it != loaded.end()) {
+      v = it->second;
+    } else {
+      v = fresh(is_complex ? 2 : 1);
+      Ins i;
+      i.op = is_complex ? I_LOADC : I_LOADR;
+      i.dst = v;
+      i.in = in;
+      i.flat = flat;
+      ins.push_back(i);
+      loaded[key] = v;
+    }
+    CE e;
+    e.re = RR{v, 1.0};
+    e.im = is_complex ? RR{v + 1, 1.0} : rr_const(0.0);
+    return e;
+  }
+
+  // ---- term algebra ------------------------------------------------------------------------
+  static void push_product(std::vector<Term>& out, RR a, RR b, double sign) {
+    if (a.is_zero() || b.is_zero()) return;
+    double k = sign * a.coef * b.coef;
+    if (a.is_const() && b.is_const())
+      out.push_back({k, -1, -1});
+    else if (a.is_const())
+      out.push_back({k, b.var, -1});
+    else if (b.is_const())
+      out.push_back({k, a.var, -1});
+    else
+      out.push_back({k, a.var < b.var ? a.var : b.var, a.var < b.var ? b.var : a.var});
+  }
+  static void push_rr(std::vector<Term>& out, RR a, double sign) {
+    if (a.is_zero()) return;
+    if (a.is_const())
+      out.push_back({sign * a.coef, -1, -1});
+    else
+      out.push_back({sign * a.coef, a.var, -1});
+  }
+  // (re, im) += sign * a * b
+  static void push_cmul(std::vector<Term>& re, std::vector<Term>& im, const CE& a, const CE& b, double sign) {
+    push_product(re, a.re, b.re, sign);
+    push_product(re, a.im, b.im, -sign);
+    push_product(im, a.re, b.im, sign);
+    push_product(im, a.im, b.re, sign);
+  }
+
+  // emit the sum of `terms`; returns what the result is
+  RR sum(std::vector<Term> terms) {
+    // merge like terms
+    std::map<std::pair<int, int>, double> acc_map;
+    std::vector<std::pair<int, int>> order;
+    for (auto& t : terms) {
+      auto key = std::make_pair(t.x, t.y);
+      auto it = acc_map.find(key);
+      if (it == acc_map.end()) {
+        acc_map[key] = t.k;
+        order.push_back(key);
+      } else {
+        it->second += t.k;
+      }
+    }
+    std::vector<Term> bil, lin;
+    double cst = 0.0;
+    for (auto& key : order) {
+      double k = acc_map[key];
+      if (k == 0.0) continue;
+      if (key.first < 0)
+        cst += k;
+      else if (key.second < 0)
+        lin.push_back({k, key.first, -1});
+      else
+        bil.push_back({k, key.first, key.second});
+    }
+    if (bil.empty() && lin.empty()) return rr_const(cst);
+    if (bil.empty() && lin.size() == 1 && cst == 0.0) return RR{lin[0].x, lin[0].k};
+    const double s = std::fabs(bil.empty() ? lin[0].k : bil[0].k);
+    int av = -1, as = 1;  // running accumulator: as * value(av)
+    for (auto& t : bil) {
+      Ins i;
+      i.k = t.k / s;
+      i.x = t.x;
+      i.y = t.y;
+      i.dst = fresh();
+      if (av < 0) {
+        i.op = I_MUL;
+      } else {
+        i.op = I_FMA;
+        i.z = av;
+        i.sz = as;
+      }
+      ins.push_back(i);
+      av = i.dst;
+      as = 1;
+    }
+    for (auto& t : lin) {
+      double r = t.k / s;
+      if (av < 0 && std::fabs(r) == 1.0) {
+        av = t.x;
+        as = r > 0 ? 1 : -1;
+        continue;
+      }
+      Ins i;
+      i.k = r;
+      i.x = t.x;
+      i.dst = fresh();
+      if (av < 0) {
+        i.op = I_MULK;
+      } else {
+        i.op = I_FMAK;
+        i.z = av;
+        i.sz = as;
+      }
+      ins.push_back(i);
+      av = i.dst;
+      as = 1;
+    }
+    if (cst != 0.0) {
+      Ins i;
+      i.op = I_ADDK;
+      i.z = av;
+      i.sz = as;
+      i.kc = cst / s;
+      i.dst = fresh();
+      ins.push_back(i);
+      av = i.dst;
+      as = 1;
+    }
+    return RR{av, s * as};
+  }
+
+  // 1 / (re + i im)
+  CE reciprocal(const CE& a) {
+    if (a.re.is_const() && a.im.is_const()) {
+      double d = a.re.coef * a.re.coef + a.im.coef * a.im.coef;
+      return CE{rr_const(a.re.coef / d), rr_const(-a.im.coef / d)};
+    }
+    std::vector<Term> t;
+    push_product(t, a.re, a.re, 1.0);
+    push_product(t, a.im, a.im, 1.0);
+    RR d = sum(t);
+    auto div = [&](RR n, double sign) -> RR {
+      if (n.is_zero()) return rr_const(0.0);
+      // n / d with d = d.coef * value(d.var); x < 0: the numerator is the literal k
+      Ins i;
+      i.op = I_DIV;
+      i.x = n.is_const() ? -1 : n.var;
+      i.y = d.var;
+      i.k = sign * n.coef / d.coef;
+      i.dst = fresh();
+      ins.push_back(i);
+      return RR{i.dst, 1.0};
+    };
+    return CE{div(a.re, 1.0), div(a.im, -1.0)};
+  }
+
+  // ---- dead code elimination + statistics ---------------------------------------------------
+  // keep only instructions that feed `roots`; returns the number of FP64 arithmetic instructions
+  struct Stats {
+    uint64_t n_fp = 0, n_fma = 0, n_loads = 0, n_load_bytes = 0;
+  };
+  Stats eliminate_dead(const std::vector<int>& roots) {
+    std::vector<char> live(n_vals, 0);
+    for (int r : roots)
+      if (r >= 0) live[r] = 1;
+    std::vector<Ins> kept;
+    for (size_t n = ins.size(); n-- > 0;) {
+      const Ins& i = ins[n];
+      bool l = live[i.dst] || (i.op == I_LOADC && live[i.dst + 1]);
+      if (!l) continue;
+      if (i.x >= 0) live[i.x] = 1;
+      if (i.y >= 0) live[i.y] = 1;
+      if (i.z >= 0) live[i.z] = 1;
+      kept.push_back(i);
+    }
+    ins.assign(kept.rbegin(), kept.rend());
+    Stats s;
+    for (auto& i : ins) {
+      switch (i.op) {
+        case I_LOADC: s.n_loads++; s.n_load_bytes += 16; break;
+        case I_LOADR: s.n_loads++; s.n_load_bytes += 8; break;
+        case I_MUL: s.n_fp += (std::fabs(i.k) == 1.0) ? 1 : 2; break;
+        case I_FMA: s.n_fp += (std::fabs(i.k) == 1.0) ? 1 : 2; s.n_fma++; break;
+        case I_DIV: s.n_fp += 8; break;
+        default: s.n_fp += 1; break;
+      }
+    }
+    return s;
+  }
+};
+
+inline std::string lit(double v) {
+  char buf[64];
+  std::snprintf(buf, sizeof buf, "%.17g", v);
+  std::string s = buf;
+  if (s.find_first_of(".en") == std::string::npos) s += ".0";  // "inf"/"nan" contain 'n'
+  return s;
+}
+
+}  // namespace spn

@@ -1,0 +1,96 @@
+// Device-resident tensors of the engine (the replacement for spenso's DataTensor storage,
+// spenso/src/tensors/data.rs:190-193): batched dense buffers over the point axis, and shared
+// (point-independent) dense / sparse tensors that also keep a host copy for plan building.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "structure.hpp"
+
+struct spn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  int sm_count = 148;
+};
+
+struct spn_tensor {
+  spn_ctx* ctx = nullptr;
+  spn::Structure st;
+  int storage = SPN_STORAGE_BATCHED;
+  int dtype = SPN_C64;
+  int layout = SPN_POINT_MAJOR;
+  uint64_t n_points = 1;
+  void* dptr = nullptr;  // batched: the buffer; shared: densified Complex<f64> copy
+  bool owns = false;
+  // shared tensors: host copies (canonical row major)
+  std::vector<double2> host_dense;
+  std::map<uint64_t, double2> entries;  // sparse only, keyed (and therefore sorted) by flat index
+
+  uint64_t size() const { return st.size(); }
+  size_t elem_bytes() const { return dtype == SPN_C64 ? 16 : 8; }
+  bool batched() const { return storage == SPN_STORAGE_BATCHED; }
+  bool sparse() const { return storage == SPN_STORAGE_SHARED_SPARSE; }
+  spn::DevOperand operand() const {
+    spn::DevOperand o;
+    o.ptr = dptr;
+    o.is_complex = dtype == SPN_C64;
+    if (!batched()) {
+      o.ps = 0;
+      o.fs = 1;
+    } else if (layout == SPN_POINT_MAJOR) {
+      o.ps = (long long)size();
+      o.fs = 1;
+    } else {
+      o.ps = 1;
+      o.fs = (long long)n_points;
+    }
+    return o;
+  }
+  spn::DevOut output() const {
+    spn::DevOperand o = operand();
+    spn::DevOut r;
+    r.ptr = dptr;
+    r.ps = o.ps;
+    r.fs = o.fs;
+    r.is_complex = o.is_complex;
+    return r;
+  }
+  ~spn_tensor() {
+    if (owns && dptr) cudaFree(dptr);
+  }
+};
+
+namespace spn {
+
+void set_error(const std::string& s);
+inline void cuda_check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+                   ? SPN_ERR_NO_DEVICE
+                   : SPN_ERR_CUDA;
+    throw Error(code, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+}
+
+// host-side helpers shared by the pairwise API and the network compiler
+struct KTables {
+  std::vector<int> off_a, off_b;
+  std::vector<unsigned char> sign;
+};
+KTables build_k_tables(const spn_contract_plan& p);
+DevOutMap out_map_of(const spn_contract_plan& p);
+
+spn_tensor* new_shared_dense(spn_ctx* ctx, const Structure& st, const double2* data);
+spn_tensor* new_shared_sparse(spn_ctx* ctx, const Structure& st, const std::map<uint64_t, double2>& entries);
+spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, int dtype, int layout, void* wrap);
+
+// the Contract trait: result in *out (new tensor)
+void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out);
+void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out);
+
+}  // namespace spn

@@ -407,3 +407,69 @@ class ONet:
         if rc:
             raise OracleError(rc, lib().orc_last_error().decode())
         return out, s
+
+
+# ---- NetSpec (spenso_b200/workloads.py) -> oracle network ---------------------------------------------
+def _spec_slots(sl) -> np.ndarray:
+    return np.array([s.record() for s in sl], dtype=SLOT_DTYPE)
+
+
+def net_from_spec(spec, arrays, point: int = 0):
+    """Build the oracle network of a NetSpec with the batched leaves filled from arrays[input][point].
+
+    arrays[k]: complex [n_points, size_k] in the CANONICAL order of the k-th batched leaf.
+    Returns (ONet, batched_node_ids, arrays_per_node) — the last two feed ONet.eval_batch; re-indexed
+    leaves reuse the array of the leaf they alias (only identical canonical permutations supported).
+    """
+    net = ONet()
+    ids, node_input, input_idx = {}, {}, 0
+    b_nodes, b_arrays = [], []
+    batched_nodes = [i for i, n in enumerate(spec.nodes) if n[0] == "batched"]
+    for k, node in enumerate(spec.nodes):
+        kind = node[0]
+        if kind in ("batched", "reindex"):
+            if kind == "batched":
+                inp = input_idx
+                input_idx += 1
+                sl = _spec_slots(node[1])
+            else:
+                inp = node_input[node[1]]
+                sl = _spec_slots(node[2])
+            canon, perm, _, _ = order_structure(sl) if len(sl) else (sl, [], 0, 0)
+            src_sl = _spec_slots(spec.nodes[batched_nodes[inp]][1])
+            _, src_perm, _, _ = order_structure(src_sl) if len(src_sl) else (src_sl, [], 0, 0)
+            if list(perm) != list(src_perm):
+                raise NotImplementedError("re-indexed leaf with a different canonical permutation")
+            node_input[k] = inp
+            t = OTensor.dense(canon, arrays[inp][point], canonicalize=False)
+            net._keep.append(t)
+            ids[k] = net.tensor(t)
+            b_nodes.append(ids[k])
+            b_arrays.append(arrays[inp])
+        elif kind == "lib":
+            which, sl = node[1], _spec_slots(node[2])
+            l = OLib.metric(sl[0]) if which == 6 else OLib.builtin(which)
+            net._keep.append(l)
+            ids[k] = net.lib_tensor(l, sl)
+        elif kind == "custom":
+            sl = _spec_slots(node[1])
+            l = OLib.custom_sparse(sl, node[2])
+            net._keep.append(l)
+            ids[k] = net.lib_tensor(l, sl)
+        elif kind == "scalar":
+            ids[k] = net.scalar(node[1])
+        else:
+            ids[k] = net.op(node[1], [ids[c] for c in node[2]], node[3])
+    net.set_root(ids[spec.root])
+    return net, b_nodes, b_arrays
+
+
+def eval_spec(spec, arrays, n_threads: int = 1, want_out: bool = True):
+    """Oracle evaluation of a NetSpec at every point: (out [n_points, out_size] canonical, sum, out slots)."""
+    probe, _, _ = net_from_spec(spec, arrays, 0)
+    probe.execute()
+    r = probe.result()
+    out_size, out_slots = r.size, r.slots
+    net, nodes, arrs = net_from_spec(spec, arrays, 0)
+    out, s = net.eval_batch(nodes, arrs, out_size, n_threads=n_threads, want_out=want_out)
+    return out, s, out_slots

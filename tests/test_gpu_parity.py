@@ -1,0 +1,361 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): 1e-12 relative, norm-wise per output tensor
+(max|x - y| <= 1e-12 * max|ref|).  Structures, sparse index sets and plans: bit-exact.
+The pairwise kernels keep the reference's operation order and IEEE ops (no FMA), so they are also
+checked for bit-identical values where the enumeration order is pinned.
+"""
+import numpy as np
+import pytest
+
+import _oracle as O
+import _cases
+import spenso_b200 as sp
+from spenso_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return sp.Context(0)
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = max(np.abs(want).max() if want.size else 0.0, 1e-300)
+    return (np.abs(got - want).max() if want.size else 0.0) / scale
+
+
+def dense_pair(ctx, rng, sl, n_points, layout=sp.POINT_MAJOR):
+    """(engine BatchTensor, [oracle tensor per point], canonical host data [n, *shape])."""
+    canon = O.order_structure(sl)[0] if len(sl) else sl
+    shape = [int(d) for d in canon["dim"]]
+    data = _cases.random_complex(rng, [n_points] + shape)
+    t = sp.BatchTensor.empty(ctx, canon, n_points, sp.C64, layout)
+    t.upload(data.reshape(n_points, -1))
+    return t, [O.OTensor.dense(canon, data[p], canonicalize=False) for p in range(n_points)], data
+
+
+# ---- reference KATs through the device ------------------------------------------------------------------
+def test_kat_dense_dense_single_contract(ctx):
+    # spenso/src/tests.rs:416-437 + snapshots/spenso__tests__dense_dense_single_contract.snap
+    a = sp.DenseTensor.from_data(ctx, [sp.Euclidean.new_slot(4, 1), sp.Euclidean.new_slot(4, 2)], np.arange(1, 17))
+    b = sp.DenseTensor.from_data(ctx, [sp.Euclidean.new_slot(4, 2), sp.Euclidean.new_slot(3, 3)], np.arange(1, 13))
+    c = a.contract(b)
+    want = np.array([70, 80, 90, 158, 184, 210, 246, 288, 330, 334, 392, 450]).reshape(4, 3)
+    ainds = [int(x) for x in c.slots["aind"]]
+    got = np.transpose(c.to_numpy(), [ainds.index(1), ainds.index(3)])
+    assert (got == want).all()
+
+
+def test_kat_sparse_diag_dense_and_storage_rule(ctx):
+    # tests.rs:439-473: diag(1,2,3,4) sparse . B ; result Dense unless both Sparse (contraction.rs:219-224)
+    e = [sp.Euclidean.new_slot(4, 1), sp.Euclidean.new_slot(4, 2)]
+    a = sp.SparseTensor.from_entries(ctx, e, {(i, i): i + 1 for i in range(4)})
+    bs = [sp.Euclidean.new_slot(4, 2), sp.Euclidean.new_slot(3, 3)]
+    b = sp.DenseTensor.from_data(ctx, bs, np.arange(1, 13))
+    c = a.contract(b)
+    assert not c.is_sparse
+    ainds = [int(x) for x in c.slots["aind"]]
+    got = np.transpose(c.to_numpy(), [ainds.index(1), ainds.index(3)]).reshape(-1)
+    assert (got == np.array([1, 2, 3, 8, 10, 12, 21, 24, 27, 40, 44, 48])).all()
+    bsp = sp.SparseTensor.from_entries(ctx, bs, {(i, j): 3 * i + j + 1 for i in range(4) for j in range(3)})
+    c2 = a.contract(bsp)
+    assert c2.is_sparse
+    got2 = np.transpose(c2.to_numpy(), [ainds.index(1), ainds.index(3)]).reshape(-1)
+    assert (got2 == got).all()
+
+
+def test_kat_sparse_sparse_index_set(ctx):
+    # tests.rs:1164-1195: [(0,0):1,(1,1):2] x [(0,1):1,(1,0):?]... -> {(0,1):2,(1,0):2} as a SET of flat indices
+    e12 = [sp.Euclidean.new_slot(2, 1), sp.Euclidean.new_slot(2, 2)]
+    e23 = [sp.Euclidean.new_slot(2, 2), sp.Euclidean.new_slot(2, 3)]
+    a = sp.SparseTensor.from_entries(ctx, e12, {(0, 0): 1.0, (1, 1): 2.0})
+    b = sp.SparseTensor.from_entries(ctx, e23, {(0, 1): 2.0, (1, 0): 1.0})
+    oa = O.OTensor.sparse(O.slots(("euc", 2, 1), ("euc", 2, 2)), {(0, 0): 1.0, (1, 1): 2.0})
+    ob = O.OTensor.sparse(O.slots(("euc", 2, 2), ("euc", 2, 3)), {(0, 1): 2.0, (1, 0): 1.0})
+    assert a.contract(b).entries() == oa.contract(ob).entries() == {1: 2 + 0j, 2: 2 + 0j}
+
+
+def test_minkowski_sign_convention(ctx):
+    # network/library/symbolic.rs:998-1050: p.q = p0 q0 - p1 q1 - p2 q2 - p3 q3
+    m = [sp.Minkowski.new_slot(4, 2)]
+    p = sp.DenseTensor.from_data(ctx, m, [1, 2, 3, 4])
+    q = sp.DenseTensor.from_data(ctx, m, [5, 6, 7, 8])
+    assert p.contract(q).to_numpy().reshape(-1)[0] == 5 - 12 - 21 - 32
+
+
+# ---- pairwise contraction, random structures -----------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("layout", [sp.POINT_MAJOR, sp.COMPONENT_MAJOR])
+def test_contract_batched_batched_vs_oracle(ctx, seed, layout):
+    rng = np.random.default_rng(1000 + seed)
+    n_points, done, exact = 5, 0, 0
+    for _ in range(25):
+        a, b = _cases.random_pair(rng)
+        ta, oa, _ = dense_pair(ctx, rng, a, n_points, layout)
+        tb, ob, _ = dense_pair(ctx, rng, b, n_points, layout)
+        try:
+            refs = [x.contract(y) for x, y in zip(oa, ob)]
+        except O.OracleError as e:
+            with pytest.raises(sp.SpensoError):
+                ta.contract(tb)
+            continue
+        c = ta.contract(tb)
+        assert c.slots.tobytes() == refs[0].slots.tobytes()          # structure: bit-exact
+        want = np.stack([r.to_dense() for r in refs])
+        got = c.to_numpy()
+        assert rel_err(got, want) <= TOL
+        exact += int((got == want).all())
+        done += 1
+    assert done >= 15
+    assert exact == done, f"pairwise kernels should reproduce the reference rounding exactly ({exact}/{done})"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_contract_batched_sparse_vs_oracle(ctx, seed):
+    """K2: Dense(per point) x Sparse(shared) and Sparse x Dense, both receiver orders."""
+    rng = np.random.default_rng(2000 + seed)
+    n_points, done = 4, 0
+    for it in range(25):
+        a, b = _cases.random_pair(rng)
+        cb = O.order_structure(b)[0] if len(b) else b
+        ent = _cases.random_sparse_entries(rng, [int(d) for d in cb["dim"]])
+        ta, oa, _ = dense_pair(ctx, rng, a, n_points)
+        tb = sp.SparseTensor.from_entries(ctx, cb, ent)
+        ob = O.OTensor.sparse(cb, ent)
+        swap = it % 2 == 1
+        try:
+            refs = [(ob.contract(x) if swap else x.contract(ob)) for x in oa]
+        except O.OracleError:
+            continue
+        c = tb.contract(ta) if swap else ta.contract(tb)
+        assert c.storage == sp.BATCHED
+        assert c.slots.tobytes() == refs[0].slots.tobytes()
+        assert rel_err(c.to_numpy(), np.stack([r.to_dense() for r in refs])) <= TOL
+        done += 1
+    assert done >= 15
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_contract_shared_combinations_vs_oracle(ctx, seed):
+    """Dense x Dense, Dense x Sparse, Sparse x Dense, Sparse x Sparse at one point: values, result storage
+    and (for sparse results) the stored index SET must match the oracle."""
+    rng = np.random.default_rng(3000 + seed)
+    done = 0
+    for it in range(30):
+        a, b = _cases.random_pair(rng, max_free=2, max_common=2)
+        ca = O.order_structure(a)[0] if len(a) else a
+        cb = O.order_structure(b)[0] if len(b) else b
+        sa, sb = bool(it & 1), bool(it & 2)
+        def mk(c, sparse):
+            dims = [int(d) for d in c["dim"]]
+            if sparse:
+                ent = _cases.random_sparse_entries(rng, dims)
+                return sp.SparseTensor.from_entries(ctx, c, ent), O.OTensor.sparse(c, ent)
+            d = _cases.random_complex(rng, dims)
+            return sp.DenseTensor.from_data(ctx, c, d), O.OTensor.dense(c, d, canonicalize=False)
+        ta, oa = mk(ca, sa)
+        tb, ob = mk(cb, sb)
+        try:
+            ref = oa.contract(ob)
+        except O.OracleError:
+            continue
+        c = ta.contract(tb)
+        assert c.is_sparse == ref.is_sparse == (sa and sb)
+        assert c.slots.tobytes() == ref.slots.tobytes()
+        assert rel_err(c.to_numpy(), ref.to_dense()) <= TOL
+        if ref.is_sparse:
+            assert set(c.entries()) == set(ref.entries())
+        done += 1
+    assert done >= 20
+
+
+def test_contract_edge_cases(ctx):
+    rng = np.random.default_rng(7)
+    # scalar x tensor (exterior product with a rank-0 operand), dim-1 indices
+    s, os_, _ = dense_pair(ctx, rng, np.zeros(0, O.SLOT_DTYPE), 3)
+    t, ot, _ = dense_pair(ctx, rng, O.slots(("euc", 1, 1), ("mink", 4, 2)), 3)
+    for x, y, ox, oy in ((s, t, os_, ot), (t, s, ot, os_)):
+        c = x.contract(y)
+        want = np.stack([a.contract(b).to_dense() for a, b in zip(ox, oy)])
+        assert rel_err(c.to_numpy(), want) <= TOL
+    # mismatched point counts
+    u, _, _ = dense_pair(ctx, rng, O.slots(("mink", 4, 2)), 2)
+    with pytest.raises(sp.SpensoError):
+        t.contract(u)
+    # zero points: allowed, empty result
+    z = sp.BatchTensor.empty(ctx, O.slots(("mink", 4, 2)), 0)
+    assert z.contract(z).to_numpy().shape[0] == 0
+
+
+def test_elementwise_trace_reduce(ctx):
+    rng = np.random.default_rng(11)
+    sl = O.slots(("bis", 4, 1), ("mink", 4, 2))
+    a, oa, da = dense_pair(ctx, rng, sl, 6)
+    b, ob, db = dense_pair(ctx, rng, sl, 6)
+    assert ((a + b).to_numpy() == da + db).all()
+    assert ((a - b).to_numpy() == da - db).all()
+    assert ((-a).to_numpy() == -da).all()
+    assert (a.conj().to_numpy() == da.conj()).all()
+    want = np.stack([x.scalar_mul(0.5 - 2j).to_dense() for x in oa])
+    assert (a.scalar_mul(0.5 - 2j).to_numpy() == want).all()
+    with pytest.raises(sp.SpensoError):
+        a + dense_pair(ctx, rng, O.slots(("bis", 4, 1), ("mink", 4, 3)), 6)[0]
+    # Monte-Carlo sum over points
+    assert rel_err(a.sum_points(), da.sum(axis=0)) <= 1e-14
+    # trace over a repeated Minkowski pair with metric sign, and a repeated bispinor pair
+    for reps in ((("mink", 4, 5), ("bis", 2, 1), ("mink", 4, 5)), (("bis", 4, 3), ("bis", 4, 3), ("euc", 3, 9))):
+        raw = O.slots(*reps)
+        shape = [int(d) for d in raw["dim"]]
+        data = _cases.random_complex(rng, [4] + shape)
+        # the engine's trace takes the tensor in the caller's slot order (data row major over it)
+        canon_like = np.array([(1, 0, 0, d, 900 + i) for i, d in enumerate(shape)], dtype=sp.SLOT_DTYPE)
+        holder = sp.BatchTensor.empty(ctx, canon_like, 4)
+        holder.upload(data.reshape(4, -1))
+        got = holder.trace(raw)
+        refs = []
+        for p in range(4):
+            h = O.lib().orc_tensor_dense_raw(O._ptr(raw), len(raw), O._ptr(np.ascontiguousarray(data[p]).view(np.float64)))
+            refs.append(O.OTensor(h).trace().to_dense())
+        assert rel_err(got.to_numpy(), np.stack(refs)) <= TOL
+
+
+def test_empty_sparse_error(ctx):
+    # ContractionError::EmptySparse (singlecontract.rs:153-159)
+    sl = O.slots(("euc", 3, 1))
+    empty_sparse = sp.SparseTensor.from_entries(ctx, sl, {})
+    empty_dense = sp.BatchTensor.empty(ctx, sl, 0)
+    with pytest.raises(sp.SpensoError) as e:
+        empty_sparse.contract(empty_dense)
+    assert e.value.code == 1
+
+
+# ---- networks ------------------------------------------------------------------------------------------------------
+def run_network(ctx, spec, arrays, mode, layout=sp.POINT_MAJOR, want_sum=False):
+    import torch
+
+    net = workloads.build_engine(spec, ctx, mode)
+    n = arrays[0].shape[0]
+    inputs = []
+    for node, a in zip([x for x in spec.nodes if x[0] == "batched"], arrays):
+        t = sp.BatchTensor.empty(ctx, node[1], n, sp.C64, layout)
+        t.upload(a)
+        inputs.append(t)
+    out = sp.BatchTensor.empty(ctx, net.result_slots, n, sp.C64, layout)
+    s = torch.zeros(2 * net.result_size, dtype=torch.float64, device="cuda:0") if want_sum else None
+    net.execute(inputs, out, sum_out_ptr=s.data_ptr() if want_sum else 0)
+    ctx.synchronize()
+    res = out.to_numpy().reshape(n, -1)
+    return (res, s.cpu().numpy().view(np.complex128)) if want_sum else res
+
+
+def test_cfg1_gamma_trace_closed_form(ctx):
+    # spenso-hep-lib/tests/gamma_algebra_validate.rs:29-70 with p=(0,1,2,3), q=(1,2,3,4)
+    spec = workloads.gamma_trace4()
+    p, q = np.array([[0, 1, 2, 3.0]], dtype=complex), np.array([[1, 2, 3, 4.0]], dtype=complex)
+    want = np.array([[136, 4, 8, 12], [4, -112, 44, 64], [8, 44, -56, 116], [12, 64, 116, 32]], dtype=complex)
+    for mode in (sp.FUSED, sp.STEPWISE):
+        got = run_network(ctx, spec, [p, q], mode)
+        assert (got.reshape(4, 4) == want).all()      # integers: exact
+    # random kinematics vs the closed form and the oracle
+    arrays = workloads.synthetic_inputs(spec, 257, 5, real=True)
+    ref, _, _ = O.eval_spec(spec, arrays)
+    cf = workloads.gamma_trace4_closed_form(arrays[0].real, arrays[1].real).reshape(257, 16)
+    for mode in (sp.FUSED, sp.STEPWISE):
+        got = run_network(ctx, spec, arrays, mode)
+        assert rel_err(got, ref) <= TOL
+        assert rel_err(got, cf) <= 1e-12
+
+
+@pytest.mark.parametrize("name,n_points,scale", [("cfg2", 1000, 1.0), ("cfg3", 300, 1.0), ("cfg5", 500, 100.0),
+                                                 ("gl03", 64, 100.0)])
+@pytest.mark.parametrize("mode", [sp.FUSED, sp.STEPWISE])
+@pytest.mark.parametrize("layout", [sp.POINT_MAJOR, sp.COMPONENT_MAJOR])
+def test_network_vs_oracle(ctx, name, n_points, scale, mode, layout):
+    spec = workloads.WORKLOADS[name]()
+    arrays = workloads.synthetic_inputs(spec, n_points, 1234, scale=scale, real=name in ("cfg5", "gl03"))
+    ref, ref_sum, oslots = O.eval_spec(spec, arrays)
+    got, s = run_network(ctx, spec, arrays, mode, layout, want_sum=True)
+    if name == "gl03":
+        assert not ref.any() and not got.any()     # vanishes identically
+        return
+    assert rel_err(got, ref) <= TOL
+    assert rel_err(s, ref_sum) <= TOL
+    assert rel_err(s, got.sum(axis=0)) <= 1e-13
+
+
+def test_network_ragged_ranges_and_sum_only(ctx):
+    import torch
+
+    spec = workloads.eemumu()
+    n = 1000
+    arrays = workloads.synthetic_inputs(spec, n, 99)
+    ref, _, _ = O.eval_spec(spec, arrays)
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    inputs = []
+    for node, a in zip([x for x in spec.nodes if x[0] == "batched"], arrays):
+        t = sp.BatchTensor.empty(ctx, node[1], n)
+        t.upload(a)
+        inputs.append(t)
+    s = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+    for first, cnt in ((0, 1), (1, 1), (3, 130), (129, 871), (999, 1), (5, 0)):
+        net.execute(inputs, None, sum_out_ptr=s.data_ptr(), first_point=first, n_points=cnt)
+        ctx.synchronize()
+        got = s.cpu().numpy().view(np.complex128)[0]
+        want = ref[first:first + cnt, 0].sum() if cnt else (ref[first:, 0].sum())
+        assert abs(got - want) <= TOL * max(1.0, np.abs(ref).max() * max(cnt, 1))
+    out = sp.BatchTensor.empty(ctx, net.result_slots, n)
+    out.upload(np.zeros((n, 1), dtype=complex))
+    net.execute(inputs, out, first_point=100, n_points=50)
+    ctx.synchronize()
+    got = out.to_numpy().reshape(-1)
+    assert rel_err(got[100:150], ref[100:150, 0]) <= TOL and not got[:100].any() and not got[150:].any()
+    # errors: wrong input count / structure / nothing requested
+    with pytest.raises(sp.SpensoError):
+        net.execute(inputs[:3], out)
+    with pytest.raises(sp.SpensoError):
+        net.execute(inputs, None)
+    with pytest.raises(sp.SpensoError):
+        net.execute([inputs[1], inputs[0], inputs[2], inputs[3]], out)
+
+
+def test_cfg2_full_size_properties(ctx):
+    """BASELINE config 2 at its full size (2^20 points): linearity in one spinor, agreement of the per-point
+    output with the fused Monte-Carlo sum, determinism, and an oracle spot check on a sample."""
+    import torch
+
+    spec = workloads.eemumu()
+    n = 1 << 20
+    arrays = workloads.synthetic_inputs(spec, n, 1234)
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    nodes = [x for x in spec.nodes if x[0] == "batched"]
+
+    def run(arrs):
+        ins = []
+        for node, a in zip(nodes, arrs):
+            t = sp.BatchTensor.empty(ctx, node[1], n)
+            t.upload(a)
+            ins.append(t)
+        out = sp.BatchTensor.empty(ctx, net.result_slots, n)
+        s = torch.zeros(2, dtype=torch.float64, device="cuda:0")
+        net.execute(ins, out, sum_out_ptr=s.data_ptr())
+        ctx.synchronize()
+        return out.to_numpy().reshape(-1), s.cpu().numpy().view(np.complex128)[0]
+
+    base, s0 = run(arrays)
+    again, s1 = run(arrays)
+    assert (base == again).all() and s0 == s1                                   # deterministic, incl. the sum
+    assert abs(s0 - base.sum()) <= 1e-12 * np.abs(base).sum()
+    z = 0.75 - 1.25j
+    scaled, _ = run([arrays[0] * z] + arrays[1:])
+    assert rel_err(scaled, base * z) <= 1e-13                                   # linear in vbar
+    summed, _ = run([arrays[0], arrays[1] + arrays[3][::-1], arrays[2], arrays[3]])
+    other, _ = run([arrays[0], arrays[3][::-1], arrays[2], arrays[3]])
+    assert rel_err(summed, base + other) <= 1e-13                               # additive in u
+    idx = np.random.default_rng(0).choice(n, 2000, replace=False)
+    ref, _, _ = O.eval_spec(spec, [a[idx] for a in arrays])
+    assert rel_err(base[idx], ref[:, 0]) <= TOL
