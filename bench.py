@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — network evaluations / second (c64, batched) of the hot path on N B200s.
+
+Workload (default, N=1): BASELINE.json configs[1] — the e+e- -> mu+mu- tree spinor-chain network
+evaluated over 2^20 synthetic phase-space points per GPU.  One "step" = one pass
+of the network executor over one batch: ONE launch of the fused sm_100a network kernel, which reads
+the four spinors of every point (256 B) and writes the amplitude (16 B).
+
+  value         whole-job evals/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e           the same through the C ABI with HOST buffers: pinned H2D of the step's inputs,
+                execute, D2H of the per-point results, all inside the timed region
+  roofline      algorithmic bytes per launch / measured launch duration vs MEASURED_PEAKS.json HBM GB/s
+  cpu_baseline  oracle (C++ restatement of the reference's CPU Contract/Network path) timed on the
+                host cores on a bounded sample of the same workload
+  --impl reference   the reference arm: the same oracle, all host threads, same config/metric/unit
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "network evals/sec (c64, batched)"
+UNIT = "evals/s"
+WORKLOAD_DESC = {
+    "cfg2": "cfg2: e+e- -> mu+mu- tree spinor-chain network [vbar g^mu u][ubar g_mu v], Bispinor4 x Minkowski4, "
+            "Complex<f64>, 2^20 synthetic phase-space points per GPU",
+    "cfg3": "cfg3: SU(3) colour-factor network X.T + D.f (Dense per point x Sparse shared)",
+    "cfg5": "cfg5: one-loop numerator network (gl_03 topology, massive), Monte-Carlo sum",
+}
+DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg3": 1 << 18, "cfg5": 1 << 22}
+SCALE = {"cfg2": 1.0, "cfg3": 1.0, "cfg5": 100.0}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--points", type=int, default=0, help="points per GPU per step (default: the config's)")
+    ap.add_argument("--layout", default="point", choices=["point", "component"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU side: the oracle (only for cpu_baseline / --impl reference) ---------------------------------------
+def oracle_rate(spec, arrays_fn, n_threads, target_seconds):
+    """evals/s of the oracle port on a bounded sample; returns (rate, sample_points, seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+
+    probe_n = 2048 * n_threads
+    arrs = arrays_fn(probe_n)
+    t0 = time.perf_counter()
+    _oracle.eval_spec(spec, arrs, n_threads=n_threads, want_out=False)
+    dt = time.perf_counter() - t0
+    rate = probe_n / dt
+    n = int(min(max(rate * target_seconds, probe_n), 1 << 22))
+    arrs = arrays_fn(n)
+    t0 = time.perf_counter()
+    _oracle.eval_spec(spec, arrs, n_threads=n_threads, want_out=False)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  The reference is Rust and cannot be
+    built in this image (no cargo/rustc), so this is the oracle port of its Contract/Network::execute path,
+    one network evaluation per point, all host threads."""
+    from spenso_b200 import workloads
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    spec = workloads.WORKLOADS[args.workload]()
+    n_threads = os.cpu_count() or 1
+    real = args.workload == "cfg5"
+    fn = lambda n: workloads.synthetic_inputs(spec, n, 1234, scale=SCALE[args.workload], real=real)
+    points = args.points or DEFAULT_POINTS[args.workload]
+    # each step = a bounded sample of the workload; keep the whole run within a few minutes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle
+
+    probe = 1024 * n_threads
+    arrs = fn(probe)
+    t0 = time.perf_counter()
+    _oracle.eval_spec(spec, arrs, n_threads=n_threads, want_out=False)
+    rate = probe / (time.perf_counter() - t0)
+    budget_s = 120.0
+    sample = int(max(probe, min(points, rate * budget_s / max(args.steps + args.warmup, 1))))
+    arrs = fn(sample)
+    for _ in range(args.warmup):
+        _oracle.eval_spec(spec, arrs, n_threads=n_threads, want_out=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _oracle.eval_spec(spec, arrs, n_threads=n_threads, want_out=False)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[args.workload], "points_per_step": sample,
+                   "note": "bounded sample of the workload per step; CPU, no GPU involved"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": "port",
+                         "sample": f"{sample} points/step x {args.steps} steps, {n_threads} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.stop = [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        while not self.stop:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.nv:
+            self.t.join(timeout=1.0)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---- GPU arm --------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import spenso_b200 as sp
+    from spenso_b200 import workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — spenso_b200 has no CPU execution path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = args.workload
+    spec = workloads.WORKLOADS[wl]()
+    n = args.points or DEFAULT_POINTS[wl]
+    layout = sp.POINT_MAJOR if args.layout == "point" else sp.COMPONENT_MAJOR
+    stream = torch.cuda.current_stream()
+    ctx = sp.Context(local_rank, stream=stream.cuda_stream)
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    out_size = net.result_size
+    leaf_slots = [x[1] for x in spec.nodes if x[0] == "batched"]
+    want_sum = wl == "cfg5"        # Monte-Carlo estimate: no per-point store, only the sum over points
+
+    # synthetic kinematics: ROT rotating input sets so that consecutive steps never re-read what L2 holds
+    bytes_in = sum(sz for _, sz in spec.inputs) * 16 * n
+    rot = max(2, min(8, int(np.ceil(2.5 * 126e6 / bytes_in)) + 1))
+    host_sets, dev_sets = [], []
+    for r in range(rot):
+        arrs = workloads.synthetic_inputs(spec, n, 1234 + 1000 * rank + r, scale=SCALE[wl], real=(wl == "cfg5"))
+        pinned = [torch.from_numpy(a.view(np.float64).reshape(n, -1)).pin_memory() for a in arrs]
+        host_sets.append(pinned)
+        tens = []
+        for sl, a in zip(leaf_slots, arrs):
+            t = sp.BatchTensor.empty(ctx, sl, n, sp.C64, layout)
+            t.upload(a)
+            tens.append(t)
+        dev_sets.append(tens)
+    out = None if want_sum else sp.BatchTensor.empty(ctx, net.result_slots, n, sp.C64, layout)
+    sums = torch.zeros(2 * out_size, dtype=torch.float64, device=dev)
+    sum_ptr = sums.data_ptr() if want_sum else 0
+
+    def step(i):
+        net.execute(dev_sets[i % rot], out, sum_out_ptr=sum_ptr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region: exactly K steps ------------------------------------------------------------------------
+    # The K launches are captured into ONE CUDA graph (the step is a single ~50 us kernel: eager launches from
+    # Python would time the interpreter) and replayed between two events on the launching stream.  The
+    # roofline uses (elapsed / K) as the kernel's launch duration: an upper bound that includes the
+    # inter-kernel gap.  A second, eager pass with an event pair around every launch is reported beside it.
+    K = args.steps
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph, cap_stream = None, torch.cuda.Stream(device=dev)
+    try:
+        ctx.set_stream(cap_stream.cuda_stream)
+        cap_stream.wait_stream(stream)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=cap_stream):
+            for i in range(K):
+                step(i)
+        graph = g
+    except Exception as e:  # capture not possible: eager launches on the same stream
+        print(f"bench.py: CUDA graph capture failed ({e}); timing eager launches", file=sys.stderr)
+        graph = None
+    ctx.set_stream(stream.cuda_stream)
+    torch.cuda.synchronize()
+    if graph is not None:
+        graph.replay()          # one untimed replay: graph upload
+        torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t_begin.record(stream)
+        if graph is not None:
+            graph.replay()
+        else:
+            for i in range(K):
+                step(i)
+        if world > 1 and want_sum:
+            dist.all_reduce(sums)          # the one collective of the path: final Monte-Carlo sum
+        t_end.record(stream)
+        barrier()
+    launches = (ctx.launch_count - launches0) if graph is None else K * (2 if want_sum else 1)
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    kernel_ms = elapsed_ms / K
+    # eager pass: event pair around every launch (includes event/launch overhead of a lone launch)
+    KE2 = min(K, 50)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KE2)]
+    for i in range(KE2):
+        ev[i][0].record(stream)
+        step(i)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    kernel_ms_eager = float(np.median([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = n * K * world / (elapsed_ms * 1e-3)
+
+    # ---- e2e: host buffers through the public API, copies inside the timed region --------------------------------
+    e2e_in = [sp.BatchTensor.empty(ctx, sl, n, sp.C64, layout) for sl in leaf_slots]
+    e2e_out = sp.BatchTensor.empty(ctx, net.result_slots, n, sp.C64, sp.POINT_MAJOR)
+    host_out = torch.empty(n * out_size * 2, dtype=torch.float64).pin_memory()
+    host_sum = torch.empty(2 * out_size, dtype=torch.float64).pin_memory()
+    h2d = sum(int(p.numel()) * 8 for p in host_sets[0])
+    d2h = host_sum.numel() * 8 if want_sum else host_out.numel() * 8
+
+    def e2e_step(i):
+        for t, p in zip(e2e_in, host_sets[i % rot]):
+            t.upload_ptr(p.data_ptr(), 0, n, sync=False)
+        if want_sum:
+            net.execute(e2e_in, None, sum_out_ptr=sums.data_ptr())
+            host_sum.copy_(sums, non_blocking=True)
+        else:
+            net.execute(e2e_in, e2e_out)
+            sp.check(sp.lib().spn_tensor_download(e2e_out.h, host_out.data_ptr(), 0, n))
+        torch.cuda.synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    KE = max(1, args.e2e_steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(KE):
+        e2e_step(i)
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = n * KE * world / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (the fused network kernel) ----------------------------------------------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = spec.algorithmic_bytes * n
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", f"traffic_{wl}.json")
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "spn_fused_net_*",
+                "kernel_ms": kernel_ms, "kernel_ms_eager_event_pair": kernel_ms_eager,
+                "timing": "CUDA graph of K launches" if graph is not None else "eager launches",
+                "algorithmic_bytes_per_eval": spec.algorithmic_bytes,
+                "fp64_instr_per_eval": net.fp64_instr_per_point}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world >= 1:
+            nthr = os.cpu_count() or 1
+            fn = lambda m: workloads.synthetic_inputs(spec, m, 1234, scale=SCALE[wl], real=(wl == "cfg5"))
+            rate, sample, secs = oracle_rate(spec, fn, nthr, args.cpu_seconds)
+            cpu = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
+                   "sample": f"{sample} points of the same workload, {nthr} threads, {secs:.1f} s "
+                             "(C++ restatement of spenso's CPU Contract/Network::execute path)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[wl], "points_per_gpu_per_step": n, "layout": args.layout + "-major",
+                       "result": "sum over points" if want_sum else "per-point tensor",
+                       "l2": f"{rot} rotating input sets of {bytes_in / 1e6:.0f} MB (> 126 MB L2 between reuses)",
+                       "parallelism": f"points sharded, {world} rank(s), no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": KE, "ms_per_step": e2e_ms / KE},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

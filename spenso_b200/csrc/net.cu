@@ -100,10 +100,56 @@ std::string cache_dir() {
 
 const char* kJitArch = "--gpu-architecture=sm_100a";
 
+// NVRTC is bound at run time by absolute path: a host process may already hold another libnvrtc.so.12
+// (PyTorch bundles the CUDA 12.8 one, whose ptxas rejects the 256-bit loads of PTX 8.8), and a link-time
+// dependency would silently resolve to that copy.
+struct Nvrtc {
+  void* h = nullptr;
+  int major = 0, minor = 0;
+  nvrtcResult (*Version)(int*, int*) = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+  bool has_256bit_loads() const { return major > 12 || (major == 12 && minor >= 9); }
+};
+
+Nvrtc& nvrtc() {
+  static Nvrtc n;
+  if (n.h) return n;
+  std::vector<std::string> cand;
+  if (const char* e = getenv("SPN_NVRTC")) cand.push_back(e);
+  cand.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+  cand.push_back("/usr/local/cuda/lib64/libnvrtc.so");
+  cand.push_back("libnvrtc.so.12");
+  cand.push_back("libnvrtc.so");
+  for (auto& c : cand) {
+    n.h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (n.h) break;
+  }
+  if (!n.h) throw Error(SPN_ERR_JIT, std::string("cannot load NVRTC: ") + dlerror());
+#define SPN_NVRTC_SYM(field, name)                                              \
+  n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.h, name));              \
+  if (!n.field) throw Error(SPN_ERR_JIT, std::string("NVRTC symbol missing: ") + name)
+  SPN_NVRTC_SYM(Version, "nvrtcVersion");
+  SPN_NVRTC_SYM(CreateProgram, "nvrtcCreateProgram");
+  SPN_NVRTC_SYM(CompileProgram, "nvrtcCompileProgram");
+  SPN_NVRTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+  SPN_NVRTC_SYM(GetProgramLog, "nvrtcGetProgramLog");
+  SPN_NVRTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+  SPN_NVRTC_SYM(GetCUBIN, "nvrtcGetCUBIN");
+  SPN_NVRTC_SYM(DestroyProgram, "nvrtcDestroyProgram");
+#undef SPN_NVRTC_SYM
+  n.Version(&n.major, &n.minor);
+  return n;
+}
+
 void jit_compile(JitKernel& k) {
-  int maj = 0, min = 0;
-  nvrtcVersion(&maj, &min);
-  std::string key = k.source + "|" + kJitArch + "|" + std::to_string(maj) + "." + std::to_string(min);
+  Nvrtc& rt = nvrtc();
+  std::string key = k.source + "|" + kJitArch + "|" + std::to_string(rt.major) + "." + std::to_string(rt.minor);
   char hex[32];
   std::snprintf(hex, sizeof hex, "%016llx", (unsigned long long)fnv1a(key));
   const std::string dir = cache_dir();
@@ -117,23 +163,23 @@ void jit_compile(JitKernel& k) {
     }
   }
   nvrtcProgram prog;
-  if (nvrtcCreateProgram(&prog, k.source.c_str(), (k.name + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
+  if (rt.CreateProgram(&prog, k.source.c_str(), (k.name + ".cu").c_str(), 0, nullptr, nullptr) != NVRTC_SUCCESS)
     throw Error(SPN_ERR_JIT, "nvrtcCreateProgram failed");
   const char* opts[] = {kJitArch, "-lineinfo", "--std=c++17", "--fmad=true", "-default-device"};
-  nvrtcResult r = nvrtcCompileProgram(prog, 5, opts);
+  nvrtcResult r = rt.CompileProgram(prog, 5, opts);
   if (r != NVRTC_SUCCESS) {
     size_t n = 0;
-    nvrtcGetProgramLogSize(prog, &n);
+    rt.GetProgramLogSize(prog, &n);
     std::string log(n, '\0');
-    nvrtcGetProgramLog(prog, &log[0]);
-    nvrtcDestroyProgram(&prog);
+    rt.GetProgramLog(prog, &log[0]);
+    rt.DestroyProgram(&prog);
     throw Error(SPN_ERR_JIT, "nvrtc: " + log.substr(0, 2000));
   }
   size_t n = 0;
-  nvrtcGetCUBINSize(prog, &n);
+  rt.GetCUBINSize(prog, &n);
   k.cubin.resize(n);
-  nvrtcGetCUBIN(prog, k.cubin.data());
-  nvrtcDestroyProgram(&prog);
+  rt.GetCUBIN(prog, k.cubin.data());
+  rt.DestroyProgram(&prog);
   if (use_cache) {
     mkdir(dir.c_str(), 0755);
     std::string tmp = path + ".tmp" + std::to_string((long)getpid());
@@ -188,6 +234,11 @@ struct spn_net {
   };
   std::map<std::string, Variant> variants;
   std::string default_source;
+  double2* sum_scratch = nullptr;  // per-block partials of the fused Monte-Carlo sum
+  size_t sum_scratch_elems = 0;
+  ~spn_net() {
+    if (sum_scratch) cudaFree(sum_scratch);
+  }
   // stepwise
   std::vector<std::unique_ptr<spn_tensor>> const_tensors;  // per value id (leaf consts), lazily uploaded
 
@@ -553,7 +604,7 @@ struct spn_net {
           name[(size_t)i.dst] = ln + ".x";
           name[(size_t)i.dst + 1] = ln + ".y";
           if (variant[(size_t)i.in] == 'p' || variant[(size_t)i.in] == 'q') {
-            const bool pairable = sz % 2 == 0 && variant[(size_t)i.in] == 'p';
+            const bool pairable = sz % 2 == 0 && variant[(size_t)i.in] == 'p' && nvrtc().has_256bit_loads();
             const uint64_t base = i.flat & ~1ull;
             if (pairable && live_loads.count({i.in, base}) && live_loads.count({i.in, base + 1})) {
               if (!done_pair.count({i.in, base})) {
@@ -1055,9 +1106,17 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
         (char*)out->dptr + (out->layout == SPN_POINT_MAJOR ? first_point * out->size() * eb : first_point * eb));
   }
   double2* partial = nullptr;
-  if (sum_out_device)
-    cuda_check(cudaMallocAsync((void**)&partial, (size_t)grid * size_out * sizeof(double2) + 16, ctx->stream),
-               "sum scratch");
+  if (sum_out_device) {
+    // sized for the largest grid any variant can use, allocated once (keeps execute graph-capturable)
+    const size_t want = (size_t)cap * size_out;
+    if (net->sum_scratch_elems < want) {
+      if (net->sum_scratch) cuda_check(cudaFree(net->sum_scratch), "sum scratch");
+      net->sum_scratch = nullptr;
+      cuda_check(cudaMalloc((void**)&net->sum_scratch, want * sizeof(double2)), "sum scratch");
+      net->sum_scratch_elems = want;
+    }
+    partial = net->sum_scratch;
+  }
   unsigned long long np = n_points;
   std::vector<void*> args;
   for (uint32_t i = 0; i < n_inputs; ++i) {
@@ -1076,7 +1135,6 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
                                       ctx->stream),
                "reduce_partials_kernel");
     ctx->launches++;
-    cudaFreeAsync(partial, ctx->stream);
   }
   return SPN_OK;
   NET_CATCH(false)
