@@ -210,6 +210,11 @@ uint32_t spn_net_n_inputs(const spn_net* net);
 int spn_net_schedule(const spn_net* net, int32_t* pairs, uint32_t cap);
 /* generated CUDA source of the fused kernel (NUL terminated; owned by net) */
 const char* spn_net_cuda_source(const spn_net* net);
+/* JIT (and cache) the kernel variant `key` ahead of the first execute and return its source; NULL on
+ * error.  key = one char per input ('p' point major 32-byte aligned, 'q' point major, 'c' component
+ * major), then the output ('n' none, 'p', 'c', optional 'r' = real output), then 's' if the sum over
+ * points is wanted.  Used by build() to pre-compile the benchmark kernels where no GPU exists. */
+const char* spn_net_prepare_variant(spn_net* net, const char* key);
 /* FP64 arithmetic instructions (DMUL/DADD/DFMA) per point of the compiled fused program */
 uint64_t spn_net_macs_per_point(const spn_net* net);
 /* bytes of per-point input the fused kernel actually reads (components multiplied by structural

@@ -478,6 +478,13 @@ class Network:
     def cuda_source(self) -> str:
         return (lib().spn_net_cuda_source(self.h) or b"").decode()
 
+    def prepare_variant(self, key: str) -> str:
+        """JIT + cache one kernel variant ahead of time (see spn_net_prepare_variant); returns its source."""
+        src = lib().spn_net_prepare_variant(self.h, key.encode())
+        if src is None:
+            raise SpensoError(8, lib().spn_last_error().decode(errors="replace"))
+        return src.decode()
+
     @property
     def fp64_instr_per_point(self) -> int:
         return int(lib().spn_net_macs_per_point(self.h))

@@ -1026,6 +1026,17 @@ int spn_net_schedule(const spn_net* net, int32_t* pairs, uint32_t cap) {
   return (int)c;
 }
 const char* spn_net_cuda_source(const spn_net* net) { return net->default_source.c_str(); }
+const char* spn_net_prepare_variant(spn_net* net, const char* variant) {
+  try {
+    if (!net->compiled || net->exec_mode != SPN_EXEC_FUSED) throw Error(SPN_ERR_INVALID, "not a compiled fused network");
+    std::string v = variant;
+    if (v.size() < net->n_inputs + 1) throw Error(SPN_ERR_INVALID, "variant key too short");
+    return net->get_variant(v).source.c_str();
+  } catch (const std::exception& e) {
+    spn::set_error(e.what());
+    return nullptr;
+  }
+}
 uint64_t spn_net_macs_per_point(const spn_net* net) { return net->stats.n_fp; }
 uint64_t spn_net_input_bytes_per_point(const spn_net* net) { return net->stats.n_load_bytes; }
 

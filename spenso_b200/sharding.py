@@ -1,0 +1,26 @@
+"""Multi-GPU plumbing: phase-space points are independent, so the batch is cut into contiguous blocks,
+one per rank; nothing is exchanged while the network is evaluated.  The only collective
+of the path is the final all-reduce of the Monte-Carlo partial sums (2*|out| doubles)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def shard_range(n_points: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first_point, count) of rank's block: blocks are contiguous, ordered by rank, cover [0, n_points)
+    exactly once and differ in size by at most one point (ragged totals allowed, empty blocks allowed)."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(n_points, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def allreduce_partial_sums(partial, group=None):
+    """In-place SUM all-reduce of a tensor of per-rank Monte-Carlo partial sums (torch tensor, f64;
+    NCCL over NVLink on GPUs, gloo in the CPU tests).  No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return partial
