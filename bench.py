@@ -35,8 +35,9 @@ WORKLOAD_DESC = {
             "Complex<f64>, 2^20 synthetic phase-space points per GPU",
     "cfg3": "cfg3: SU(3) colour-factor network X.T + D.f (Dense per point x Sparse shared)",
     "cfg5": "cfg5: one-loop numerator network (gl_03 topology, massive), Monte-Carlo sum",
+    "cfg4": "cfg4: dense pairwise contraction of rank-6 c64 tensors, dim-32 indices, 3 shared (ZGEMM 32768^3, FP64 DMMA)",
 }
-DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22}
+DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg4": 1}
 SCALE = {"cfg2": 1.0, "cfg3": 1.0, "cfg5": 100.0}
 
 
@@ -52,6 +53,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dim", type=int, default=32, help="cfg4: index dimension (32 = the BASELINE config)")
     return ap.parse_args()
 
 
@@ -92,6 +94,10 @@ def run_reference(args):
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload == "cfg4":
+        print(json.dumps({"impl": "reference", "unavailable": "cfg4 (16 GiB operands) has no bounded CPU arm; "
+                          "the reference arm is defined for the network workloads"}))
         return
     spec = workloads.WORKLOADS[args.workload]()
     n_threads = os.cpu_count() or 1
@@ -382,10 +388,76 @@ def run_b200(args):
     return line
 
 
+def run_cfg4(args):
+    """Config 4: ONE pairwise contraction per step through spn_tensor_contract (the Contract trait): rank-6
+    tensors with dim-d indices, three shared => complex GEMM with M = N = K = d^3 on the FP64 tensor pipe.
+    Not the headline line; reported against the cuBLAS ZGEMM throughput measured in the same run."""
+    import torch
+
+    import spenso_b200 as sp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    dev = torch.device("cuda:0")
+    d = args.dim
+    n = d ** 3
+    stream = torch.cuda.current_stream()
+    ctx = sp.Context(0, stream=stream.cuda_stream)
+    g = torch.Generator(device=dev).manual_seed(1236)
+    mk = lambda: torch.complex(torch.rand(n, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1,
+                               torch.rand(n, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
+    A, B = mk(), mk()
+    ta = sp.BatchTensor.wrap(ctx, [sp.Euclidean.new_slot(d, i) for i in (1, 2, 3, 4, 5, 6)], 1, A.data_ptr(), keepalive=A)
+    tb = sp.BatchTensor.wrap(ctx, [sp.Euclidean.new_slot(d, i) for i in (4, 5, 6, 7, 8, 9)], 1, B.data_ptr(), keepalive=B)
+    K, W = min(args.steps, 3), 3 if d < 32 else 1
+    for _ in range(W):
+        ta.contract(tb)
+    torch.cuda.synchronize()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        e0.record(stream)
+        for _ in range(K):
+            c = ta.contract(tb)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    flops = 8.0 * n * n * n
+    # denominator: cuBLAS ZGEMM measured here (best of 3), 8192^3 complex
+    m = 8192
+    X = torch.randn(m, m, dtype=torch.complex128, device=dev)
+    Y = torch.randn(m, m, dtype=torch.complex128, device=dev)
+    best = 1e30
+    for _ in range(4):
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        Z = X @ Y
+        a1.record()
+        torch.cuda.synchronize()
+        best = min(best, a0.elapsed_time(a1))
+    cublas_tf = 8.0 * m ** 3 / (best * 1e-3) / 1e12
+    achieved = flops / (ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC["cfg4"], "dim": d, "M=N=K": n,
+                   "l2": f"operands {2 * n * n * 16 / 2**30:.0f} GiB >> 126 MB L2"},
+        "gpu_launches": int(ctx.launch_count - launches0),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": cublas_tf, "unit": "TFLOP/s",
+                     "frac": achieved / cublas_tf, "traffic": None, "kernel": "contract_zgemm_kernel",
+                     "peak_source": f"cuBLAS ZGEMM {m}^3 measured in this run (FP64 tensor pipe; tcgen05 has no f64 kind)",
+                     "flops_per_eval": flops},
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg4":
+        run_cfg4(args)
     else:
         run_b200(args)
 

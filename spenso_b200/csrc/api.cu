@@ -145,6 +145,74 @@ static void check_empty_sparse(const spn_tensor* a, const spn_tensor* b, int mer
     throw Error(SPN_ERR_EMPTY_SPARSE, "Sparse tensor is empty");
 }
 
+// ---- K6 dispatch: does this dense x dense contraction reshape to a GEMM worth the tensor pipe? -------------
+struct GemmShape {
+  long long M = 1, N = 1;
+};
+static GemmShape gemm_shape(const spn_contract_plan& p) {
+  GemmShape g;
+  for (uint32_t r = 0; r < p.order_out; ++r) (p.partition[r] ? g.M : g.N) *= p.out_dim[r];
+  return g;
+}
+static bool zgemm_applicable(const spn_contract_plan& p, const spn_tensor* a, const spn_tensor* b, const spn_tensor* res,
+                             uint64_t n_points, const KTables& kt) {
+  if (getenv("SPN_NO_ZGEMM")) return false;
+  if (a->sparse() || b->sparse()) return false;
+  if (a->dtype != SPN_C64 || b->dtype != SPN_C64 || res->dtype != SPN_C64) return false;
+  if (p.n_partition != p.order_out || p.n_common == 0) return false;
+  // element stride 1 within a point (point-major batched, or shared)
+  if (a->operand().fs != 1 || b->operand().fs != 1 || res->operand().fs != 1) return false;
+  if (n_points > 65535) return false;
+  GemmShape g = gemm_shape(p);
+  return g.M >= 32 && g.N >= 32 && kt.off_a.size() >= 8 && (double)g.M * (double)g.N * (double)kt.off_a.size() >= 65536.0;
+}
+static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KTables& kt, const spn_tensor* a,
+                              const spn_tensor* b, spn_tensor* res, uint64_t n_points) {
+  GemmShape g = gemm_shape(p);
+  std::vector<uint64_t> ostride(p.order_out, 1);
+  for (uint32_t r = p.order_out; r-- > 1;) ostride[r - 1] = ostride[r] * p.out_dim[r];
+  std::vector<long long> row_a, out_row, col_b, out_col;
+  auto enumerate = [&](bool from_a, std::vector<long long>& src, std::vector<long long>& dst) {
+    std::vector<uint32_t> dims;
+    for (uint32_t r = 0; r < p.order_out; ++r)
+      if ((p.partition[r] != 0) == from_a) dims.push_back(r);
+    const long long n = from_a ? g.M : g.N;
+    src.resize((size_t)n);
+    dst.resize((size_t)n);
+    std::vector<uint32_t> idx(dims.size(), 0);
+    for (long long i = 0; i < n; ++i) {
+      long long so = 0, d0 = 0;
+      for (size_t d = 0; d < dims.size(); ++d) {
+        so += (long long)idx[d] * (long long)(from_a ? p.out_stride_a[dims[d]] : p.out_stride_b[dims[d]]);
+        d0 += (long long)idx[d] * (long long)ostride[dims[d]];
+      }
+      src[(size_t)i] = so;
+      dst[(size_t)i] = d0;
+      for (size_t d = dims.size(); d-- > 0;) {
+        if (++idx[d] < p.out_dim[dims[d]]) break;
+        idx[d] = 0;
+      }
+    }
+  };
+  enumerate(true, row_a, out_row);
+  enumerate(false, col_b, out_col);
+  std::vector<long long> k_a(kt.off_a.begin(), kt.off_a.end()), k_b(kt.off_b.begin(), kt.off_b.end());
+  std::vector<double> ks;
+  bool any_sign = false;
+  for (auto s : kt.sign) any_sign |= s != 0;
+  if (any_sign)
+    for (auto s : kt.sign) ks.push_back(s ? -1.0 : 1.0);
+  DevArray<long long> d_row_a(row_a, ctx->stream), d_out_row(out_row, ctx->stream), d_col_b(col_b, ctx->stream),
+      d_out_col(out_col, ctx->stream), d_k_a(k_a, ctx->stream), d_k_b(k_b, ctx->stream);
+  DevArray<double> d_ks(ks, ctx->stream);
+  cuda_check(launch_contract_zgemm(static_cast<const double2*>(a->dptr), static_cast<const double2*>(b->dptr),
+                                   static_cast<double2*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
+                                   d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
+                                   a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
+             "contract_zgemm_kernel");
+  ctx->launches++;
+}
+
 void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out) {
   spn_contract_plan plan = plan_contract(a->st, b->st);
   check_empty_sparse(a, b, (int)plan.merge_kind);
@@ -207,6 +275,9 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
                                    point_fastest, ctx->stream),
                "contract_csr_kernel");
     ctx->launches++;
+  } else if (zgemm_applicable(plan, a, b, res.get(), n_points, kt)) {
+    // K6: the contraction reshapes to a complex GEMM large enough for the FP64 tensor pipe
+    launch_zgemm_path(ctx, plan, kt, a, b, res.get(), n_points);
   } else {
     // K1/K5/K7 (and sparse x sparse over the densified shared copies; the structural/zero
     // filter of the sparse result is applied below)

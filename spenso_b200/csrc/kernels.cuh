@@ -47,6 +47,15 @@ cudaError_t launch_contract_csr(DevOperand dense, DevOut out, const int* row_ptr
                                 unsigned long long size_out, unsigned long long nnz, unsigned long long n_points,
                                 bool point_fastest, cudaStream_t stream);
 
+// K6: dense x dense contraction that reshapes to a complex GEMM, on the FP64 tensor pipe (DMMA):
+//   C[out_row[r] + out_col[c]] = sum_k sign[k] A[row_a[r] + k_a[k]] B[col_b[c] + k_b[k]]   (zgemm.cu)
+// ksign: +-1.0 per k or nullptr; ps_*: point strides in elements (0 for a shared operand).
+cudaError_t launch_contract_zgemm(const double2* A, const double2* B, double2* C, const long long* row_a,
+                                  const long long* k_a, const long long* col_b, const long long* k_b,
+                                  const long long* out_row, const long long* out_col, const double* ksign,
+                                  long long M, long long N, long long K, long long ps_a, long long ps_b,
+                                  long long ps_c, unsigned long long n_points, cudaStream_t stream);
+
 // element-wise (algebra/add_assign.rs, sub_assign.rs, neg.rs, scalar_mul.rs; FUN_LIB conj)
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2, EW_SCALE = 3, EW_CONJ = 4, EW_COPY = 5, EW_RECIP = 6 };
 cudaError_t launch_elementwise(int op, DevOperand a, DevOperand b, DevOut out, double2 scalar,

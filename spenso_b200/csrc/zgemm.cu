@@ -1,0 +1,217 @@
+// Dense x dense pairwise contraction that genuinely reshapes to a complex GEMM (BASELINE config 4:
+// rank-6, dim-32 tensors over three shared indices = ZGEMM 32768^3) on the FP64 tensor pipe.
+//
+//   C[out_row[r] + out_col[c]] = sum_k sign[k] * A[row_a[r] + k_a[k]] * B[col_b[c] + k_b[k]]
+//
+// is the same sum the reference's MultiContract / SingleContract kernels compute
+// (/root/reference/spenso/src/contraction/multicontract.rs:25-78, singlecontract.rs:25-76); the offset
+// tables come from the stride plan of the merge (spn_plan_contract), so every MergeInfo — including
+// interleaved results and transposed operands — goes through this one kernel: tiles are GATHERED through
+// the tables with 16-byte cp.async (contiguous runs of the tables give coalesced 128-byte segments).
+//
+// sm_100a notes: tcgen05.mma has no f64 kind, so the FP64 tensor path is the warp-level DMMA
+// (mma.sync.aligned.m8n8k4.f64).  CTA tile 64x64 complex, 4 warps of 32x32, BK = 8, 4-stage cp.async
+// pipeline, operands kept interleaved (re,im) in shared memory and read as 128-bit fragments with
+// conflict-free strides (A: 12, B: 66 sixteen-byte units); a complex tile product is 4 real DMMAs
+// (rr, -ii, ri, ir).  Grouped rasterisation keeps an 8-tile-tall band of A resident in L2.
+#include "kernels.cuh"
+
+namespace spn {
+
+namespace {
+
+typedef long long ll;
+typedef unsigned long long ull;
+
+constexpr int BM = 64, BN = 64, BK = 8, STAGES = 4;
+constexpr int SA = BK + 4;   // row stride of the A tile in double2 units (== 4 mod 8)
+constexpr int SB = BN + 2;   // row stride of the B tile in double2 units (== 2 mod 8)
+constexpr int GROUP_M = 8;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int bytes = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <bool SIGN>
+__global__ void __launch_bounds__(128, 2)
+contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ C,
+                      const ll* __restrict__ row_a, const ll* __restrict__ k_a, const ll* __restrict__ col_b,
+                      const ll* __restrict__ k_b, const ll* __restrict__ out_row, const ll* __restrict__ out_col,
+                      const double* __restrict__ ksign, ll M, ll N, ll K, ll ps_a, ll ps_b, ll ps_c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2* As = reinterpret_cast<double2*>(smem_raw);          // [STAGES][BM][SA]
+  double2* Bs = As + STAGES * BM * SA;                          // [STAGES][BK][SB]
+  ll* s_row = reinterpret_cast<ll*>(Bs + STAGES * BK * SB);     // [BM] offsets of this tile's rows in A
+  ll* s_col = s_row + BM;                                       // [BN] offsets of this tile's columns in B
+
+  // grouped rasterisation: consecutive CTAs walk GROUP_M row tiles before moving to the next column tile
+  const ll tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const ll pid = blockIdx.x;
+  const ll group = pid / (GROUP_M * tiles_n);
+  const ll first_m = group * GROUP_M;
+  const ll gsz = min((ll)GROUP_M, tiles_m - first_m);
+  const ll tile_m = first_m + (pid % (GROUP_M * tiles_n)) % gsz;
+  const ll tile_n = (pid % (GROUP_M * tiles_n)) / gsz;
+  const ll m0 = tile_m * BM, n0 = tile_n * BN;
+  const ll p = blockIdx.y;
+  A += p * ps_a;
+  B += p * ps_b;
+  C += p * ps_c;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  if (tid < BM) s_row[tid] = (m0 + tid < M) ? __ldg(row_a + m0 + tid) : -1;
+  if (tid >= 64 && tid < 64 + BN) s_col[tid - 64] = (n0 + tid - 64 < N) ? __ldg(col_b + n0 + tid - 64) : -1;
+  __syncthreads();
+
+  // loader assignment: A tile 64 rows x 8 k -> 4 elements per thread (k fastest across threads);
+  //                    B tile 8 k x 64 n   -> 4 elements per thread (n fastest across threads)
+  const int a_kk = tid & 7, a_r0 = tid >> 3;        // rows a_r0 + 16 i
+  const int b_n = tid & 63, b_k0 = tid >> 6;        // k rows b_k0 + 2 i
+  const ll KT = (K + BK - 1) / BK;
+
+  auto load_tile = [&](int stage, ll kt) {
+    const ll kbase = kt * BK;
+    double2* as = As + stage * BM * SA;
+    double2* bs = Bs + stage * BK * SB;
+    {
+      const ll k = kbase + a_kk;
+      const bool kv = k < K;
+      const ll koff = kv ? __ldg(k_a + k) : 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = a_r0 + 16 * i;
+        const ll ro = s_row[r];
+        const bool v = kv && ro >= 0;
+        cp_async16(as + r * SA + a_kk, A + (v ? ro + koff : 0), v);
+      }
+    }
+    {
+      const ll co = s_col[b_n];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int kk = b_k0 + 2 * i;
+        const ll k = kbase + kk;
+        const bool v = k < K && co >= 0;
+        const ll koff = (k < K) ? __ldg(k_b + k) : 0;
+        cp_async16(bs + kk * SB + b_n, B + (v ? co + koff : 0), v);
+      }
+    }
+  };
+
+  double cr[4][4][2], ci[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT) load_tile(s, s);
+    cp_async_commit();
+  }
+
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row (or column) and k position of this lane
+  for (ll kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const ll nxt = kt + STAGES - 1;
+      if (nxt < KT) load_tile((int)(nxt % STAGES), nxt);
+      cp_async_commit();
+    }
+    const int stage = (int)(kt % STAGES);
+    const double2* as = As + stage * BM * SA;
+    const double2* bs = Bs + stage * BK * SB;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double2 a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = as[(wm + 8 * i + fr) * SA + k4 * 4 + fk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bs[(k4 * 4 + fk) * SB + wn + 8 * j + fr];
+      if (SIGN) {
+        const ll k = kt * BK + k4 * 4 + fk;
+        const double sg = (k < K) ? __ldg(ksign + k) : 1.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          a[i].x *= sg;
+          a[i].y *= sg;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double nai = -a[i].y;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+          dmma884(cr[i][j][0], cr[i][j][1], nai, b[j].y);
+          dmma884(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
+          dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: lane holds C[row = lane/4][cols 2*(lane%4), +1] of every 8x8 tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const ll r = m0 + wm + 8 * i + fr;
+    if (r >= M) continue;
+    const ll orow = __ldg(out_row + r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const ll c = n0 + wn + 8 * j + 2 * fk + e;
+        if (c < N) C[orow + __ldg(out_col + c)] = make_double2(cr[i][j][e], ci[i][j][e]);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t zgemm_smem_bytes() {
+  return (size_t)STAGES * (BM * SA + BK * SB) * sizeof(double2) + (BM + BN) * sizeof(long long);
+}
+
+cudaError_t launch_contract_zgemm(const double2* A, const double2* B, double2* C, const long long* row_a,
+                                  const long long* k_a, const long long* col_b, const long long* k_b,
+                                  const long long* out_row, const long long* out_col, const double* ksign,
+                                  long long M, long long N, long long K, long long ps_a, long long ps_b,
+                                  long long ps_c, unsigned long long n_points, cudaStream_t stream) {
+  if (M == 0 || N == 0 || n_points == 0) return cudaSuccess;
+  const ll tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  if (tiles > 0x7fffffffLL || n_points > 65535) return cudaErrorInvalidConfiguration;
+  const size_t smem = zgemm_smem_bytes();
+  dim3 grid((unsigned)tiles, (unsigned)n_points);
+  cudaError_t e;
+  if (ksign) {
+    e = cudaFuncSetAttribute(contract_zgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    contract_zgemm_kernel<true><<<grid, 128, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, ksign, M,
+                                                            N, K, ps_a, ps_b, ps_c);
+  } else {
+    e = cudaFuncSetAttribute(contract_zgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    contract_zgemm_kernel<false><<<grid, 128, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, nullptr,
+                                                             M, N, K, ps_a, ps_b, ps_c);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace spn

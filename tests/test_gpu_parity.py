@@ -359,3 +359,100 @@ def test_cfg2_full_size_properties(ctx):
     idx = np.random.default_rng(0).choice(n, 2000, replace=False)
     ref, _, _ = O.eval_spec(spec, [a[idx] for a in arrays])
     assert rel_err(base[idx], ref[:, 0]) <= TOL
+
+
+# ---- K6: contractions that reshape to a complex GEMM (FP64 DMMA kernel, zgemm.cu) ---------------------------
+GEMM_CASES = [
+    # (slots a, slots b) in argument order; all large enough to take the tensor-pipe path
+    ((("euc", 8, 1), ("euc", 8, 2), ("euc", 6, 3), ("euc", 6, 4)), (("euc", 6, 3), ("euc", 6, 4), ("euc", 9, 5), ("euc", 8, 6))),
+    # interleaved result + Minkowski metric signs on two contracted indices, ragged tile edges
+    ((("mink", 4, 1), ("mink", 4, 2), ("euc", 16, 3), ("euc", 5, 9)), (("mink", 4, 1), ("mink", 4, 2), ("euc", 8, 4), ("euc", 7, 6))),
+    # dualizable pair contracted, second-before-first ordering of the result
+    ((("lor", 12, 1), ("euc", 40, 7)), (("lor_d", 12, 1), ("euc", 6, 2), ("euc", 7, 3))),
+    # single contracted index, K = 64 (SingleContract shape)
+    ((("euc", 64, 1), ("bis", 33, 2)), (("euc", 64, 1), ("coad", 35, 3))),
+    # cfg4 in miniature: rank-6 tensors, three shared indices (dim 6 -> M = N = K = 216)
+    (tuple(("euc", 6, i) for i in (1, 2, 3, 4, 5, 6)), tuple(("euc", 6, i) for i in (4, 5, 6, 7, 8, 9))),
+]
+
+
+@pytest.mark.parametrize("case", range(len(GEMM_CASES)))
+@pytest.mark.parametrize("n_points", [1, 3])
+def test_zgemm_path_vs_oracle(ctx, case, n_points):
+    rng = np.random.default_rng(500 + case)
+    a, b = (O.slots(*x) for x in GEMM_CASES[case])
+    ta, oa, _ = dense_pair(ctx, rng, a, n_points)
+    tb, ob, _ = dense_pair(ctx, rng, b, n_points)
+    before = ctx.launch_count
+    c = ta.contract(tb)
+    assert ctx.launch_count == before + 1
+    refs = [x.contract(y) for x, y in zip(oa, ob)]
+    assert c.slots.tobytes() == refs[0].slots.tobytes()
+    want = np.stack([r.to_dense() for r in refs])
+    got = c.to_numpy()
+    assert rel_err(got, want) <= TOL
+    # and the shared (single point) form of the same contraction
+    if n_points == 1:
+        ca, cb = O.order_structure(a)[0], O.order_structure(b)[0]
+        sa = sp.DenseTensor.from_data(ctx, ca, oa[0].to_dense())
+        sb = sp.DenseTensor.from_data(ctx, cb, ob[0].to_dense())
+        assert rel_err(sa.contract(sb).to_numpy(), want[0]) <= TOL
+
+
+def test_cfg4_full_size_rank6_dim32(ctx):
+    """BASELINE config 4 at full size: A, B in C^{32^6} (16 GiB each), three shared indices = ZGEMM 32768^3.
+    Checked through size-independent properties: a rank-one closed form for the whole result, and sampled
+    rows of a random contraction against cuBLAS (torch.matmul) — both checks are test infrastructure."""
+    import torch
+
+    free, total = torch.cuda.mem_get_info()
+    if free < 120 * 2 ** 30:
+        pytest.skip("needs ~100 GiB of free HBM")
+    d, n = 32, 32 ** 3
+    dev = torch.device("cuda:0")
+    sa = [sp.Euclidean.new_slot(d, i) for i in (1, 2, 3, 4, 5, 6)]
+    sb = [sp.Euclidean.new_slot(d, i) for i in (4, 5, 6, 7, 8, 9)]
+    g = torch.Generator(device=dev).manual_seed(1236)
+
+    def rnd(*shape):
+        return torch.complex(torch.rand(*shape, generator=g, device=dev, dtype=torch.float64) * 2 - 1,
+                             torch.rand(*shape, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
+
+    # (1) rank-one operands: A = x y^T, B = z w^T  =>  C = (y.z) x w^T
+    x, y, z, w = rnd(n), rnd(n), rnd(n), rnd(n)
+    A = torch.outer(x, y).contiguous()
+    B = torch.outer(z, w).contiguous()
+    ta = sp.BatchTensor.wrap(ctx, sa, 1, A.data_ptr(), keepalive=A)
+    tb = sp.BatchTensor.wrap(ctx, sb, 1, B.data_ptr(), keepalive=B)
+    c = ta.contract(tb)
+    ctx.synchronize()
+    assert [int(v) for v in c.slots["aind"]] == [1, 2, 3, 7, 8, 9] and c.size == n * n
+    import ctypes
+
+    # view the engine's result buffer as a torch tensor (no copy): cudaMemcpy D2D into a torch allocation
+    C = torch.empty((n, n), dtype=torch.complex128, device=dev)
+    torch.cuda.synchronize()
+    rt = ctypes.CDLL("libcudart.so.12")
+    assert rt.cudaMemcpy(ctypes.c_void_p(C.data_ptr()), ctypes.c_void_p(c.device_ptr), ctypes.c_size_t(n * n * 16), 3) == 0
+    del c
+    yz = torch.dot(y, z)          # bilinear (no conjugation)
+    err = 0.0
+    scale = float((yz.abs() * x.abs().max() * w.abs().max()).item())
+    for r0 in range(0, n, 4096):
+        want = yz * torch.outer(x[r0:r0 + 4096], w)
+        err = max(err, float((C[r0:r0 + 4096] - want).abs().max().item()))
+    assert err <= 1e-12 * scale
+    del A, B, ta, tb
+    # (2) random full-rank operands, sampled rows vs cuBLAS
+    A = rnd(n, n)
+    B = rnd(n, n)
+    ta = sp.BatchTensor.wrap(ctx, sa, 1, A.data_ptr(), keepalive=A)
+    tb = sp.BatchTensor.wrap(ctx, sb, 1, B.data_ptr(), keepalive=B)
+    c = ta.contract(tb)
+    ctx.synchronize()
+    assert rt.cudaMemcpy(ctypes.c_void_p(C.data_ptr()), ctypes.c_void_p(c.device_ptr), ctypes.c_size_t(n * n * 16), 3) == 0
+    del c
+    rows = torch.randint(0, n, (48,), generator=torch.Generator().manual_seed(1)).to(dev)
+    want = A[rows] @ B
+    got = C[rows]
+    assert float((got - want).abs().max().item()) <= 1e-12 * float(want.abs().max().item())
