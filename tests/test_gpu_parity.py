@@ -456,3 +456,53 @@ def test_cfg4_full_size_rank6_dim32(ctx):
     want = A[rows] @ B
     got = C[rows]
     assert float((got - want).abs().max().item()) <= 1e-12 * float(want.abs().max().item())
+
+
+# ---- f64 data tensors (RealOrComplexTensor::Real, tensors/complex.rs:66-69, 674-690) -------------------------------
+def test_real_tensors_upgrade_like_the_reference(ctx):
+    """Real x Real stays real, Real x Complex upgrades f64 -> (x, 0.0) before the complex product
+    (upgrading_arithmetic.rs:1285-1293); values must equal the oracle's on the embedded complex data."""
+    rng = np.random.default_rng(77)
+    n = 6
+    a_sl = O.order_structure(O.slots(("mink", 4, 1), ("bis", 4, 2)))[0]
+    b_sl = O.order_structure(O.slots(("mink", 4, 1), ("bis", 4, 3)))[0]
+    ra = rng.uniform(-1, 1, size=(n, 16))
+    rb = rng.uniform(-1, 1, size=(n, 16))
+    cb = _cases.random_complex(rng, (n, 16))
+    for layout in (sp.POINT_MAJOR, sp.COMPONENT_MAJOR):
+        ta = sp.BatchTensor.empty(ctx, a_sl, n, sp.F64, layout)
+        ta.upload(ra)
+        tb = sp.BatchTensor.empty(ctx, b_sl, n, sp.F64, layout)
+        tb.upload(rb)
+        tc = sp.BatchTensor.empty(ctx, b_sl, n, sp.C64, layout)
+        tc.upload(cb)
+        rr = ta.contract(tb)
+        rc = ta.contract(tc)
+        cr = tc.contract(ta)
+        assert rr.dtype == sp.F64 and rc.dtype == sp.C64 and cr.dtype == sp.C64
+        o = lambda sl, d: [O.OTensor.dense(sl, d[p].astype(complex), canonicalize=False) for p in range(n)]
+        oa, ob, oc = o(a_sl, ra), o(b_sl, rb), o(b_sl, cb)
+        want_rr = np.stack([x.contract(y).to_dense() for x, y in zip(oa, ob)])
+        want_rc = np.stack([x.contract(y).to_dense() for x, y in zip(oa, oc)])
+        want_cr = np.stack([y.contract(x).to_dense() for x, y in zip(oa, oc)])
+        assert (rr.to_numpy() == want_rr.real).all() and not want_rr.imag.any()
+        assert (rc.to_numpy() == want_rc).all()
+        assert (cr.to_numpy() == want_cr).all()
+        assert ((ta + tb.contract(tb).contract(ta) if False else ta).to_numpy() == ra.reshape(n, 4, 4)).all()
+    # fused network on f64 inputs: p.q with the Minkowski metric, result written as f64 and as c64
+    net = sp.Network(ctx)
+    p = net.batched([sp.Minkowski.new_slot(4, 1)], sp.F64)
+    q = net.batched([sp.Minkowski.new_slot(4, 1)], sp.F64)
+    net.set_root(net.product(p, q))
+    net.compile(sp.FUSED)
+    P, Q = rng.uniform(-1, 1, size=(n, 4)), rng.uniform(-1, 1, size=(n, 4))
+    tp = sp.BatchTensor.empty(ctx, [sp.Minkowski.new_slot(4, 1)], n, sp.F64)
+    tq = sp.BatchTensor.empty(ctx, [sp.Minkowski.new_slot(4, 1)], n, sp.F64)
+    tp.upload(P)
+    tq.upload(Q)
+    want = P[:, 0] * Q[:, 0] - (P[:, 1:] * Q[:, 1:]).sum(axis=1)
+    for dt in (sp.F64, sp.C64):
+        out = sp.BatchTensor.empty(ctx, net.result_slots, n, dt)
+        net.execute([tp, tq], out)
+        ctx.synchronize()
+        assert rel_err(out.to_numpy().reshape(-1).real, want) <= 1e-14
