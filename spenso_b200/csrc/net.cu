@@ -290,12 +290,23 @@ struct spn_net {
   // values do not depend on it, so we are free to choose: contract the connected pair
   // with the smallest result (ties: point-independent pairs first — they cost nothing per point —
   // then fewest multiply-adds); unconnected factors (scalars first) are multiplied in last.
+  // With trial > 0 (fused compiler's schedule search) the choice among near-cheapest connected pairs is
+  // randomised by a deterministic LCG; the trial whose generated kernel has the fewest FP64 instructions wins.
+  uint64_t rng_state = 0;
+  int trial = 0;
+  double rnd() {
+    rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
+    return (double)(rng_state >> 11) / 9007199254740992.0;
+  }
   int schedule_product(std::vector<int> vals) {
     if (vals.empty()) throw Error(SPN_ERR_INVALID, "empty product");
+    struct Cand {
+      size_t i, j;
+      std::array<double, 3> cost;
+    };
     while (vals.size() > 1) {
       size_t bi = 0, bj = 1;
-      bool found = false;
-      std::array<double, 3> best{};
+      std::vector<Cand> cands;
       for (size_t i = 0; i < vals.size(); ++i)
         for (size_t j = i + 1; j < vals.size(); ++j) {
           const Structure &A = values[vals[i]].st, &B = values[vals[j]].st;
@@ -303,16 +314,28 @@ struct spn_net {
           if (nc == 0) continue;
           spn_contract_plan p = plan_contract(A, B);
           bool free_pair = !values[vals[i]].batched && !values[vals[j]].batched;
-          std::array<double, 3> cost{(double)p.size_out, free_pair ? 0.0 : 1.0,
-                                     (double)p.size_out * (double)p.n_contracted};
-          if (!found || cost < best) {
-            best = cost;
-            bi = i;
-            bj = j;
-            found = true;
-          }
+          cands.push_back({i, j, {(double)p.size_out, free_pair ? 0.0 : 1.0, (double)p.size_out * (double)p.n_contracted}});
         }
-      if (!found) {
+      if (!cands.empty()) {
+        std::stable_sort(cands.begin(), cands.end(), [](const Cand& x, const Cand& y) { return x.cost < y.cost; });
+        size_t pick = 0;
+        if (trial > 0) {
+          // candidates whose result is at most 8x the smallest one, plus every point-independent pair (free per
+          // point whatever its size); earlier (cheaper) ones more likely
+          std::stable_partition(cands.begin(), cands.end(), [&](const Cand& c) {
+            return c.cost[0] <= 8.0 * cands[0].cost[0] || (c.cost[1] == 0.0 && c.cost[0] <= 4096.0);
+          });
+          const double lim = cands[0].cost[0];
+          size_t n_ok = 0;
+          while (n_ok < cands.size() && (cands[n_ok].cost[0] <= 8.0 * lim || (cands[n_ok].cost[1] == 0.0 && cands[n_ok].cost[0] <= 4096.0))) ++n_ok;
+          if (n_ok == 0) n_ok = 1;
+          double r = rnd();
+          pick = (size_t)(r * r * (double)n_ok);
+          if (pick >= n_ok) pick = n_ok - 1;
+        }
+        bi = cands[pick].i;
+        bj = cands[pick].j;
+      } else {
         // outer product of the two smallest factors
         std::vector<size_t> idx(vals.size());
         for (size_t i = 0; i < idx.size(); ++i) idx[i] = i;
@@ -988,11 +1011,43 @@ int spn_net_compile(spn_net* net, int exec_mode) {
   if (net->root < 0) throw Error(SPN_ERR_INVALID, "network has no root");
   if (exec_mode != SPN_EXEC_FUSED && exec_mode != SPN_EXEC_STEPWISE) throw Error(SPN_ERR_INVALID, "unknown exec mode");
   net->exec_mode = exec_mode;
-  std::map<int, int> memo;
-  net->result_value = net->build(net->root, memo);
+  const size_t n_nodes0 = net->nodes.size();
+  auto build_with = [&](int trial) {
+    net->nodes.resize(n_nodes0);  // drop constants appended by a previous trial
+    net->values.clear();
+    net->steps.clear();
+    net->schedule.clear();
+    net->prog = Program();
+    net->result_el.clear();
+    net->trial = trial;
+    net->rng_state = 0x9e3779b97f4a7c15ull * (uint64_t)(trial + 1);
+    std::map<int, int> memo;
+    net->result_value = net->build(net->root, memo);
+    if (exec_mode == SPN_EXEC_FUSED) net->compile_fused();
+  };
+  build_with(0);
+  if (exec_mode == SPN_EXEC_FUSED) {
+    // schedule search: the objective is the instruction count of the kernel that would be generated
+    int trials = 256;
+    if (const char* e = getenv("SPN_SCHEDULE_TRIALS")) trials = atoi(e);
+    int best_trial = 0;
+    auto key = [&]() { return std::make_pair(net->stats.n_fp, net->stats.n_load_bytes); };
+    auto best = key();
+    for (int t = 1; t <= trials && best.first > 0; ++t) {
+      try {
+        build_with(t);
+      } catch (const Error&) {
+        continue;  // e.g. an intermediate too large for the fused executor under this order
+      }
+      if (key() < best) {
+        best = key();
+        best_trial = t;
+      }
+    }
+    build_with(best_trial);
+  }
   net->const_tensors.resize(net->values.size());
   if (exec_mode == SPN_EXEC_FUSED) {
-    net->compile_fused();
     JitKernel& k = net->get_variant(net->default_variant(false));
     net->default_source = k.source;
   }
