@@ -391,39 +391,65 @@ def run_b200(args):
 def run_cfg4(args):
     """Config 4: ONE pairwise contraction per step through spn_tensor_contract (the Contract trait): rank-6
     tensors with dim-d indices, three shared => complex GEMM with M = N = K = d^3 on the FP64 tensor pipe.
-    Not the headline line; reported against the cuBLAS ZGEMM throughput measured in the same run."""
+    N > 1: the first free index of A (rows of A and C) is cut into N blocks, B is replicated, no collective
+     => strong scaling.  Not the headline line; reported against the cuBLAS ZGEMM throughput
+    measured in the same run."""
     import torch
+    import torch.distributed as dist
 
     import spenso_b200 as sp
+    from spenso_b200.sharding import shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device")
-    dev = torch.device("cuda:0")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
     d = args.dim
     n = d ** 3
+    first, d1 = shard_range(d, rank, world)        # this rank's block of the first index of A
+    rows = d1 * d * d
     stream = torch.cuda.current_stream()
-    ctx = sp.Context(0, stream=stream.cuda_stream)
+    ctx = sp.Context(local_rank, stream=stream.cuda_stream)
     g = torch.Generator(device=dev).manual_seed(1236)
-    mk = lambda: torch.complex(torch.rand(n, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1,
-                               torch.rand(n, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
-    A, B = mk(), mk()
-    ta = sp.BatchTensor.wrap(ctx, [sp.Euclidean.new_slot(d, i) for i in (1, 2, 3, 4, 5, 6)], 1, A.data_ptr(), keepalive=A)
+    mk = lambda r: torch.complex(torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1,
+                                 torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
+    B = mk(n)                                       # same seed on every rank: B is replicated
+    A = mk(max(rows, 1))
+    sa = [sp.Euclidean.new_slot(d1 if i == 1 else d, i) for i in (1, 2, 3, 4, 5, 6)]
+    ta = sp.BatchTensor.wrap(ctx, sa, 1, A.data_ptr(), keepalive=A)
     tb = sp.BatchTensor.wrap(ctx, [sp.Euclidean.new_slot(d, i) for i in (4, 5, 6, 7, 8, 9)], 1, B.data_ptr(), keepalive=B)
     K, W = min(args.steps, 3), 3 if d < 32 else 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for _ in range(W):
         ta.contract(tb)
-    torch.cuda.synchronize()
+    barrier()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(0) as clocks:
+    with ClockSampler(local_rank) as clocks:
+        barrier()
         e0.record(stream)
         for _ in range(K):
             c = ta.contract(tb)
         e1.record(stream)
-        torch.cuda.synchronize()
+        barrier()
     ms = e0.elapsed_time(e1) / K
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     flops = 8.0 * n * n * n
-    # denominator: cuBLAS ZGEMM measured here (best of 3), 8192^3 complex
+    del c
+    # denominator: cuBLAS ZGEMM measured here (best of 4), 8192^3 complex
     m = 8192
     X = torch.randn(m, m, dtype=torch.complex128, device=dev)
     Y = torch.randn(m, m, dtype=torch.complex128, device=dev)
@@ -436,20 +462,25 @@ def run_cfg4(args):
         torch.cuda.synchronize()
         best = min(best, a0.elapsed_time(a1))
     cublas_tf = 8.0 * m ** 3 / (best * 1e-3) / 1e12
-    achieved = flops / (ms * 1e-3) / 1e12
-    line = {
-        "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_DESC["cfg4"], "dim": d, "M=N=K": n,
-                   "l2": f"operands {2 * n * n * 16 / 2**30:.0f} GiB >> 126 MB L2"},
-        "gpu_launches": int(ctx.launch_count - launches0),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": cublas_tf, "unit": "TFLOP/s",
-                     "frac": achieved / cublas_tf, "traffic": None, "kernel": "contract_zgemm_kernel",
-                     "peak_source": f"cuBLAS ZGEMM {m}^3 measured in this run (FP64 tensor pipe; tcgen05 has no f64 kind)",
-                     "flops_per_eval": flops},
-        "clocks": clocks.summary(),
-    }
-    print(json.dumps(line), flush=True)
+    achieved = flops / world / (ms * 1e-3) / 1e12      # per GPU
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC["cfg4"], "dim": d, "M=N=K": n,
+                       "l2": f"operands {2 * n * n * 16 / 2**30:.0f} GiB >> 126 MB L2",
+                       "parallelism": f"rows of A/C cut into {world} block(s), B replicated, no collective"},
+            "gpu_launches": int(ctx.launch_count - launches0),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": cublas_tf, "unit": "TFLOP/s",
+                         "frac": achieved / cublas_tf, "traffic": None, "kernel": "contract_zgemm_kernel",
+                         "peak_source": f"cuBLAS ZGEMM {m}^3 measured in this run (FP64 tensor pipe; tcgen05 has no f64 kind)",
+                         "flops_per_eval": flops, "per_gpu": True},
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

@@ -242,7 +242,8 @@ struct spn_net {
   // stepwise
   std::vector<std::unique_ptr<spn_tensor>> const_tensors;  // per value id (leaf consts), lazily uploaded
 
-  static constexpr int kBlock = 128;
+  int kBlock = getenv("SPN_BLOCK") ? atoi(getenv("SPN_BLOCK")) : 128;  // threads per CTA of the fused kernels
+  int kMinBlocks = getenv("SPN_MIN_BLOCKS") ? atoi(getenv("SPN_MIN_BLOCKS")) : 0;
   static constexpr uint64_t kMaxFusedElems = 1u << 16;
 
   // ---- graph -> schedule ----------------------------------------------------------------------
@@ -596,13 +597,11 @@ struct spn_net {
     o << "__device__ __forceinline__ double ld8(const double* p) { return __ldg(p); }\n";
     o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
          "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
-    o << "extern \"C\" __global__ void __launch_bounds__(" << kBlock << ") " << kname << "(";
+    o << "extern \"C\" __global__ void __launch_bounds__(" << kBlock << (kMinBlocks ? ", " + std::to_string(kMinBlocks) : std::string()) << ") " << kname << "(";
     for (uint32_t k = 0; k < n_inputs; ++k) o << "const double* __restrict__ in" << k << ", ull cs" << k << ", ";
     o << "double* __restrict__ out, ull ocs, double2* __restrict__ block_sums, ull n_points) {\n";
     if (want_sum)
       for (uint64_t c = 0; c < size_out; ++c) o << "  double sr" << c << " = 0.0, si" << c << " = 0.0;\n";
-    o << "  for (ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << kBlock
-      << ") {\n";
     // value names
     std::vector<std::string> name((size_t)prog.n_vals);
     auto vname = [&](int v) -> const std::string& { return name[(size_t)v]; };
@@ -614,52 +613,89 @@ struct spn_net {
     };
     // 256-bit loads: pair (flat, flat+1) of a point-major complex input when flat is even, the
     // tensor has an even number of components (=> 32-byte aligned) and both are live
-    std::set<std::pair<int, uint64_t>> live_loads;
+    std::map<std::pair<int, uint64_t>, int> load_dst;
     for (auto& i : prog.ins)
-      if (i.op == I_LOADC) live_loads.insert({i.in, i.flat});
+      if (i.op == I_LOADC) load_dst[{i.in, i.flat}] = i.dst;
     std::set<std::pair<int, uint64_t>> done_pair;
+    // one load statement: `pre` is the variable prefix ("l" current point, "n" prefetched next point),
+    // `decl` says whether the statement also declares its variables
+    auto emit_load = [&](std::ostream& os, const Ins& i, const std::string& pv, const std::string& pre, bool decl) {
+      const Node& n = nodes[input_nodes[(size_t)i.in]];
+      const uint64_t sz = n.st.size();
+      const char lay = variant[(size_t)i.in];
+      if (i.op == I_LOADR) {
+        os << (decl ? "const double " : "") << pre << i.dst << " = ld8(in" << i.in;
+        if (lay != 'c')
+          os << " + " << pv << " * " << sz << "ull + " << i.flat << "ull);\n";
+        else
+          os << " + " << i.flat << "ull * cs" << i.in << " + " << pv << ");\n";
+        return;
+      }
+      const std::string ln = pre + std::to_string(i.dst);
+      if (lay == 'c') {
+        os << (decl ? "const double2 " : "") << ln << " = ld16(in" << i.in << " + (" << i.flat << "ull * cs" << i.in << " + "
+           << pv << ") * 2);\n";
+        return;
+      }
+      const bool pairable = sz % 2 == 0 && lay == 'p' && nvrtc().has_256bit_loads();
+      const uint64_t base = i.flat & ~1ull;
+      if (pairable && load_dst.count({i.in, base}) && load_dst.count({i.in, base + 1})) {
+        if (done_pair.count({i.in, base})) return;  // emitted together with its partner
+        done_pair.insert({i.in, base});
+        const std::string a = pre + std::to_string(load_dst[{i.in, base}]), b = pre + std::to_string(load_dst[{i.in, base + 1}]);
+        if (decl) os << "double2 " << a << ", " << b << "; ";
+        os << "ld32(in" << i.in << " + (" << pv << " * " << sz << "ull + " << base << "ull) * 2, " << a << ", " << b << ");\n";
+      } else {
+        os << (decl ? "const double2 " : "") << ln << " = ld16(in" << i.in << " + (" << pv << " * " << sz << "ull + " << i.flat
+           << "ull) * 2);\n";
+      }
+    };
+    // Compute-heavy networks (FP64 time per point comparable to its HBM time) run at low occupancy (many live
+    // registers), so the input loads of the NEXT point are issued before the arithmetic of the current one.
+    const double t_fp = (double)stats.n_fp / (64.0 * 148.0 * 1.9e9), t_hbm = (double)(stats.n_load_bytes + (out_mode == 'n' ? 0 : 16 * size_out)) / 6.5e12;
+    const bool prefetch = stats.n_load_bytes > 0 && stats.n_load_bytes <= 512 && t_fp > 0.5 * t_hbm && !getenv("SPN_NO_PREFETCH");
+    for (const Ins& i : prog.ins) {
+      if (i.op == I_LOADC) {
+        name[(size_t)i.dst] = "l" + std::to_string(i.dst) + ".x";
+        name[(size_t)i.dst + 1] = "l" + std::to_string(i.dst) + ".y";
+      } else if (i.op == I_LOADR) {
+        name[(size_t)i.dst] = "l" + std::to_string(i.dst);
+      }
+    }
+    if (prefetch) {
+      o << "  ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x;\n  const ull stride = (ull)gridDim.x * " << kBlock << ";\n";
+      for (const Ins& i : prog.ins) {
+        if (i.op == I_LOADC) o << "  double2 l" << i.dst << " = make_double2(0.0, 0.0), n" << i.dst << " = make_double2(0.0, 0.0);\n";
+        if (i.op == I_LOADR) o << "  double l" << i.dst << " = 0.0, n" << i.dst << " = 0.0;\n";
+      }
+      o << "  if (p < n_points) {\n";
+      for (const Ins& i : prog.ins)
+        if (i.op == I_LOADC || i.op == I_LOADR) {
+          std::ostringstream t;
+          emit_load(t, i, "p", "l", false);
+          if (!t.str().empty()) o << "    " << t.str();
+        }
+      done_pair.clear();
+      o << "  }\n  for (; p < n_points; p += stride) {\n    const ull pn = p + stride;\n    if (pn < n_points) {\n";
+      for (const Ins& i : prog.ins)
+        if (i.op == I_LOADC || i.op == I_LOADR) {
+          std::ostringstream t;
+          emit_load(t, i, "pn", "n", false);
+          if (!t.str().empty()) o << "      " << t.str();
+        }
+      o << "    }\n";
+    } else {
+      o << "  for (ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << kBlock
+        << ") {\n";
+    }
     for (const Ins& i : prog.ins) {
       switch (i.op) {
-        case I_LOADC: {
-          const Node& n = nodes[input_nodes[(size_t)i.in]];
-          const uint64_t sz = n.st.size();
-          std::string ln = "l" + std::to_string(i.dst);
-          name[(size_t)i.dst] = ln + ".x";
-          name[(size_t)i.dst + 1] = ln + ".y";
-          if (variant[(size_t)i.in] == 'p' || variant[(size_t)i.in] == 'q') {
-            const bool pairable = sz % 2 == 0 && variant[(size_t)i.in] == 'p' && nvrtc().has_256bit_loads();
-            const uint64_t base = i.flat & ~1ull;
-            if (pairable && live_loads.count({i.in, base}) && live_loads.count({i.in, base + 1})) {
-              if (!done_pair.count({i.in, base})) {
-                done_pair.insert({i.in, base});
-                // declare both halves now; the partner instruction only defines its names
-                int partner_dst = -1;
-                for (const Ins& j : prog.ins)
-                  if (j.op == I_LOADC && j.in == i.in && j.flat == (i.flat ^ 1ull)) partner_dst = j.dst;
-                std::string a = "l" + std::to_string(i.flat == base ? i.dst : partner_dst);
-                std::string b = "l" + std::to_string(i.flat == base ? partner_dst : i.dst);
-                o << "    double2 " << a << ", " << b << "; ld32(in" << i.in << " + (p * " << sz << "ull + " << base
-                  << "ull) * 2, " << a << ", " << b << ");\n";
-              }
-            } else {
-              o << "    const double2 " << ln << " = ld16(in" << i.in << " + (p * " << sz << "ull + " << i.flat
-                << "ull) * 2);\n";
-            }
-          } else {
-            o << "    const double2 " << ln << " = ld16(in" << i.in << " + (" << i.flat << "ull * cs" << i.in
-              << " + p) * 2);\n";
-          }
-          break;
-        }
+        case I_LOADC:
         case I_LOADR: {
-          const Node& n = nodes[input_nodes[(size_t)i.in]];
-          name[(size_t)i.dst] = "l" + std::to_string(i.dst);
-          if (variant[(size_t)i.in] != 'c')
-            o << "    const double l" << i.dst << " = ld8(in" << i.in << " + p * " << n.st.size() << "ull + " << i.flat
-              << "ull);\n";
-          else
-            o << "    const double l" << i.dst << " = ld8(in" << i.in << " + " << i.flat << "ull * cs" << i.in
-              << " + p);\n";
+          if (prefetch) break;
+          std::ostringstream t;
+          emit_load(t, i, "p", "l", true);
+          if (!t.str().empty()) o << "    " << t.str();
           break;
         }
         case I_MUL:
@@ -713,6 +749,9 @@ struct spn_net {
       else
         o << "    reinterpret_cast<double2*>(out)[" << idx << "] = make_double2(" << re << ", " << im << ");\n";
     }
+    if (prefetch)
+      for (const Ins& i : prog.ins)
+        if (i.op == I_LOADC || i.op == I_LOADR) o << "    l" << i.dst << " = n" << i.dst << ";\n";
     o << "  }\n";
     if (want_sum) {
       // per-block partial of the Monte-Carlo sum: fixed shuffle tree + fixed order over warps
@@ -1144,13 +1183,13 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   if (out && out->dtype == SPN_F64) variant += 'r';
   if (sum_out_device) variant += 's';
   JitKernel& k = net->get_variant(variant);
-  jit_load(k, spn_net::kBlock);
+  jit_load(k, net->kBlock);
 
   if (n_points == 0) {
     if (sum_out_device) cuda_check(cudaMemsetAsync(sum_out_device, 0, size_out * 16, ctx->stream), "memset");
     return SPN_OK;
   }
-  const uint64_t need = (n_points + spn_net::kBlock - 1) / spn_net::kBlock;
+  const uint64_t need = (n_points + net->kBlock - 1) / net->kBlock;
   const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
   const unsigned grid = (unsigned)std::min<uint64_t>(need, cap);
 
@@ -1193,7 +1232,7 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   args.push_back(&ocs);
   args.push_back(&partial);
   args.push_back(&np);
-  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(spn_net::kBlock), args.data(), 0, ctx->stream),
+  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), 0, ctx->stream),
              "launch fused network kernel");
   ctx->launches++;
   if (sum_out_device) {

@@ -507,3 +507,65 @@ def test_real_tensors_upgrade_like_the_reference(ctx):
         net.execute([tp, tq], out)
         ctx.synchronize()
         assert rel_err(out.to_numpy().reshape(-1).real, want) <= 1e-14
+
+
+# ---- full op coverage of the executor: Power, Function(conj), nested sums (network.rs:1468-1703) -----------------
+def _net_pair(ctx, build, arrays, slots_list, mode):
+    """Build the same expression on the engine and on the oracle; return (engine out, oracle out)."""
+    n = arrays[0].shape[0]
+    net = sp.Network(ctx)
+    leaves = [net.batched(sl) for sl in slots_list]
+    net.set_root(build(net, leaves))
+    net.compile(mode)
+    ins = []
+    for sl, a in zip(slots_list, arrays):
+        t = sp.BatchTensor.empty(ctx, sl, n)
+        t.upload(a)
+        ins.append(t)
+    got = net.evaluate(ins).to_numpy().reshape(n, -1)
+    want = []
+    for p in range(n):
+        on = O.ONet()
+        ol = []
+        for sl, a in zip(slots_list, arrays):
+            t = O.OTensor.dense(sp.slots(sl), a[p], canonicalize=False)
+            on._keep.append(t)
+            ol.append(on.tensor(t))
+        on.set_root(build(on, ol))
+        on.execute()
+        want.append(on.result().to_dense().reshape(-1))
+    return got, np.stack(want)
+
+
+@pytest.mark.parametrize("mode", [sp.FUSED, sp.STEPWISE])
+def test_network_power_conj_scalars(ctx, mode):
+    rng = np.random.default_rng(31)
+    n = 40
+    m1, m2 = [sp.Minkowski.new_slot(4, 1)], [sp.Minkowski.new_slot(4, 2)]
+    P, Q = _cases.random_complex(rng, (n, 4)), _cases.random_complex(rng, (n, 4))
+
+    class Both:  # the two builders share method names except conj/power/scalar
+        pass
+
+    def conj(net, x):
+        return net.conj(x) if isinstance(net, sp.Network) else net.op(O.N_CONJ, [x])
+
+    def power(net, x, k):
+        return net.power(x, k) if isinstance(net, sp.Network) else net.op(O.N_POWER, [x], k)
+
+    cases = [
+        # (p.p)^2 : even power of a tensor -> scalar, squared
+        (lambda net, l: power(net, l[0], 4), [m1], [P]),
+        # 1 / (p.p) : negative exponent on the scalar p^2
+        (lambda net, l: power(net, l[0], -2), [m1], [P]),
+        # p^3 = (p.p) p : odd power keeps the tensor
+        (lambda net, l: power(net, l[0], 3), [m1], [P]),
+        # conj(p) q summed with q, times a constant scalar, negated
+        (lambda net, l: net.neg(net.product(net.scalar(0.5 - 2j), net.sum(net.product(conj(net, l[0]), l[1]),
+                                                                          net.product(l[1], l[1])))), [m1, m1], [P, Q]),
+        # outer product of unconnected factors, scaled by 1/(q.q)
+        (lambda net, l: net.product(l[0], l[1], power(net, net.product(l[1], l[1]), -1)), [m1, m2], [P, Q]),
+    ]
+    for build, sls, arrs in cases:
+        got, want = _net_pair(ctx, build, arrs, sls, mode)
+        assert rel_err(got, want) <= TOL
