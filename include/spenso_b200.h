@@ -198,6 +198,12 @@ int spn_net_leaf_library_custom(spn_net* net, const spn_slot* slots, uint32_t n,
 int spn_net_leaf_scalar(spn_net* net, double re, double im);
 int spn_net_op(spn_net* net, int op, const int32_t* children, uint32_t n_children, int32_t power);
 int spn_net_set_root(spn_net* net, int node);
+/* Plan interchange: the expression graph as JSON text (format: csrc/net.cu).  A host that owns
+ * the real spenso Network (graph + store derive serde, spenso/src/network.rs:33-51, network/graph.rs:39-58) can
+ * emit this text instead of making one call per node.  to_json returns a string owned by net (valid until the
+ * next call); from_json creates an UNCOMPILED network (ctx may be NULL for a plan-only network). */
+const char* spn_net_to_json(spn_net* net);
+int spn_net_from_json(spn_ctx* ctx, const char* json, spn_net** out);
 /* Run the graph walk, merge and schedule ONCE (they are identical for every point), then build
  * the device program. */
 int spn_net_compile(spn_net* net, int exec_mode);

@@ -380,12 +380,24 @@ class Network:
     leaves (spenso/src/network.rs:47-51, network/graph.rs).  compile() resolves index matching,
     contraction order and stride plans once; execute() evaluates the network at every point."""
 
-    def __init__(self, ctx: Optional[Context]):
+    def __init__(self, ctx: Optional[Context], _handle=None):
         self.ctx = ctx
-        h = C.c_void_p()
-        check(lib().spn_net_create(ctx.h if ctx is not None else None, C.byref(h)))
-        self.h = h
+        if _handle is None:
+            _handle = C.c_void_p()
+            check(lib().spn_net_create(ctx.h if ctx is not None else None, C.byref(_handle)))
+        self.h = _handle
         self._keep = []
+
+    def to_json(self) -> str:
+        """The expression graph in the plan interchange format (spn_net_to_json)."""
+        return lib().spn_net_to_json(self.h).decode()
+
+    @staticmethod
+    def from_json(ctx: Optional[Context], text: str) -> "Network":
+        """Uncompiled network from the plan interchange format (spn_net_from_json)."""
+        h = C.c_void_p()
+        check(lib().spn_net_from_json(ctx.h if ctx is not None else None, text.encode(), C.byref(h)))
+        return Network(ctx, _handle=h)
 
     def __del__(self):
         try:

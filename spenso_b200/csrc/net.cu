@@ -26,6 +26,7 @@
 #include <set>
 #include <sstream>
 
+#include "json_min.hpp"
 #include "library.hpp"
 #include "symbolic.hpp"
 #include "tensor.hpp"
@@ -53,6 +54,7 @@ struct Node {
   // re-indexed view of another batched leaf: canonical flat index here -> canonical flat index of
   // the bound input tensor (empty = identity)
   std::vector<uint64_t> flat_map;
+  int alias_of = -1;  // node id of the batched leaf this one re-indexes
 };
 
 enum StepOp { ST_CONTRACT = 0, ST_ADD = 1, ST_NEG = 2, ST_CONJ = 3, ST_RECIP = 4 };
@@ -233,7 +235,7 @@ struct spn_net {
     std::unique_ptr<JitKernel> k;
   };
   std::map<std::string, Variant> variants;
-  std::string default_source;
+  std::string default_source, json;
   double2* sum_scratch = nullptr;  // per-block partials of the fused Monte-Carlo sum
   size_t sum_scratch_elems = 0;
   ~spn_net() {
@@ -954,6 +956,7 @@ int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t
   nd.st = canonicalize(nd.args, &nd.perm);
   nd.input = src.input;
   nd.dtype = src.dtype;
+  nd.alias_of = leaf;
   // canonical index tuple here -> argument order -> canonical tuple of the bound tensor
   const uint64_t size = nd.st.size();
   auto src_strides = src.st.strides();
@@ -1040,6 +1043,135 @@ int spn_net_set_root(spn_net* net, int node) {
   check_uncompiled(net);
   if (node < 0 || node >= (int)net->nodes.size()) throw Error(SPN_ERR_INVALID, "root id out of range");
   net->root = node;
+  return SPN_OK;
+  NET_CATCH(false)
+}
+
+// ---- plan interchange: the expression graph as JSON, so that a host that owns the real
+// spenso Network (graph + store derive serde, network.rs:33-51) can hand it over without linking anything.
+// Slots are [rep_kind, rep_id, dim, aind_kind, aind]; tensors carry canonical slots and canonical flat indices.
+static void json_slots(std::ostringstream& o, const std::vector<spn_slot>& sl) {
+  o << "[";
+  for (size_t i = 0; i < sl.size(); ++i)
+    o << (i ? "," : "") << "[" << (int)sl[i].rep_kind << "," << sl[i].rep_id << "," << sl[i].dim << "," << (int)sl[i].aind_kind
+      << "," << sl[i].aind << "]";
+  o << "]";
+}
+static std::vector<spn_slot> slots_of_json(const JVal& v) {
+  std::vector<spn_slot> sl;
+  for (auto& e : v.arr()) {
+    auto& f = e.arr();
+    if (f.size() != 5) throw Error(SPN_ERR_INVALID, "plan json: a slot is [rep_kind, rep_id, dim, aind_kind, aind]");
+    sl.push_back(spn_slot{(uint8_t)f[0].i64(), (uint8_t)f[3].i64(), (int16_t)f[1].i64(), (uint32_t)f[2].u64(), (uint64_t)f[4].u64()});
+  }
+  return sl;
+}
+const char* spn_net_to_json(spn_net* net) {
+  static const char* op_names[] = {"product", "sum", "neg", "power", "conj"};
+  std::ostringstream o;
+  o << "{\"version\":1,\"nodes\":[";
+  // only the nodes the caller created (compile may append folded constants after them)
+  size_t n_nodes = net->nodes.size();
+  for (size_t k = 0; k < n_nodes; ++k) {
+    const Node& n = net->nodes[k];
+    o << (k ? ",\n" : "\n");
+    if (n.kind == LEAF_BATCHED && n.alias_of < 0) {
+      o << "{\"kind\":\"batched\",\"dtype\":\"" << (n.dtype == SPN_C64 ? "c64" : "f64") << "\",\"slots\":";
+      json_slots(o, n.args);
+      o << "}";
+    } else if (n.kind == LEAF_BATCHED) {
+      o << "{\"kind\":\"reindex\",\"leaf\":" << n.alias_of << ",\"slots\":";
+      json_slots(o, n.args);
+      o << "}";
+    } else if (n.kind == LEAF_CONST) {
+      o << "{\"kind\":\"tensor\",\"sparse\":" << (n.sparse ? "true" : "false") << ",\"slots\":";
+      json_slots(o, n.st.slots);
+      o << ",\"entries\":[";
+      bool first = true;
+      auto put = [&](uint64_t f, double2 v) {
+        o << (first ? "" : ",") << "[" << f << "," << lit(v.x) << "," << lit(v.y) << "]";
+        first = false;
+      };
+      if (n.sparse)
+        for (auto& kv : n.entries) put(kv.first, kv.second);
+      else
+        for (size_t f = 0; f < n.dense.size(); ++f) put(f, n.dense[f]);
+      o << "]}";
+    } else {
+      o << "{\"kind\":\"op\",\"op\":\"" << op_names[n.op - SPN_OP_PRODUCT] << "\",\"power\":" << n.power << ",\"children\":[";
+      for (size_t c = 0; c < n.children.size(); ++c) o << (c ? "," : "") << n.children[c];
+      o << "]}";
+    }
+  }
+  o << "\n],\"root\":" << net->root << "}\n";
+  net->json = o.str();
+  return net->json.c_str();
+}
+
+int spn_net_from_json(spn_ctx* ctx, const char* text, spn_net** out) {
+  NET_TRY
+  JVal doc;
+  try {
+    doc = JParser(text).parse();
+  } catch (const std::exception& e) {
+    throw Error(SPN_ERR_INVALID, e.what());
+  }
+  try {
+    if (doc.at("version").i64() != 1) throw Error(SPN_ERR_INVALID, "plan json: unsupported version");
+    auto net = std::make_unique<spn_net>();
+    net->ctx = ctx;
+    for (auto& jn : doc.at("nodes").arr()) {
+      const std::string& kind = jn.at("kind").str();
+      int id;
+      if (kind == "batched") {
+        auto sl = slots_of_json(jn.at("slots"));
+        const JVal* dt = jn.find("dtype");
+        id = spn_net_leaf_batched(net.get(), sl.data(), (uint32_t)sl.size(), dt && dt->str() == "f64" ? SPN_F64 : SPN_C64);
+      } else if (kind == "reindex") {
+        auto sl = slots_of_json(jn.at("slots"));
+        id = spn_net_leaf_reindex(net.get(), (int)jn.at("leaf").i64(), sl.data(), (uint32_t)sl.size());
+      } else if (kind == "library") {
+        auto sl = slots_of_json(jn.at("slots"));
+        id = spn_net_leaf_library(net.get(), (int)jn.at("which").i64(), sl.data(), (uint32_t)sl.size());
+      } else if (kind == "tensor") {
+        auto sl = slots_of_json(jn.at("slots"));
+        Structure st = structure_of_canonical(sl.data(), (uint32_t)sl.size());
+        std::map<uint64_t, double2> ent;
+        for (auto& e : jn.at("entries").arr()) {
+          auto& f = e.arr();
+          if (f.size() != 3) throw Error(SPN_ERR_INVALID, "plan json: an entry is [flat, re, im]");
+          ent[f[0].u64()] = make_double2(f[1].num(), f[2].num());
+        }
+        const JVal* spj = jn.find("sparse");
+        const bool sparse = spj && spj->kind == JVal::Bool && spj->b;
+        if (!sparse && ent.size() != st.size()) throw Error(SPN_ERR_DIMENSION, "plan json: dense tensor needs every entry");
+        id = add_const_leaf(net.get(), st, ent, sparse, nullptr);
+        if (!sparse) net->nodes.back().entries.clear();
+      } else if (kind == "scalar") {
+        id = spn_net_leaf_scalar(net.get(), jn.at("re").num(), jn.at("im").num());
+      } else if (kind == "op") {
+        const std::string& op = jn.at("op").str();
+        int code = op == "product" ? SPN_OP_PRODUCT : op == "sum" ? SPN_OP_SUM : op == "neg" ? SPN_OP_NEG
+                 : op == "power" ? SPN_OP_POWER : op == "conj" ? SPN_OP_CONJ : -1;
+        if (code < 0) throw Error(SPN_ERR_INVALID, "plan json: unknown op \"" + op + "\"");
+        std::vector<int32_t> ch;
+        for (auto& c : jn.at("children").arr()) ch.push_back((int32_t)c.i64());
+        const JVal* pw = jn.find("power");
+        id = spn_net_op(net.get(), code, ch.data(), (uint32_t)ch.size(), pw ? (int32_t)pw->i64() : 1);
+      } else {
+        throw Error(SPN_ERR_INVALID, "plan json: unknown node kind \"" + kind + "\"");
+      }
+      if (id < 0) throw Error(-id, spn_last_error());
+    }
+    check_uncompiled(net.get());
+    int rc = spn_net_set_root(net.get(), (int)doc.at("root").i64());
+    if (rc) throw Error(rc, spn_last_error());
+    *out = net.release();
+  } catch (const Error&) {
+    throw;
+  } catch (const std::exception& e) {
+    throw Error(SPN_ERR_INVALID, e.what());
+  }
   return SPN_OK;
   NET_CATCH(false)
 }

@@ -189,3 +189,29 @@ def test_network_errors():
 def test_stepwise_compile_plan_only():
     net = workloads.build_engine(workloads.eemumu(), None, sp.STEPWISE)
     assert len(net.schedule) == 5 and net.result_size == 1
+
+
+def test_plan_json_round_trip():
+    """Plan interchange: export -> import -> compile must give the identical generated kernel."""
+    import json
+
+    for name in ("cfg1", "cfg2", "cfg3", "cfg5"):
+        net = workloads.build_engine(workloads.WORKLOADS[name](), None)
+        text = net.to_json()
+        doc = json.loads(text)                      # it is real JSON
+        assert doc["version"] == 1 and doc["nodes"][doc["root"]]["kind"] == "op"
+        net2 = sp.Network.from_json(None, text).compile(sp.FUSED)
+        assert net2.cuda_source == net.cuda_source
+        assert net2.result_slots.tobytes() == net.result_slots.tobytes()
+        assert net2.to_json() == text
+    # a document written by hand (what a Rust shim would emit with serde_json): p(mu) q(mu) with f64 inputs
+    doc = {"version": 1, "root": 2, "nodes": [
+        {"kind": "batched", "dtype": "f64", "slots": [[2, 0, 4, 0, 7]]},
+        {"kind": "batched", "dtype": "f64", "slots": [[2, 0, 4, 0, 7]]},
+        {"kind": "op", "op": "product", "children": [0, 1]}]}
+    net = sp.Network.from_json(None, json.dumps(doc)).compile()
+    assert net.n_inputs == 2 and net.result_size == 1 and net.fp64_instr_per_point == 4
+    for bad in ("{", '{"version":2,"nodes":[],"root":0}', '{"version":1,"nodes":[{"kind":"what"}],"root":0}',
+                '{"version":1,"nodes":[{"kind":"op","op":"product","children":[5]}],"root":0}'):
+        with pytest.raises(sp.SpensoError):
+            sp.Network.from_json(None, bad)
