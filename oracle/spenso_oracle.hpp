@@ -1791,8 +1791,10 @@ struct Network {
         int squares = np / 2;
         Tensor square = contract(t, t, opt);
         if (np % 2 == 1) {
-          for (int k = 0; k < squares; ++k) square = contract(square, square, opt);
-          t = contract(square, t, opt);
+          if (np != 1) {  // network.rs:1591-1596 / 1647-1652: n == 1 (pow == -1) leaves t untouched
+            for (int k = 0; k < squares; ++k) square = contract(square, square, opt);
+            t = contract(square, t, opt);
+          }
           if (pow < 0) {
             if (!t.st.is_scalar()) throw std::runtime_error("NegativeExponentNonScalar");
             replace_with_leaf(id, N_SCALAR, push_scalar(cpow_inv(t.to_dense_data()[0])));

@@ -55,6 +55,7 @@ struct Node {
   // the bound input tensor (empty = identity)
   std::vector<uint64_t> flat_map;
   int alias_of = -1;  // node id of the batched leaf this one re-indexes
+  bool is_scalar_leaf = false;  // created by spn_net_leaf_scalar (NetworkLeaf::Scalar)
 };
 
 enum StepOp { ST_CONTRACT = 0, ST_ADD = 1, ST_NEG = 2, ST_CONJ = 3, ST_RECIP = 4 };
@@ -65,6 +66,9 @@ struct Value {
   Structure st;
   bool batched = false;
   int leaf = -1;  // node id for leaf values
+  // the reference distinguishes NetworkLeaf::Scalar from a rank-0 LocalTensor (network.rs:1526-1703 treats
+  // them differently in Power); true = Scalar
+  bool scalar_kind = false;
 };
 
 // ---- JIT: CUDA source -> cubin (NVRTC, sm_100a) -> cudaKernel_t -------------------------------
@@ -370,6 +374,7 @@ struct spn_net {
     int v = -1;
     if (nodes[(size_t)id].kind != NODE_OP) {
       v = new_value(nodes[(size_t)id].st, nodes[(size_t)id].kind == LEAF_BATCHED, id);
+      values[(size_t)v].scalar_kind = nodes[(size_t)id].is_scalar_leaf;
     } else {
       // copy what we need: recursion may append nodes and move the vector
       struct {
@@ -381,8 +386,13 @@ struct spn_net {
           std::vector<int> kids, vals;
           flatten(id, SPN_OP_PRODUCT, kids);
           if (kids.empty()) throw Error(SPN_ERR_INVALID, "empty product");
-          for (int c : kids) vals.push_back(build(c, memo));
+          bool all_scalars = true;  // ContractScalars: a product of Scalars is a Scalar (contract.rs:73-208)
+          for (int c : kids) {
+            vals.push_back(build(c, memo));
+            all_scalars = all_scalars && values[(size_t)vals.back()].scalar_kind;
+          }
           v = schedule_product(vals);
+          if (all_scalars && kids.size() > 1) values[(size_t)v].scalar_kind = true;
           break;
         }
         case SPN_OP_SUM: {  // network.rs:1342-1467
@@ -398,31 +408,41 @@ struct spn_net {
                                                  : "sum of tensors of different structure");
             v = emit(ST_ADD, v, w, values[v].st);
           }
+          // scalar mode of Sum (network.rs:1342-1467): the accumulated value is pushed as a Scalar
+          if (kids.size() > 1 && values[(size_t)v].st.order() == 0) values[(size_t)v].scalar_kind = true;
           break;
         }
         case SPN_OP_NEG:
           if (n.children.size() != 1) throw Error(SPN_ERR_INVALID, "neg takes one child");
           v = build(n.children[0], memo);
-          v = emit(ST_NEG, v, -1, values[v].st);
+          {
+            const bool sk = values[(size_t)v].scalar_kind;
+            v = emit(ST_NEG, v, -1, values[v].st);
+            values[(size_t)v].scalar_kind = sk;
+          }
           break;
         case SPN_OP_CONJ:  // FUN_LIB conj, spenso-hep-lib/src/lib.rs:511-520
           if (n.children.size() != 1) throw Error(SPN_ERR_INVALID, "conj takes one child");
           v = build(n.children[0], memo);
-          v = emit(ST_CONJ, v, -1, values[v].st);
+          {
+            const bool sk = values[(size_t)v].scalar_kind;
+            v = emit(ST_CONJ, v, -1, values[v].st);
+            values[(size_t)v].scalar_kind = sk;
+          }
           break;
-        case SPN_OP_POWER: {  // network.rs:1526-1703
+        case SPN_OP_POWER: {  // network.rs:1526-1703, restated literally (including its odd-power behaviour)
           if (n.children.size() != 1) throw Error(SPN_ERR_INVALID, "power takes one child");
           int c = build(n.children[0], memo);
           const int pw = n.power, np = pw < 0 ? -pw : pw;
-          const bool is_scalar = values[c].st.order() == 0;
-          if (is_scalar) {
+          if (values[(size_t)c].scalar_kind) {  // NetworkLeaf::Scalar
             if (np == 0) {
               v = c;  // the reference returns the scalar itself for a zero exponent
               break;
             }
             v = c;
             for (int k = 1; k < np; ++k) v = emit_contract(v, c);
-            if (pw < 0) v = emit(ST_RECIP, v, -1, values[v].st);
+            if (pw < 0) v = emit(ST_RECIP, v, -1, values[(size_t)v].st);
+            values[(size_t)v].scalar_kind = true;
             break;
           }
           if (pw == 0) {
@@ -435,17 +455,22 @@ struct spn_net {
           }
           int square = emit_contract(c, c);
           if (np % 2 == 1) {
-            for (int k = 0; k < np / 2; ++k) square = emit_contract(square, square);
-            v = emit_contract(square, c);
+            v = c;
+            if (np != 1) {
+              for (int k = 0; k < np / 2; ++k) square = emit_contract(square, square);
+              v = emit_contract(square, c);
+            }
             if (pw < 0) {
-              if (values[v].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "negative exponent on a non-scalar");
-              v = emit(ST_RECIP, v, -1, values[v].st);
+              if (values[(size_t)v].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "negative exponent on a non-scalar");
+              v = emit(ST_RECIP, v, -1, values[(size_t)v].st);
+              values[(size_t)v].scalar_kind = true;
             }
           } else {
-            if (values[square].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "even power of a tensor is not a scalar");
+            if (values[(size_t)square].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "even power of a tensor is not a scalar");
             v = square;
             for (int k = 1; k < np / 2; ++k) v = emit_contract(v, square);
-            if (pw < 0) v = emit(ST_RECIP, v, -1, values[v].st);
+            if (pw < 0) v = emit(ST_RECIP, v, -1, values[(size_t)v].st);
+            values[(size_t)v].scalar_kind = true;
           }
           break;
         }
@@ -460,7 +485,9 @@ struct spn_net {
     n.kind = LEAF_CONST;
     n.dense = {s};
     nodes.push_back(n);
-    return new_value(Structure(), false, (int)nodes.size() - 1);
+    int v = new_value(Structure(), false, (int)nodes.size() - 1);
+    values[(size_t)v].scalar_kind = true;
+    return v;
   }
 
   // ---- fused: replay the schedule symbolically ---------------------------------------------------
@@ -1019,7 +1046,9 @@ int spn_net_leaf_scalar(spn_net* net, double re, double im) {
   NET_TRY
   check_uncompiled(net);
   std::vector<double2> d{make_double2(re, im)};
-  return add_const_leaf(net, Structure(), {}, false, &d);
+  int id = add_const_leaf(net, Structure(), {}, false, &d);
+  net->nodes.back().is_scalar_leaf = true;
+  return id;
   NET_CATCH(true)
 }
 int spn_net_op(spn_net* net, int op, const int32_t* children, uint32_t n_children, int32_t power) {
@@ -1083,6 +1112,8 @@ const char* spn_net_to_json(spn_net* net) {
       o << "{\"kind\":\"reindex\",\"leaf\":" << n.alias_of << ",\"slots\":";
       json_slots(o, n.args);
       o << "}";
+    } else if (n.kind == LEAF_CONST && n.is_scalar_leaf) {
+      o << "{\"kind\":\"scalar\",\"re\":" << lit(n.dense[0].x) << ",\"im\":" << lit(n.dense[0].y) << "}";
     } else if (n.kind == LEAF_CONST) {
       o << "{\"kind\":\"tensor\",\"sparse\":" << (n.sparse ? "true" : "false") << ",\"slots\":";
       json_slots(o, n.st.slots);

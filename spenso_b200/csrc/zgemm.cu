@@ -82,20 +82,31 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
   const int b_n = tid & 63, b_k0 = tid >> 6;        // k rows b_k0 + 2 i
   const ll KT = (K + BK - 1) / BK;
 
-  auto load_tile = [&](int stage, ll kt) {
+  // k-offsets of a tile are fetched one pipeline step ahead of the cp.async that needs them, so the
+  // gather addresses never wait on a global load
+  ll ka_next = 0, kb_next[4] = {0, 0, 0, 0};
+  auto fetch_koffs = [&](ll kt) {
+    const ll kbase = kt * BK;
+    const ll k = kbase + a_kk;
+    ka_next = (kt < KT && k < K) ? __ldg(k_a + k) : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const ll kk = kbase + b_k0 + 2 * i;
+      kb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
+    }
+  };
+  auto load_tile = [&](int stage, ll kt) {  // uses the offsets fetched by fetch_koffs(kt)
     const ll kbase = kt * BK;
     double2* as = As + stage * BM * SA;
     double2* bs = Bs + stage * BK * SB;
     {
-      const ll k = kbase + a_kk;
-      const bool kv = k < K;
-      const ll koff = kv ? __ldg(k_a + k) : 0;
+      const bool kv = kbase + a_kk < K;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = a_r0 + 16 * i;
         const ll ro = s_row[r];
         const bool v = kv && ro >= 0;
-        cp_async16(as + r * SA + a_kk, A + (v ? ro + koff : 0), v);
+        cp_async16(as + r * SA + a_kk, A + (v ? ro + ka_next : 0), v);
       }
     }
     {
@@ -103,10 +114,8 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int kk = b_k0 + 2 * i;
-        const ll k = kbase + kk;
-        const bool v = k < K && co >= 0;
-        const ll koff = (k < K) ? __ldg(k_b + k) : 0;
-        cp_async16(bs + kk * SB + b_n, B + (v ? co + koff : 0), v);
+        const bool v = kbase + kk < K && co >= 0;
+        cp_async16(bs + kk * SB + b_n, B + (v ? co + kb_next[i] : 0), v);
       }
     }
   };
@@ -119,9 +128,11 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
+    fetch_koffs(s);
     if (s < KT) load_tile(s, s);
     cp_async_commit();
   }
+  fetch_koffs(STAGES - 1);
 
   const int fr = lane >> 2, fk = lane & 3;  // fragment row (or column) and k position of this lane
   for (ll kt = 0; kt < KT; ++kt) {
@@ -131,6 +142,7 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
       const ll nxt = kt + STAGES - 1;
       if (nxt < KT) load_tile((int)(nxt % STAGES), nxt);
       cp_async_commit();
+      fetch_koffs(nxt + 1);
     }
     const int stage = (int)(kt % STAGES);
     const double2* as = As + stage * BM * SA;
@@ -151,17 +163,25 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
           a[i].y *= sg;
         }
       }
+      // four passes over the 16 accumulator tiles: consecutive DMMAs never touch the same accumulator
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const double nai = -a[i].y;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dmma884(cr[i][j][0], cr[i][j][1], a[i].x, b[j].x);
-          dmma884(cr[i][j][0], cr[i][j][1], nai, b[j].y);
-          dmma884(ci[i][j][0], ci[i][j][1], a[i].x, b[j].y);
-          dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
-        }
+        for (int j = 0; j < 4; ++j) dmma884(cr[i][j][0], cr[i][j][1], nai, b[j].y);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(ci[i][j][0], ci[i][j][1], a[i].y, b[j].x);
     }
   }
   cp_async_wait<0>();

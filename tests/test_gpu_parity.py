@@ -560,12 +560,90 @@ def test_network_power_conj_scalars(ctx, mode):
         (lambda net, l: power(net, l[0], -2), [m1], [P]),
         # p^3 = (p.p) p : odd power keeps the tensor
         (lambda net, l: power(net, l[0], 3), [m1], [P]),
-        # conj(p) q summed with q, times a constant scalar, negated
+        # conj(p).q + q.q, times a constant scalar, negated.  (The oracle, like the reference, owns every leaf
+        # once — its executor rewrites nodes in place — so a tensor used twice is entered twice.)
         (lambda net, l: net.neg(net.product(net.scalar(0.5 - 2j), net.sum(net.product(conj(net, l[0]), l[1]),
-                                                                          net.product(l[1], l[1])))), [m1, m1], [P, Q]),
+                                                                          net.product(l[2], l[3])))),
+         [m1, m1, m1, m1], [P, Q, Q, Q]),
+        # the reference treats a rank-0 LocalTensor and a Scalar leaf differently in Power (network.rs:1526-1703):
+        # odd power of the rank-0 tensor p.q goes through the squaring loop, a Scalar is multiplied n times
+        (lambda net, l: power(net, net.product(l[0], l[1]), 3), [m1, m1], [P, Q]),
+        (lambda net, l: net.product(l[0], power(net, net.scalar(1.5 - 0.5j), 3)), [m1], [P]),
+        (lambda net, l: net.product(l[0], power(net, net.product(l[1], l[2]), 0)), [m1, m2, m2], [P, Q, Q]),
         # outer product of unconnected factors, scaled by 1/(q.q)
-        (lambda net, l: net.product(l[0], l[1], power(net, net.product(l[1], l[1]), -1)), [m1, m2], [P, Q]),
+        (lambda net, l: net.product(l[0], l[1], power(net, net.product(l[2], l[3]), -1)), [m1, m2, m2, m2], [P, Q, Q, Q]),
     ]
     for build, sls, arrs in cases:
         got, want = _net_pair(ctx, build, arrs, sls, mode)
         assert rel_err(got, want) <= TOL
+
+
+# ---- random networks (fuzz): sums of products over random index structures ---------------------------------
+def random_netspec(rng, n_factors, with_const=True):
+    """Product of n_factors tensors over a random chain/tree of shared indices, free indices sprinkled in;
+    some factors are point-independent sparse constants.  Returns a NetSpec."""
+    pool = [(sp.Euclidean, 2), (sp.Euclidean, 3), (sp.Bispinor, 4), (sp.Minkowski, 4), (sp.ColorAdjoint, 3),
+            (sp.Lorentz, 3), (sp.ColorFundamental, 3)]
+    spec = workloads.NetSpec("fuzz")
+    aind = iter(range(1, 1000))
+    fslots = [[] for _ in range(n_factors)]
+    # connect factor k to a random earlier factor (tree), sometimes with a second shared index
+    for k in range(1, n_factors):
+        for _ in range(1 + int(rng.random() < 0.3)):
+            j = int(rng.integers(0, k))
+            rep, dim = pool[int(rng.integers(len(pool)))]
+            a = next(aind)
+            s1 = rep.new_slot(dim, a)
+            fslots[j].append(s1)
+            fslots[k].append(s1.dual())
+    for k in range(n_factors):
+        for _ in range(int(rng.integers(0, 2))):
+            rep, dim = pool[int(rng.integers(len(pool)))]
+            s = rep.new_slot(dim, next(aind))
+            fslots[k].append(s.dual() if rng.random() < 0.5 else s)
+    ids = []
+    for k in range(n_factors):
+        sl = [fslots[k][i] for i in rng.permutation(len(fslots[k]))]
+        size = int(np.prod([s.dim for s in sl])) if sl else 1
+        if with_const and size <= 64 and rng.random() < 0.4 and sl:
+            dims = [s.dim for s in sl]
+            ids.append(spec.custom(sl, _cases.random_sparse_entries(rng, dims, density=0.4)))
+        else:
+            ids.append(spec.batched(sl, f"t{k}"))
+    if not spec.inputs:       # at least one per-point tensor
+        return random_netspec(rng, n_factors, with_const=False)
+    prod = spec.product(*ids)
+    if rng.random() < 0.5:
+        prod = spec.product(spec.scalar(complex(rng.uniform(-2, 2), rng.uniform(-2, 2))), prod)
+    if rng.random() < 0.4:
+        prod = spec.sum(prod, spec.neg(prod)) if rng.random() < 0.2 else spec.sum(prod, prod)
+    spec.root = prod
+    return spec
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_networks_vs_oracle(ctx, seed):
+    rng = np.random.default_rng(9000 + seed)
+    checked = 0
+    for _ in range(6):
+        spec = random_netspec(rng, int(rng.integers(2, 6)))
+        total = max(int(np.prod([sz for _, sz in spec.inputs])), 1)
+        n = 7
+        arrays = workloads.synthetic_inputs(spec, n, int(rng.integers(1 << 30)))
+        try:
+            ref, ref_sum, oslots = O.eval_spec(spec, arrays)
+        except (O.OracleError, NotImplementedError):
+            continue
+        if ref.shape[1] > 4096:
+            continue
+        for mode in (sp.FUSED, sp.STEPWISE):
+            try:
+                got = run_network(ctx, spec, arrays, mode)
+            except sp.SpensoError as e:
+                if e.code == 7 and "too large" in str(e):
+                    continue
+                raise
+            assert got.shape == ref.shape
+            assert rel_err(got, ref) <= TOL, (seed, mode)
+        checked += 1
+    assert checked >= 3
