@@ -233,6 +233,19 @@ uint64_t spn_net_input_bytes_per_point(const spn_net* net);
 int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_inputs, spn_tensor* out,
                     double* sum_out_device, uint64_t first_point, uint64_t n_points);
 
+/* Network::execute on HOST data — the reference's own calling convention (its tensors are host
+ * Vec<Complex<f64>>, spenso/src/tensors/data/dense.rs:51-54).  host_inputs[i]: n_points tensors of input i laid end to
+ * end (canonical order); host_out (optional): n_points result tensors; host_sum (optional): the sum over points
+ * (2*result_size doubles, host).  The batch streams through a 3-deep chunk pipeline on private streams (H2D of
+ * chunk k+1 || kernel of chunk k || D2H of chunk k-1), so device memory use does not depend on n_points.
+ * chunk_points = 0: default (2^17).  Host buffers should be pinned (spn_host_alloc).  Fused networks only.
+ * Synchronous: host_out / host_sum are complete on return. */
+int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
+                         void* host_out, double* host_sum, uint64_t chunk_points);
+/* pinned host memory for the host-buffer entry points (cudaHostAlloc / cudaFreeHost) */
+void* spn_host_alloc(uint64_t bytes);
+void spn_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -512,6 +512,21 @@ class Network:
         check(lib().spn_net_execute(self.h, C.cast(arr, C.c_void_p), len(inputs), out.h if out is not None else None,
                                     C.c_void_p(sum_out_ptr) if sum_out_ptr else None, first_point, n_points))
 
+    def execute_host(self, host_inputs: Sequence[np.ndarray], out: Optional[np.ndarray] = None,
+                     want_sum: bool = False, chunk_points: int = 0):
+        """Network::execute on host data (spn_net_execute_host): host_inputs[i] is [n_points, size_i] complex128
+        (float64 for f64 leaves) in canonical order; `out` (optional) a preallocated [n_points, result_size]
+        complex128 array; returns (out, sum or None).  Copies overlap the kernels chunk by chunk; pass pinned
+        arrays (e.g. views of torch pinned tensors) for full overlap."""
+        ins = [np.ascontiguousarray(a) for a in host_inputs]
+        n = ins[0].shape[0] if ins else (out.shape[0] if out is not None else 1)
+        ptrs = (C.c_void_p * max(len(ins), 1))(*[a.ctypes.data for a in ins])
+        s = np.zeros(self.result_size, dtype=np.complex128) if want_sum else None
+        check(lib().spn_net_execute_host(self.h, C.cast(ptrs, C.c_void_p), len(ins), n,
+                                         ptr(out) if out is not None else None, ptr(s) if want_sum else None,
+                                         chunk_points))
+        return out, s
+
     def evaluate(self, inputs: Sequence[BatchTensor], layout: int = POINT_MAJOR) -> BatchTensor:
         """Convenience: allocate the result tensor, execute, return it."""
         n = inputs[0].n_points if inputs else 1

@@ -104,6 +104,9 @@ SYMBOLS = {
     "spn_net_macs_per_point": (_U64, [_P]),
     "spn_net_input_bytes_per_point": (_U64, [_P]),
     "spn_net_execute": (_I, [_P, _P, _U32, _P, _P, _U64, _U64]),
+    "spn_net_execute_host": (_I, [_P, _P, _U32, _U64, _P, _P, _U64]),
+    "spn_host_alloc": (_P, [_U64]),
+    "spn_host_free": (None, [_P]),
 }
 
 _lib = None

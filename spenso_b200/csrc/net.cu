@@ -242,8 +242,36 @@ struct spn_net {
   std::string default_source, json;
   double2* sum_scratch = nullptr;  // per-block partials of the fused Monte-Carlo sum
   size_t sum_scratch_elems = 0;
+  // host-buffer pipeline (spn_net_execute_host): kPipe slots, each with its own stream and device staging
+  static constexpr int kPipe = 3;
+  struct HostPipe {
+    cudaStream_t stream[kPipe] = {nullptr, nullptr, nullptr};
+    std::vector<void*> in[kPipe];
+    void* out[kPipe] = {nullptr, nullptr, nullptr};
+    double2* partial[kPipe] = {nullptr, nullptr, nullptr};
+    double2* chunk_sums = nullptr;
+    uint64_t chunk_points = 0, n_chunks_cap = 0;
+    size_t partial_elems = 0;
+    void release() {
+      for (int s = 0; s < kPipe; ++s) {
+        for (void* p : in[s]) cudaFree(p);
+        in[s].clear();
+        if (out[s]) cudaFree(out[s]);
+        if (partial[s]) cudaFree(partial[s]);
+        out[s] = nullptr;
+        partial[s] = nullptr;
+      }
+      if (chunk_sums) cudaFree(chunk_sums);
+      chunk_sums = nullptr;
+      chunk_points = n_chunks_cap = 0;
+      partial_elems = 0;
+    }
+  } pipe;
   ~spn_net() {
     if (sum_scratch) cudaFree(sum_scratch);
+    pipe.release();
+    for (int s = 0; s < kPipe; ++s)
+      if (pipe.stream[s]) cudaStreamDestroy(pipe.stream[s]);
   }
   // stepwise
   std::vector<std::unique_ptr<spn_tensor>> const_tensors;  // per value id (leaf consts), lazily uploaded
@@ -1296,6 +1324,131 @@ const char* spn_net_prepare_variant(spn_net* net, const char* variant) {
 }
 uint64_t spn_net_macs_per_point(const spn_net* net) { return net->stats.n_fp; }
 uint64_t spn_net_input_bytes_per_point(const spn_net* net) { return net->stats.n_load_bytes; }
+
+// Network::execute on HOST data: the reference's calling convention (tensors are host Vec<Complex<f64>>).
+// host_inputs[i]: n_points tensors of input i laid end to end (point major, canonical order); host_out (optional):
+// n_points result tensors; host_sum (optional): sum over points (2*result_size doubles).  The batch is cut into
+// chunks that flow through a kPipe-deep pipeline on private streams — H2D of chunk k+1 overlaps the kernel of chunk
+// k and the D2H of chunk k-1 (both copy engines busy) — so device memory use is 3 chunks, whatever n_points is
+// (this is how 1e8-point Monte-Carlo batches run).  Host buffers should be pinned (spn_host_alloc) for the copies
+// to be asynchronous.  Synchronous: returns when host_out / host_sum are complete.
+int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
+                         void* host_out, double* host_sum, uint64_t chunk_points) {
+  NET_TRY
+  if (!net->compiled) throw Error(SPN_ERR_INVALID, "network is not compiled");
+  if (!net->ctx) throw Error(SPN_ERR_NO_DEVICE, "plan-only network (created without a context) cannot execute");
+  if (net->exec_mode != SPN_EXEC_FUSED) throw Error(SPN_ERR_INVALID, "execute_host needs a fused network");
+  if (n_inputs != net->n_inputs) throw Error(SPN_ERR_INVALID, "wrong number of input buffers");
+  if (!host_out && !host_sum) throw Error(SPN_ERR_INVALID, "nothing to compute: no output and no sum requested");
+  spn_ctx* ctx = net->ctx;
+  const uint64_t size_out = net->values[(size_t)net->result_value].st.size();
+  if (chunk_points == 0) chunk_points = 1u << 17;
+  chunk_points = std::min<uint64_t>(chunk_points, std::max<uint64_t>(n_points, 1));
+  const uint64_t n_chunks = (n_points + chunk_points - 1) / chunk_points;
+  std::vector<size_t> in_bytes(n_inputs);
+  for (uint32_t i = 0; i < n_inputs; ++i) {
+    const Node& nd = net->nodes[(size_t)net->input_nodes[i]];
+    in_bytes[i] = nd.st.size() * (nd.dtype == SPN_C64 ? 16 : 8);
+  }
+  std::string variant(n_inputs, 'p');
+  variant += host_out ? 'p' : 'n';
+  if (host_sum) variant += 's';
+  JitKernel& k = net->get_variant(variant);
+  jit_load(k, net->kBlock);
+  const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
+
+  auto& P = net->pipe;
+  for (int s = 0; s < spn_net::kPipe; ++s)
+    if (!P.stream[s]) cuda_check(cudaStreamCreateWithFlags(&P.stream[s], cudaStreamNonBlocking), "pipeline stream");
+  if (P.chunk_points < chunk_points || P.partial_elems < cap * size_out || P.n_chunks_cap < n_chunks) {
+    cuda_check(cudaDeviceSynchronize(), "pipeline resize");
+    P.release();
+    for (int s = 0; s < spn_net::kPipe; ++s) {
+      for (uint32_t i = 0; i < n_inputs; ++i) {
+        void* d = nullptr;
+        cuda_check(cudaMalloc(&d, std::max<size_t>(chunk_points * in_bytes[i], 32)), "pipeline staging");
+        P.in[s].push_back(d);
+      }
+      cuda_check(cudaMalloc(&P.out[s], std::max<size_t>(chunk_points * size_out * 16, 32)), "pipeline staging");
+      cuda_check(cudaMalloc((void**)&P.partial[s], std::max<size_t>(cap * size_out, 1) * sizeof(double2)), "pipeline staging");
+    }
+    cuda_check(cudaMalloc((void**)&P.chunk_sums, std::max<uint64_t>(n_chunks, 1) * size_out * sizeof(double2)), "pipeline staging");
+    P.chunk_points = chunk_points;
+    P.partial_elems = cap * size_out;
+    P.n_chunks_cap = n_chunks;
+  }
+  // order the pipeline after whatever the context's stream has queued
+  cudaEvent_t ev;
+  cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+  cuda_check(cudaEventRecord(ev, ctx->stream), "event");
+  for (int s = 0; s < spn_net::kPipe; ++s) cuda_check(cudaStreamWaitEvent(P.stream[s], ev, 0), "event");
+  cudaEventDestroy(ev);
+
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    const int s = (int)(c % spn_net::kPipe);
+    cudaStream_t st = P.stream[s];
+    const uint64_t first = c * chunk_points, cnt = std::min(chunk_points, n_points - first);
+    std::vector<const double*> in_ptr(n_inputs);
+    std::vector<unsigned long long> in_cs(n_inputs, chunk_points);
+    for (uint32_t i = 0; i < n_inputs; ++i) {
+      cuda_check(cudaMemcpyAsync(P.in[s][i], (const char*)host_inputs[i] + first * in_bytes[i], cnt * in_bytes[i],
+                                 cudaMemcpyHostToDevice, st),
+                 "H2D of a chunk");
+      in_ptr[i] = static_cast<const double*>(P.in[s][i]);
+    }
+    double* out_ptr = host_out ? static_cast<double*>(P.out[s]) : nullptr;
+    unsigned long long ocs = chunk_points, np = cnt;
+    double2* partial = host_sum ? P.partial[s] : nullptr;
+    const unsigned grid = (unsigned)std::min<uint64_t>((cnt + net->kBlock - 1) / net->kBlock, cap);
+    std::vector<void*> args;
+    for (uint32_t i = 0; i < n_inputs; ++i) {
+      args.push_back(&in_ptr[i]);
+      args.push_back(&in_cs[i]);
+    }
+    args.push_back(&out_ptr);
+    args.push_back(&ocs);
+    args.push_back(&partial);
+    args.push_back(&np);
+    cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), 0, st),
+               "launch fused network kernel");
+    ctx->launches++;
+    if (host_sum) {
+      cuda_check(launch_reduce_partials(partial, (int)grid, size_out, P.chunk_sums + c * size_out, st), "reduce_partials_kernel");
+      ctx->launches++;
+    }
+    if (host_out)
+      cuda_check(cudaMemcpyAsync((char*)host_out + first * size_out * 16, P.out[s], cnt * size_out * 16,
+                                 cudaMemcpyDeviceToHost, st),
+                 "D2H of a chunk");
+  }
+  for (int s = 0; s < spn_net::kPipe; ++s) cuda_check(cudaStreamSynchronize(P.stream[s]), "pipeline drain");
+  if (host_sum) {
+    if (n_chunks == 0) {
+      std::memset(host_sum, 0, size_out * 16);
+    } else {
+      // deterministic: one fixed-shape reduction over the per-chunk sums, on the context's stream
+      cuda_check(launch_reduce_partials(P.chunk_sums, (int)n_chunks, size_out, P.partial[0], ctx->stream), "reduce_partials_kernel");
+      ctx->launches++;
+      cuda_check(cudaMemcpyAsync(host_sum, P.partial[0], size_out * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H of the sum");
+      cuda_check(cudaStreamSynchronize(ctx->stream), "D2H of the sum");
+    }
+  }
+  return SPN_OK;
+  NET_CATCH(false)
+}
+
+void* spn_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+    spn::set_error("cudaHostAlloc failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void spn_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
 
 int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_inputs, spn_tensor* out,
                     double* sum_out_device, uint64_t first_point, uint64_t n_points) {

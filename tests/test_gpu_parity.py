@@ -647,3 +647,30 @@ def test_random_networks_vs_oracle(ctx, seed):
             assert rel_err(got, ref) <= TOL, (seed, mode)
         checked += 1
     assert checked >= 3
+
+
+# ---- host-buffer entry point (the reference's calling convention: host tensors in, host tensors out) -------------
+@pytest.mark.parametrize("name,n_points,scale", [("cfg2", 5000, 1.0), ("cfg5", 3001, 100.0), ("cfg1", 257, 1.0)])
+def test_execute_host_pipeline_vs_oracle(ctx, name, n_points, scale):
+    spec = workloads.WORKLOADS[name]()
+    arrays = workloads.synthetic_inputs(spec, n_points, 4321, scale=scale, real=name == "cfg5")
+    ref, ref_sum, _ = O.eval_spec(spec, arrays)
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    for chunk in (0, 1000, 977, n_points, 1):
+        if chunk == 1 and n_points > 300:
+            continue
+        out = np.zeros((n_points, net.result_size), dtype=np.complex128)
+        got, s = net.execute_host(arrays, out=out, want_sum=True, chunk_points=chunk)
+        assert rel_err(got, ref) <= TOL
+        assert rel_err(s, ref_sum) <= TOL
+    # sum only / output only; repeated calls are deterministic
+    _, s1 = net.execute_host(arrays, out=None, want_sum=True, chunk_points=512)
+    _, s2 = net.execute_host(arrays, out=None, want_sum=True, chunk_points=512)
+    assert (s1 == s2).all() and rel_err(s1, ref_sum) <= TOL
+    out = np.zeros((n_points, net.result_size), dtype=np.complex128)
+    got, s = net.execute_host(arrays, out=out)
+    assert s is None and rel_err(got, ref) <= TOL
+    with pytest.raises(sp.SpensoError):
+        net.execute_host(arrays[:1], out=out)
+    with pytest.raises(sp.SpensoError):
+        net.execute_host(arrays, out=None, want_sum=False)
