@@ -186,6 +186,24 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this rank to the CPUs next to its GPU so that its pinned host buffers are first-touched on the local
+    NUMA node (N ranks share the host's memory controllers and PCIe root complexes in the e2e leg)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64 + 4
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ---- GPU arm --------------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -205,6 +223,7 @@ def run_b200(args):
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        bind_to_gpu_numa_node(local_rank)
 
     wl = args.workload
     spec = workloads.WORKLOADS[wl]()
