@@ -383,7 +383,7 @@ def run_b200(args):
     line = None
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:   # cpu_baseline: rank 0 at N=1 only
             nthr = os.cpu_count() or 1
             fn = lambda m: workloads.synthetic_inputs(spec, m, 1234, scale=SCALE[wl], real=(wl == "cfg5"))
             rate, sample, secs = oracle_rate(spec, fn, nthr, args.cpu_seconds)

@@ -103,6 +103,12 @@ void spn_ctx_destroy(spn_ctx* ctx);
 /* use an existing cudaStream_t (e.g. torch's current stream); NULL = the legacy default stream */
 int spn_ctx_set_stream(spn_ctx* ctx, void* cuda_stream);
 int spn_ctx_synchronize(spn_ctx* ctx);
+/* Parity triage switch.  emulate_interleaved_pairing != 0: contractions whose result interleaves the operands'
+ * slots (MergeInfo::Interleaved) and that contract >= 2 indices enumerate each operand's contracted indices in its
+ * OWN slot order, like MultiContractInterleaved of the reference (spenso/src/contraction/multicontract.rs:295-689,
+ * no permutation applied); default 0 pairs every contracted slot with its dual.  The two differ only when
+ * dualizable contracted slots appear in different relative orders in the two operands. */
+int spn_ctx_set_reference_quirks(spn_ctx* ctx, int emulate_interleaved_pairing);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t spn_ctx_launch_count(const spn_ctx* ctx);
 int spn_ctx_sm_count(const spn_ctx* ctx);

@@ -25,7 +25,7 @@ void spn::set_error(const std::string& s) { g_err = s; }
 
 namespace spn {
 
-KTables build_k_tables(const spn_contract_plan& p) {
+KTables build_k_tables(const spn_contract_plan& p, bool emulate_reference_pairing) {
   KTables t;
   uint32_t nd = p.n_common;
   uint64_t nk = p.n_contracted;
@@ -33,21 +33,36 @@ KTables build_k_tables(const spn_contract_plan& p) {
   t.off_a.resize(nk);
   t.off_b.resize(nk);
   t.sign.resize(nk);
-  std::vector<uint32_t> idx(nd, 0);
+  // enumeration order of the contracted dims per operand.  Normally both operands walk them in the SAME
+  // order (other's), i.e. each slot is paired with its dual.  MultiContractInterleaved of the reference
+  // (multicontract.rs:295-689) zips self.iter_metric() with other.iter(), each in its OWN slot order, without
+  // the permutation the non-interleaved kernel applies (SURVEY K-note 3); `emulate_reference_pairing`
+  // reproduces that for parity triage.
+  std::vector<uint32_t> ord_a(nd), ord_b(nd);
+  for (uint32_t d = 0; d < nd; ++d) ord_a[d] = ord_b[d] = d;
+  if (emulate_reference_pairing && p.merge_kind == SPN_INTERLEAVED && nd >= 2) {
+    std::stable_sort(ord_a.begin(), ord_a.end(), [&](uint32_t x, uint32_t y) { return p.k_pos_a[x] < p.k_pos_a[y]; });
+    std::stable_sort(ord_b.begin(), ord_b.end(), [&](uint32_t x, uint32_t y) { return p.k_pos_b[x] < p.k_pos_b[y]; });
+  }
+  std::vector<uint32_t> ia(nd, 0), ib(nd, 0);  // odometers over ord_a / ord_b, last fastest
   for (uint64_t k = 0; k < nk; ++k) {
     long long oa = 0, ob = 0;
     bool neg = false;
     for (uint32_t d = 0; d < nd; ++d) {
-      oa += (long long)idx[d] * (long long)p.k_stride_a[d];
-      ob += (long long)idx[d] * (long long)p.k_stride_b[d];
-      if (p.k_metric[d] && idx[d] > 0) neg = !neg;
+      oa += (long long)ia[d] * (long long)p.k_stride_a[ord_a[d]];
+      ob += (long long)ib[d] * (long long)p.k_stride_b[ord_b[d]];
+      if (p.k_metric[ord_a[d]] && ia[d] > 0) neg = !neg;  // the sign comes from self's (a's) metric iterator
     }
     t.off_a[k] = (int)oa;
     t.off_b[k] = (int)ob;
     t.sign[k] = neg ? 1 : 0;
-    for (uint32_t d = nd; d-- > 0;) {  // odometer, last contracted dim fastest
-      if (++idx[d] < p.k_dim[d]) break;
-      idx[d] = 0;
+    for (uint32_t d = nd; d-- > 0;) {
+      if (++ia[d] < p.k_dim[ord_a[d]]) break;
+      ia[d] = 0;
+    }
+    for (uint32_t d = nd; d-- > 0;) {
+      if (++ib[d] < p.k_dim[ord_b[d]]) break;
+      ib[d] = 0;
     }
   }
   return t;
@@ -231,7 +246,7 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
   const int out_layout = a->batched() ? a->layout : (b->batched() ? b->layout : SPN_POINT_MAJOR);
   std::unique_ptr<spn_tensor> res(new_batched(ctx, rs, n_points, out_dtype, out_layout, nullptr));
   const bool point_fastest = out_layout == SPN_COMPONENT_MAJOR;
-  KTables kt = build_k_tables(plan);
+  KTables kt = build_k_tables(plan, ctx->emulate_reference_pairing);
   DevOutMap map = out_map_of(plan);
   if (kt.off_a.size() > (size_t)1 << 24) throw Error(SPN_ERR_INVALID, "contracted volume too large for the table path");
 
@@ -426,6 +441,10 @@ int spn_ctx_create(int device, spn_ctx** out) {
 void spn_ctx_destroy(spn_ctx* ctx) { delete ctx; }
 int spn_ctx_set_stream(spn_ctx* ctx, void* s) {
   ctx->stream = (cudaStream_t)s;
+  return SPN_OK;
+}
+int spn_ctx_set_reference_quirks(spn_ctx* ctx, int emulate_interleaved_pairing) {
+  ctx->emulate_reference_pairing = emulate_interleaved_pairing != 0;
   return SPN_OK;
 }
 int spn_ctx_synchronize(spn_ctx* ctx) {

@@ -566,7 +566,7 @@ struct spn_net {
         case ST_CONTRACT: {
           SymT& B = sym[s.b];
           spn_contract_plan p = plan_contract(values[s.a].st, values[s.b].st);
-          KTables kt = build_k_tables(p);
+          KTables kt = build_k_tables(p, ctx && ctx->emulate_reference_pairing);
           std::vector<uint32_t> idx(p.order_out, 0);
           std::vector<Term> tr, ti;
           for (uint64_t o = 0; o < p.size_out; ++o) {

@@ -16,6 +16,7 @@ struct spn_ctx {
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
   int sm_count = 148;
+  bool emulate_reference_pairing = false;  // SURVEY K-note 3, see build_k_tables
 };
 
 struct spn_tensor {
@@ -82,7 +83,7 @@ struct KTables {
   std::vector<int> off_a, off_b;
   std::vector<unsigned char> sign;
 };
-KTables build_k_tables(const spn_contract_plan& p);
+KTables build_k_tables(const spn_contract_plan& p, bool emulate_reference_pairing = false);
 DevOutMap out_map_of(const spn_contract_plan& p);
 
 spn_tensor* new_shared_dense(spn_ctx* ctx, const Structure& st, const double2* data);

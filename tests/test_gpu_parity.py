@@ -674,3 +674,32 @@ def test_execute_host_pipeline_vs_oracle(ctx, name, n_points, scale):
         net.execute_host(arrays[:1], out=out)
     with pytest.raises(sp.SpensoError):
         net.execute_host(arrays, out=None, want_sum=False)
+
+
+def test_reference_interleaved_pairing_quirk(ctx):
+    """SURVEY K-note 3: MultiContractInterleaved zips the two fibres without a permutation.  Default = every
+    contracted slot meets its dual (== oracle default); with the triage switch on the engine reproduces the
+    reference's pairing (== oracle with emulate_reference_pairing)."""
+    cases = [
+        ([(1, 0, 0, 3, 52), (2, 0, 0, 2, 15), (3, 0, 2, 2, 58), (3, 0, -1, 2, 20)],
+         [(1, 0, 0, 2, 16), (1, 0, 1, 4, 7), (3, 0, 1, 2, 20), (3, 0, -2, 2, 58)]),
+        ([(1, 0, 2, 3, 24), (3, 0, 3, 3, 51), (3, 0, -1, 2, 52)],
+         [(1, 0, 0, 3, 39), (2, 0, 0, 2, 44), (3, 0, 1, 2, 52), (3, 0, -3, 3, 51)]),
+        ([(1, 0, 1, 2, 35), (3, 0, 2, 2, 30), (3, 0, 2, 2, 61), (3, 0, 2, 2, 62), (3, 0, -1, 3, 59)],
+         [(3, 0, 1, 3, 59), (3, 0, 1, 3, 63), (3, 0, -2, 2, 30), (3, 0, -2, 2, 61), (3, 0, -3, 3, 15)]),
+    ]
+    rng = np.random.default_rng(3)
+    try:
+        for a, b in cases:
+            ca, cb = np.array(a, dtype=sp.SLOT_DTYPE), np.array(b, dtype=sp.SLOT_DTYPE)
+            ta, oa, _ = dense_pair(ctx, rng, ca, 3)
+            tb, ob, _ = dense_pair(ctx, rng, cb, 3)
+            want = np.stack([x.contract(y).to_dense() for x, y in zip(oa, ob)])
+            quirk = np.stack([x.contract(y, emulate_reference_pairing=True).to_dense() for x, y in zip(oa, ob)])
+            assert np.abs(want - quirk).max() > 1e-6           # the two pairings really differ here
+            ctx.set_reference_quirks(False)
+            assert rel_err(ta.contract(tb).to_numpy(), want) <= TOL
+            ctx.set_reference_quirks(True)
+            assert rel_err(ta.contract(tb).to_numpy(), quirk) <= TOL
+    finally:
+        ctx.set_reference_quirks(False)
