@@ -35,10 +35,20 @@ WORKLOAD_DESC = {
             "Complex<f64>, 2^20 synthetic phase-space points per GPU",
     "cfg3": "cfg3: SU(3) colour-factor network X.T + D.f (Dense per point x Sparse shared)",
     "cfg5": "cfg5: one-loop numerator network (gl_03 topology, massive), Monte-Carlo sum",
+    "cfg2m": "cfg2m: cfg2 with device-side leaf filling — inputs are the four massless momenta, the spinors are built "
+             "inside the kernel (SURVEY 8f-1)",
     "cfg4": "cfg4: dense pairwise contraction of rank-6 c64 tensors, dim-32 indices, 3 shared (ZGEMM 32768^3, FP64 DMMA)",
 }
-DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg4": 1}
-SCALE = {"cfg2": 1.0, "cfg3": 1.0, "cfg5": 100.0}
+DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg2m": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg4": 1}
+SCALE = {"cfg2": 1.0, "cfg2m": 1.0, "cfg3": 1.0, "cfg5": 100.0}
+
+
+def make_inputs(spec, wl, n, seed):
+    from spenso_b200 import workloads
+
+    if wl == "cfg2m":
+        return workloads.massless_momenta(n, seed)
+    return workloads.synthetic_inputs(spec, n, seed, scale=SCALE[wl], real=(wl == "cfg5"))
 
 
 def parse_args():
@@ -104,7 +114,7 @@ def run_reference(args):
     spec = workloads.WORKLOADS[args.workload]()
     n_threads = os.cpu_count() or 1
     real = args.workload == "cfg5"
-    fn = lambda n: workloads.synthetic_inputs(spec, n, 1234, scale=SCALE[args.workload], real=real)
+    fn = lambda n: make_inputs(spec, args.workload, n, 1234)
     points = args.points or DEFAULT_POINTS[args.workload]
     # each step = a bounded sample of the workload; keep the whole run within a few minutes
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -244,7 +254,7 @@ def run_b200(args):
     first_point, n_mine = shard_range(n * world, rank, world)   # weak scaling: n points per rank per step
     assert n_mine == n
     for r in range(rot):
-        arrs = workloads.synthetic_inputs(spec, n, 1234 + 1000 * rank + r, scale=SCALE[wl], real=(wl == "cfg5"))
+        arrs = make_inputs(spec, wl, n, 1234 + 1000 * rank + r)
         if r == 0:   # one pinned host copy feeds the e2e leg (its H2D overwrites the device inputs every step)
             host_sets.append([torch.from_numpy(a.view(np.float64).reshape(n, -1)).pin_memory() for a in arrs])
         tens = []
@@ -385,7 +395,7 @@ def run_b200(args):
         cpu = None
         if not args.no_cpu_baseline and world == 1:   # cpu_baseline: rank 0 at N=1 only
             nthr = os.cpu_count() or 1
-            fn = lambda m: workloads.synthetic_inputs(spec, m, 1234, scale=SCALE[wl], real=(wl == "cfg5"))
+            fn = lambda m: make_inputs(spec, wl, m, 1234)
             rate, sample, secs = oracle_rate(spec, fn, nthr, args.cpu_seconds)
             cpu = {"value": rate, "unit": UNIT, "cores": nthr, "kind": "port",
                    "sample": f"{sample} points of the same workload, {nthr} threads, {secs:.1f} s "

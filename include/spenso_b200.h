@@ -193,6 +193,23 @@ int spn_net_leaf_batched(spn_net* net, const spn_slot* slots, uint32_t n, int dt
  * spn_net_leaf_batched; slots are in the same argument order, same representations and dimensions.
  * No new input is created — both leaves read the input bound to the original. */
 int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t n);
+/* Leaf filling ON THE DEVICE: a per-point tensor whose components are small expressions of
+ * components of other per-point leaves — the role of the reference's EvalTensor / TensorEvaluator, which
+ * evaluates parametric leaves on the host for every point (spenso/src/tensors/parametric.rs:2266-2720,
+ * network/symbolica_interop.rs:617-640).  The expressions are inlined into the fused kernel, so only the raw
+ * kinematics cross PCIe and HBM.
+ *   params: n_params pairs (batched leaf node id, canonical flat component of that leaf)
+ *   consts: n_consts complex constants (re, im)
+ *   code:   n_code pairs (opcode, argument), postfix; one program per component in ARGUMENT-order row major,
+ *           separated by (SPN_EXPR_END, 0).  SPN_EXPR_SQRT needs an argument whose imaginary part is structurally
+ *           zero (use SPN_EXPR_RE) and non-negative at run time.
+ * Fused executor only. */
+enum {
+  SPN_EXPR_PARAM = 0, SPN_EXPR_CONST = 1, SPN_EXPR_ADD = 2, SPN_EXPR_SUB = 3, SPN_EXPR_MUL = 4, SPN_EXPR_DIV = 5,
+  SPN_EXPR_NEG = 6, SPN_EXPR_CONJ = 7, SPN_EXPR_SQRT = 8, SPN_EXPR_RE = 9, SPN_EXPR_IM = 10, SPN_EXPR_END = 11
+};
+int spn_net_leaf_function(spn_net* net, const spn_slot* slots, uint32_t n, const int32_t* params, uint32_t n_params,
+                          const double* consts_reim, uint32_t n_consts, const int32_t* code, uint32_t n_code);
 /* point-independent local tensor (Network::from_tensor): an existing shared tensor */
 int spn_net_leaf_shared(spn_net* net, const spn_tensor* shared);
 /* library tensor with concrete indices in argument order (NetworkLeaf::LibraryKey + get_lib_data,

@@ -421,6 +421,19 @@ class Network:
         s = slots(sl)
         return node_id(lib().spn_net_leaf_reindex(self.h, leaf, ptr(s), len(s)))
 
+    def function(self, sl, components) -> int:
+        """Per-point leaf computed on the device: `components` are spenso_b200.expr expressions, one per
+        component in row-major order over `sl` as written (spn_net_leaf_function)."""
+        from .expr import compile_components
+
+        s = slots(sl)
+        params, consts, code = compile_components(components)
+        pa = np.ascontiguousarray(params, dtype=np.int32).reshape(-1)
+        ca = np.ascontiguousarray(consts, dtype=np.complex128)
+        co = np.ascontiguousarray(code, dtype=np.int32).reshape(-1)
+        return node_id(lib().spn_net_leaf_function(self.h, ptr(s), len(s), ptr(pa), len(params), ptr(ca), len(consts),
+                                                   ptr(co), len(code)))
+
     def tensor(self, t: _Tensor) -> int:
         """Network::from_tensor for a point-independent local tensor."""
         self._keep.append(t)

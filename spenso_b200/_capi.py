@@ -86,6 +86,7 @@ SYMBOLS = {
     "spn_net_destroy": (None, [_P]),
     "spn_net_leaf_batched": (_I, [_P, _P, _U32, _I]),
     "spn_net_leaf_reindex": (_I, [_P, _I, _P, _U32]),
+    "spn_net_leaf_function": (_I, [_P, _P, _U32, _P, _U32, _P, _U32, _P, _U32]),
     "spn_net_leaf_shared": (_I, [_P, _P]),
     "spn_net_leaf_library": (_I, [_P, _I, _P, _U32]),
     "spn_net_leaf_library_custom": (_I, [_P, _P, _U32, _P, _P, _U64]),

@@ -35,7 +35,7 @@ using namespace spn;
 
 namespace {
 
-enum { LEAF_BATCHED = 0, LEAF_CONST = 1, NODE_OP = 2 };
+enum { LEAF_BATCHED = 0, LEAF_CONST = 1, NODE_OP = 2, LEAF_FUNCTION = 3 };
 
 struct Node {
   int kind = LEAF_CONST;
@@ -56,6 +56,11 @@ struct Node {
   std::vector<uint64_t> flat_map;
   int alias_of = -1;  // node id of the batched leaf this one re-indexes
   bool is_scalar_leaf = false;  // created by spn_net_leaf_scalar (NetworkLeaf::Scalar)
+  // LEAF_FUNCTION: per-point tensor computed on the device from components of other batched leaves
+  std::vector<std::pair<int, uint64_t>> fn_params;  // (leaf node id, canonical flat component)
+  std::vector<double2> fn_consts;
+  std::vector<std::vector<std::pair<int, int>>> fn_code;  // per CANONICAL component: postfix (op, arg)
+  std::vector<int32_t> fn_raw_code;                         // as given (argument order), for export
 };
 
 enum StepOp { ST_CONTRACT = 0, ST_ADD = 1, ST_NEG = 2, ST_CONJ = 3, ST_RECIP = 4 };
@@ -231,6 +236,7 @@ struct spn_net {
   std::vector<Step> steps;
   std::vector<std::pair<int, int>> schedule;  // (node a, node b) of every pairwise contraction, -1 = intermediate
   int result_value = -1;
+  std::map<int, int> node_value;  // node id -> value id of the compiled schedule
   // fused
   Program prog;
   std::vector<CE> result_el;
@@ -400,7 +406,13 @@ struct spn_net {
     auto it = memo.find(id);
     if (it != memo.end()) return it->second;
     int v = -1;
-    if (nodes[(size_t)id].kind != NODE_OP) {
+    if (nodes[(size_t)id].kind == LEAF_FUNCTION) {
+      // make sure the leaves it reads exist as values (they may not appear anywhere else in the graph)
+      std::vector<int> deps;
+      for (auto& pr : nodes[(size_t)id].fn_params) deps.push_back(pr.first);
+      for (int d : deps) build(d, memo);
+      v = new_value(nodes[(size_t)id].st, true, id);
+    } else if (nodes[(size_t)id].kind != NODE_OP) {
       v = new_value(nodes[(size_t)id].st, nodes[(size_t)id].kind == LEAF_BATCHED, id);
       values[(size_t)v].scalar_kind = nodes[(size_t)id].is_scalar_leaf;
     } else {
@@ -544,11 +556,99 @@ struct spn_net {
     return e;
   }
 
+  // LEAF_FUNCTION: run each component's postfix program symbolically (device-side leaf filling — what the
+  // reference does per point on the host with EvalTensor evaluators, tensors/parametric.rs:2266-2720)
+  std::vector<CE> sym_function_leaf(const Node& n, std::vector<SymT>& sym) {
+    std::vector<CE> el(n.st.size());
+    std::vector<CE> stack;
+    auto pop = [&]() {
+      if (stack.empty()) throw Error(SPN_ERR_INVALID, "function leaf: stack underflow");
+      CE e = stack.back();
+      stack.pop_back();
+      return e;
+    };
+    for (uint64_t c = 0; c < n.st.size(); ++c) {
+      stack.clear();
+      for (auto& oa : n.fn_code[c]) {
+        switch (oa.first) {
+          case SPN_EXPR_PARAM: {
+            auto& pr = n.fn_params.at((size_t)oa.second);
+            stack.push_back(sym_get(sym[(size_t)node_value.at(pr.first)], pr.second));
+            break;
+          }
+          case SPN_EXPR_CONST: {
+            double2 k = n.fn_consts.at((size_t)oa.second);
+            stack.push_back(CE{rr_const(k.x), rr_const(k.y)});
+            break;
+          }
+          case SPN_EXPR_ADD:
+          case SPN_EXPR_SUB: {
+            CE b = pop(), a = pop();
+            const double sg = oa.first == SPN_EXPR_ADD ? 1.0 : -1.0;
+            std::vector<Term> tr, ti;
+            Program::push_rr(tr, a.re, 1.0);
+            Program::push_rr(tr, b.re, sg);
+            Program::push_rr(ti, a.im, 1.0);
+            Program::push_rr(ti, b.im, sg);
+            stack.push_back(CE{prog.sum(tr), prog.sum(ti)});
+            break;
+          }
+          case SPN_EXPR_MUL: {
+            CE b = pop(), a = pop();
+            std::vector<Term> tr, ti;
+            Program::push_cmul(tr, ti, a, b, 1.0);
+            stack.push_back(CE{prog.sum(tr), prog.sum(ti)});
+            break;
+          }
+          case SPN_EXPR_DIV: {
+            CE b = pop(), a = pop();
+            stack.push_back(prog.divide(a, b));
+            break;
+          }
+          case SPN_EXPR_NEG: {
+            CE a = pop();
+            stack.push_back(CE{rr_neg(a.re), rr_neg(a.im)});
+            break;
+          }
+          case SPN_EXPR_CONJ: {
+            CE a = pop();
+            stack.push_back(CE{a.re, rr_neg(a.im)});
+            break;
+          }
+          case SPN_EXPR_SQRT: {
+            CE a = pop();
+            if (!a.im.is_zero()) throw Error(SPN_ERR_INVALID, "function leaf: sqrt needs a real argument (take re() first)");
+            stack.push_back(CE{prog.real_sqrt(a.re), rr_const(0.0)});
+            break;
+          }
+          case SPN_EXPR_RE: {
+            CE a = pop();
+            stack.push_back(CE{a.re, rr_const(0.0)});
+            break;
+          }
+          case SPN_EXPR_IM: {
+            CE a = pop();
+            stack.push_back(CE{a.im, rr_const(0.0)});
+            break;
+          }
+          default: throw Error(SPN_ERR_INVALID, "function leaf: unknown opcode");
+        }
+      }
+      if (stack.size() != 1) throw Error(SPN_ERR_INVALID, "function leaf: a component program must leave exactly one value");
+      el[c] = stack.back();
+    }
+    return el;
+  }
+
   void compile_fused() {
     std::vector<SymT> sym(values.size());
     for (size_t v = 0; v < values.size(); ++v) {
       if (values[v].leaf < 0) continue;
       const Node& n = nodes[values[v].leaf];
+      if (n.kind == LEAF_FUNCTION) {
+        sym[v].el = sym_function_leaf(n, sym);
+        continue;
+      }
       sym[v].el = sym_leaf(values[v]);
       if (n.kind == LEAF_BATCHED) {
         sym[v].input = n.input;
@@ -782,6 +882,10 @@ struct spn_net {
           name[(size_t)i.dst] = "v" + std::to_string(i.dst);
           o << "    const double v" << i.dst << " = " << signedv(i.z, i.sz) << " + " << lit(i.kc) << ";\n";
           break;
+        case I_SQRT:
+          name[(size_t)i.dst] = "v" + std::to_string(i.dst);
+          o << "    const double v" << i.dst << " = sqrt(" << scaled(i.k, i.x) << ");\n";
+          break;
         case I_DIV:
           name[(size_t)i.dst] = "v" + std::to_string(i.dst);
           if (i.x < 0)
@@ -908,6 +1012,7 @@ void run_stepwise(spn_net* net, const spn_tensor* const* inputs, spn_tensor* out
     const Value& V = net->values[v];
     if (V.leaf < 0) continue;
     const Node& n = net->nodes[(size_t)V.leaf];
+    if (n.kind == LEAF_FUNCTION) throw Error(SPN_ERR_INVALID, "function leaves need the fused executor");
     if (n.kind == LEAF_BATCHED) {
       if (v_is_alias(net, n)) {
         if (!n.flat_map.empty())
@@ -1036,6 +1141,56 @@ int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t
   return (int)net->nodes.size() - 1;
   NET_CATCH(true)
 }
+int spn_net_leaf_function(spn_net* net, const spn_slot* slots, uint32_t n, const int32_t* params, uint32_t n_params,
+                          const double* consts_reim, uint32_t n_consts, const int32_t* code, uint32_t n_code) {
+  NET_TRY
+  check_uncompiled(net);
+  Node nd;
+  nd.kind = LEAF_FUNCTION;
+  nd.args.assign(slots, slots + n);
+  nd.st = canonicalize(nd.args, &nd.perm);
+  for (uint32_t k = 0; k < n_params; ++k) {
+    const int leaf = params[2 * k];
+    if (leaf < 0 || leaf >= (int)net->nodes.size() || net->nodes[(size_t)leaf].kind != LEAF_BATCHED)
+      throw Error(SPN_ERR_INVALID, "function leaf: parameters must be components of batched leaves");
+    if (params[2 * k + 1] < 0 || (uint64_t)params[2 * k + 1] >= net->nodes[(size_t)leaf].st.size())
+      throw Error(SPN_ERR_INVALID, "function leaf: parameter component out of range");
+    nd.fn_params.emplace_back(leaf, (uint64_t)params[2 * k + 1]);
+  }
+  for (uint32_t k = 0; k < n_consts; ++k) nd.fn_consts.push_back(make_double2(consts_reim[2 * k], consts_reim[2 * k + 1]));
+  nd.fn_raw_code.assign(code, code + 2 * (size_t)n_code);
+  // split into per-component programs (argument order), then place them in canonical order
+  std::vector<std::vector<std::pair<int, int>>> comps(1);
+  for (uint32_t k = 0; k < n_code; ++k) {
+    const int op = code[2 * k], arg = code[2 * k + 1];
+    if (op == SPN_EXPR_END) {
+      comps.emplace_back();
+      continue;
+    }
+    if (op == SPN_EXPR_PARAM && (arg < 0 || arg >= (int)n_params)) throw Error(SPN_ERR_INVALID, "function leaf: bad parameter index");
+    if (op == SPN_EXPR_CONST && (arg < 0 || arg >= (int)n_consts)) throw Error(SPN_ERR_INVALID, "function leaf: bad constant index");
+    comps.back().emplace_back(op, arg);
+  }
+  if (comps.back().empty()) comps.pop_back();
+  const uint64_t size = nd.st.size();
+  if (comps.size() != size) throw Error(SPN_ERR_DIMENSION, "function leaf: one program per component is required");
+  std::vector<uint64_t> arg_stride(n, 1);
+  for (size_t i = n; i-- > 1;) arg_stride[i - 1] = arg_stride[i] * nd.args[i].dim;
+  nd.fn_code.resize(size);
+  std::vector<uint32_t> idx(n, 0);
+  for (uint64_t f = 0; f < size; ++f) {  // f canonical; g = the same index tuple in argument order
+    uint64_t g = 0;
+    for (uint32_t c = 0; c < n; ++c) g += (uint64_t)idx[c] * arg_stride[(size_t)nd.perm[c]];
+    nd.fn_code[f] = comps[g];
+    for (uint32_t c = n; c-- > 0;) {
+      if (++idx[c] < nd.st.slots[c].dim) break;
+      idx[c] = 0;
+    }
+  }
+  net->nodes.push_back(std::move(nd));
+  return (int)net->nodes.size() - 1;
+  NET_CATCH(true)
+}
 int spn_net_leaf_shared(spn_net* net, const spn_tensor* shared) {
   NET_TRY
   check_uncompiled(net);
@@ -1140,6 +1295,16 @@ const char* spn_net_to_json(spn_net* net) {
       o << "{\"kind\":\"reindex\",\"leaf\":" << n.alias_of << ",\"slots\":";
       json_slots(o, n.args);
       o << "}";
+    } else if (n.kind == LEAF_FUNCTION) {
+      o << "{\"kind\":\"function\",\"slots\":";
+      json_slots(o, n.args);
+      o << ",\"params\":[";
+      for (size_t k = 0; k < n.fn_params.size(); ++k) o << (k ? "," : "") << "[" << n.fn_params[k].first << "," << n.fn_params[k].second << "]";
+      o << "],\"consts\":[";
+      for (size_t k = 0; k < n.fn_consts.size(); ++k) o << (k ? "," : "") << "[" << lit(n.fn_consts[k].x) << "," << lit(n.fn_consts[k].y) << "]";
+      o << "],\"code\":[";
+      for (size_t k = 0; k < n.fn_raw_code.size(); ++k) o << (k ? "," : "") << n.fn_raw_code[k];
+      o << "]}";
     } else if (n.kind == LEAF_CONST && n.is_scalar_leaf) {
       o << "{\"kind\":\"scalar\",\"re\":" << lit(n.dense[0].x) << ",\"im\":" << lit(n.dense[0].y) << "}";
     } else if (n.kind == LEAF_CONST) {
@@ -1206,6 +1371,21 @@ int spn_net_from_json(spn_ctx* ctx, const char* text, spn_net** out) {
         if (!sparse && ent.size() != st.size()) throw Error(SPN_ERR_DIMENSION, "plan json: dense tensor needs every entry");
         id = add_const_leaf(net.get(), st, ent, sparse, nullptr);
         if (!sparse) net->nodes.back().entries.clear();
+      } else if (kind == "function") {
+        auto sl = slots_of_json(jn.at("slots"));
+        std::vector<int32_t> params, code;
+        std::vector<double> consts;
+        for (auto& e : jn.at("params").arr()) {
+          params.push_back((int32_t)e.arr().at(0).i64());
+          params.push_back((int32_t)e.arr().at(1).i64());
+        }
+        for (auto& e : jn.at("consts").arr()) {
+          consts.push_back(e.arr().at(0).num());
+          consts.push_back(e.arr().at(1).num());
+        }
+        for (auto& e : jn.at("code").arr()) code.push_back((int32_t)e.i64());
+        id = spn_net_leaf_function(net.get(), sl.data(), (uint32_t)sl.size(), params.data(), (uint32_t)params.size() / 2,
+                                   consts.data(), (uint32_t)consts.size() / 2, code.data(), (uint32_t)code.size() / 2);
       } else if (kind == "scalar") {
         id = spn_net_leaf_scalar(net.get(), jn.at("re").num(), jn.at("im").num());
       } else if (kind == "op") {
@@ -1253,6 +1433,7 @@ int spn_net_compile(spn_net* net, int exec_mode) {
     net->rng_state = 0x9e3779b97f4a7c15ull * (uint64_t)(trial + 1);
     std::map<int, int> memo;
     net->result_value = net->build(net->root, memo);
+    net->node_value = memo;
     if (exec_mode == SPN_EXEC_FUSED) net->compile_fused();
   };
   build_with(0);

@@ -48,7 +48,8 @@ enum InsOp : uint8_t {
   I_MULK,   // dst = k * x
   I_FMAK,   // dst = k * x + sz * z
   I_ADDK,   // dst = sz * z + kc
-  I_DIV     // dst = k * x / y
+  I_DIV,    // dst = k * x / y   (x < 0: the numerator is the literal k)
+  I_SQRT    // dst = sqrt(k * x)
 };
 
 struct Ins {
@@ -235,6 +236,40 @@ struct Program {
     return CE{div(a.re, 1.0), div(a.im, -1.0)};
   }
 
+  // a / b
+  CE divide(const CE& a, const CE& b) {
+    if (b.im.is_zero()) {  // real denominator: two real divisions
+      auto div = [&](RR n) -> RR {
+        if (n.is_zero()) return rr_const(0.0);
+        if (b.re.is_const()) return RR{n.var, n.coef / b.re.coef};
+        Ins i;
+        i.op = I_DIV;
+        i.x = n.is_const() ? -1 : n.var;
+        i.y = b.re.var;
+        i.k = n.coef / b.re.coef;
+        i.dst = fresh();
+        ins.push_back(i);
+        return RR{i.dst, 1.0};
+      };
+      return CE{div(a.re), div(a.im)};
+    }
+    CE r = reciprocal(b);
+    std::vector<Term> tr, ti;
+    push_cmul(tr, ti, a, r, 1.0);
+    return CE{sum(tr), sum(ti)};
+  }
+  // sqrt of a quantity known to be real (imaginary part structurally zero); the caller guarantees >= 0
+  RR real_sqrt(RR a) {
+    if (a.is_const()) return rr_const(std::sqrt(a.coef));
+    Ins i;
+    i.op = I_SQRT;
+    i.x = a.var;
+    i.k = a.coef;
+    i.dst = fresh();
+    ins.push_back(i);
+    return RR{i.dst, 1.0};
+  }
+
   // ---- dead code elimination + statistics ---------------------------------------------------
   // keep only instructions that feed `roots`; returns the number of FP64 arithmetic instructions
   struct Stats {
@@ -263,6 +298,7 @@ struct Program {
         case I_MUL: s.n_fp += (std::fabs(i.k) == 1.0) ? 1 : 2; break;
         case I_FMA: s.n_fp += (std::fabs(i.k) == 1.0) ? 1 : 2; s.n_fma++; break;
         case I_DIV: s.n_fp += 8; break;
+        case I_SQRT: s.n_fp += 10; break;
         default: s.n_fp += 1; break;
       }
     }

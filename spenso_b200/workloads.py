@@ -54,6 +54,11 @@ class NetSpec:
     def scalar(self, c) -> int:
         return self.add("scalar", complex(c))
 
+    def function(self, sl, build) -> int:
+        """Device-filled leaf: build(params_of) -> list of expr components, where params_of(node, n) gives the
+        expr.Param components of an earlier batched node of THIS spec (ids are mapped when the network is built)."""
+        return self.add("function", list(sl), build)
+
     def product(self, *ch) -> int:
         return self.add("op", OP_PRODUCT, list(ch), 1)
 
@@ -83,6 +88,10 @@ def build_engine(spec: NetSpec, ctx, mode: int = FUSED) -> Network:
             ids[k] = net.library_custom(node[1], node[2])
         elif kind == "scalar":
             ids[k] = net.scalar(node[1])
+        elif kind == "function":
+            from .expr import Param
+
+            ids[k] = net.function(node[1], node[2](lambda n, size: Param.vector(ids[n], size)))
         else:
             ids[k] = net.op(node[1], [ids[c] for c in node[2]], node[3])
     net.set_root(ids[spec.root])
@@ -132,6 +141,54 @@ def eemumu() -> NetSpec:
     s.root = s.product(vb, g1, u, ub, g2, v)
     s.algorithmic_bytes = 4 * 64 + 16
     return s
+
+
+def massless_spinors(p):
+    """Helicity spinors of a massless momentum p = (E, px, py, pz) in the chiral (Weyl) basis of
+    spenso-hep-lib's gamma_data_weyl (gamma^0 = [[0,1],[1,0]], gamma^k = [[0,s_k],[-s_k,0]]), as expression
+    components.  u_plus solves pslash u = 0 with gamma^5 u = +u; ubar = u^dagger gamma^0."""
+    from .expr import re, sqrt
+
+    E, px, py, pz = (re(c) for c in p)
+    a = sqrt(E + pz)                       # sqrt(p+)
+    b = (px + 1j * py) / a                 # p_perp / sqrt(p+)
+    u_plus = [0.0, 0.0, a, b]              # right-handed: lower two components
+    u_minus = [-b.conj(), a, 0.0, 0.0]     # left-handed: upper two components
+    ubar_plus = [a, b.conj(), 0.0, 0.0]    # u_plus^dagger gamma^0
+    ubar_minus = [0.0, 0.0, -b, a]         # u_minus^dagger gamma^0
+    return {"u+": u_plus, "u-": u_minus, "ubar+": ubar_plus, "ubar-": ubar_minus}
+
+
+def eemumu_from_momenta() -> NetSpec:
+    """cfg2 with device-side leaf filling: the per-point inputs are the four massless momenta
+    (4 x 64 B as c64 Minkowski vectors, or 4 x 32 B as f64) and the spinors vbar(p2), u(p1), ubar(p3), v(p4)
+    (fixed helicities; massless v(p) of helicity h == u(p) of helicity -h) are built inside the kernel."""
+    s = NetSpec("cfg2m_eemumu_from_momenta")
+    p = [s.batched([_m(100 + k)], f"p{k + 1}") for k in range(4)]
+    sp1 = lambda k, key, a: s.function([_b(a)], lambda P, k=k, key=key: massless_spinors(P(p[k], 4))[key])
+    vb = sp1(1, "ubar-", 1)   # vbar_+(p2) = ubar_-(p2)
+    u = sp1(0, "u-", 2)
+    ub = sp1(2, "ubar-", 3)
+    v = sp1(3, "u-", 4)       # v_+(p4) = u_-(p4)
+    g1 = s.lib(LIB_GAMMA_WEYL, [_b(1), _b(2), _m(1)])
+    g2 = s.lib(LIB_GAMMA_WEYL, [_b(3), _b(4), _m(1)])
+    s.root = s.product(vb, g1, u, ub, g2, v)
+    s.algorithmic_bytes = 4 * 64 + 16
+    return s
+
+
+def massless_momenta(n_points: int, seed: int):
+    """Four massless momenta per point (random directions and energies; no momentum conservation needed for a
+    throughput workload), [n, 4] complex128 each with zero imaginary parts."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(4):
+        E = rng.uniform(10.0, 100.0, n_points)
+        ct = rng.uniform(-0.95, 0.95, n_points)
+        ph = rng.uniform(0, 2 * np.pi, n_points)
+        st = np.sqrt(1 - ct * ct)
+        out.append(np.stack([E, E * st * np.cos(ph), E * st * np.sin(ph), E * ct], axis=1).astype(np.complex128))
+    return out
 
 
 # ---- cfg3 ---------------------------------------------------------------------------------------------
@@ -231,7 +288,7 @@ def one_loop_massive() -> NetSpec:
 
 
 WORKLOADS = {"cfg1": gamma_trace4, "cfg2": eemumu, "cfg3": su3_colour, "cfg5": one_loop_massive,
-             "gl03": one_loop_gl03}
+             "gl03": one_loop_gl03, "cfg2m": eemumu_from_momenta}
 
 
 def synthetic_inputs(spec: NetSpec, n_points: int, seed: int, scale: float = 1.0, real: bool = False) -> List[np.ndarray]:

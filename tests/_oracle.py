@@ -446,6 +446,25 @@ def net_from_spec(spec, arrays, point: int = 0):
             ids[k] = net.tensor(t)
             b_nodes.append(ids[k])
             b_arrays.append(arrays[inp])
+        elif kind == "function":
+            # device-filled leaf: the oracle side fills it on the host (numpy, test infrastructure) and treats it
+            # as one more per-point tensor — the reference fills such leaves with its host evaluators
+            import _expr_eval
+            from spenso_b200.expr import Param
+
+            sl = _spec_slots(node[1])
+            comps = node[2](lambda nidx, size: Param.vector(nidx, size))
+            leaf_arrays = {nidx: arrays[node_input[nidx]] for nidx in node_input}
+            vals = np.stack([_expr_eval.evaluate(c, leaf_arrays) for c in comps], axis=1)
+            canon, perm, _, _ = order_structure(sl) if len(sl) else (sl, [], 0, 0)
+            shape = [int(d) for d in sl["dim"]]
+            vals = vals.reshape([vals.shape[0]] + shape).transpose([0] + [int(q) + 1 for q in perm])
+            vals = np.ascontiguousarray(vals).reshape(vals.shape[0], -1)
+            t = OTensor.dense(canon, vals[point], canonicalize=False)
+            net._keep.append(t)
+            ids[k] = net.tensor(t)
+            b_nodes.append(ids[k])
+            b_arrays.append(vals)
         elif kind == "lib":
             which, sl = node[1], _spec_slots(node[2])
             l = OLib.metric(sl[0]) if which == 6 else OLib.builtin(which)
