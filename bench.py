@@ -37,10 +37,11 @@ WORKLOAD_DESC = {
     "cfg5": "cfg5: one-loop numerator network (gl_03 topology, massive), Monte-Carlo sum",
     "cfg2m": "cfg2m: cfg2 with device-side leaf filling — inputs are the four massless momenta, the spinors are built "
              "inside the kernel (SURVEY 8f-1)",
+    "cfg2mr": "cfg2mr: cfg2m with the momenta stored as f64 (32 B each): 144 B per evaluation",
     "cfg4": "cfg4: dense pairwise contraction of rank-6 c64 tensors, dim-32 indices, 3 shared (ZGEMM 32768^3, FP64 DMMA)",
 }
-DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg2m": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg4": 1}
-SCALE = {"cfg2": 1.0, "cfg2m": 1.0, "cfg3": 1.0, "cfg5": 100.0}
+DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg2m": 1 << 20, "cfg2mr": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg4": 1}
+SCALE = {"cfg2": 1.0, "cfg2m": 1.0, "cfg2mr": 1.0, "cfg3": 1.0, "cfg5": 100.0}
 
 
 def make_inputs(spec, wl, n, seed):
@@ -48,6 +49,8 @@ def make_inputs(spec, wl, n, seed):
 
     if wl == "cfg2m":
         return workloads.massless_momenta(n, seed)
+    if wl == "cfg2mr":
+        return [np.ascontiguousarray(a.real) for a in workloads.massless_momenta(n, seed)]
     return workloads.synthetic_inputs(spec, n, seed, scale=SCALE[wl], real=(wl == "cfg5"))
 
 
@@ -248,7 +251,7 @@ def run_b200(args):
     want_sum = wl == "cfg5"        # Monte-Carlo estimate: no per-point store, only the sum over points
 
     # synthetic kinematics: ROT rotating input sets so that consecutive steps never re-read what L2 holds
-    bytes_in = sum(sz for _, sz in spec.inputs) * 16 * n
+    bytes_in = sum(sz * (16 if dt == sp.C64 else 8) for (_, sz), dt in zip(spec.inputs, spec.input_dtypes)) * n
     rot = max(2, min(8, int(np.ceil(2.5 * 126e6 / bytes_in)) + 1))
     host_sets, dev_sets = [], []
     first_point, n_mine = shard_range(n * world, rank, world)   # weak scaling: n points per rank per step
@@ -258,8 +261,8 @@ def run_b200(args):
         if r == 0:   # one pinned host copy feeds the e2e leg (its H2D overwrites the device inputs every step)
             host_sets.append([torch.from_numpy(a.view(np.float64).reshape(n, -1)).pin_memory() for a in arrs])
         tens = []
-        for sl, a in zip(leaf_slots, arrs):
-            t = sp.BatchTensor.empty(ctx, sl, n, sp.C64, layout)
+        for sl, a, dt in zip(leaf_slots, arrs, spec.input_dtypes):
+            t = sp.BatchTensor.empty(ctx, sl, n, dt, layout)
             t.upload(a)
             tens.append(t)
         dev_sets.append(tens)
@@ -339,7 +342,8 @@ def run_b200(args):
     # ---- e2e: host buffers through the public API, copies inside the timed region --------------------------------
     # One call per step: spn_net_execute_host (Network::execute on host tensors) — pinned host inputs in, per-point
     # results (or the Monte-Carlo sum) back in host memory; the library pipelines H2D / kernel / D2H over chunks.
-    host_in = [p.numpy().view(np.complex128).reshape(n, -1) for p in host_sets[0]]
+    host_in = [p.numpy().view(np.complex128 if dt == sp.C64 else np.float64).reshape(n, -1)
+               for p, dt in zip(host_sets[0], spec.input_dtypes)]
     host_out_t = torch.empty(n * out_size * 2, dtype=torch.float64).pin_memory()
     host_out = None if want_sum else host_out_t.numpy().view(np.complex128).reshape(n, out_size)
     h2d = sum(int(p.numel()) * 8 for p in host_sets[0])

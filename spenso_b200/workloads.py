@@ -30,6 +30,7 @@ class NetSpec:
     nodes: List[tuple] = field(default_factory=list)
     root: int = -1
     inputs: List[Tuple[str, int]] = field(default_factory=list)  # (name, components per point)
+    input_dtypes: List[int] = field(default_factory=list)        # C64 / F64 per input
     # algorithmic bytes per evaluation: full dense inputs read once + result written once
     algorithmic_bytes: int = 0
 
@@ -37,10 +38,11 @@ class NetSpec:
         self.nodes.append(tuple(node))
         return len(self.nodes) - 1
 
-    def batched(self, sl, name) -> int:
+    def batched(self, sl, name, dtype: int = C64) -> int:
         size = int(np.prod([s.dim for s in sl])) if sl else 1
         self.inputs.append((name, size))
-        return self.add("batched", list(sl), name)
+        self.input_dtypes.append(dtype)
+        return self.add("batched", list(sl), name, dtype)
 
     def reindex(self, leaf, sl) -> int:
         return self.add("reindex", leaf, list(sl))
@@ -79,7 +81,7 @@ def build_engine(spec: NetSpec, ctx, mode: int = FUSED) -> Network:
     for k, node in enumerate(spec.nodes):
         kind = node[0]
         if kind == "batched":
-            ids[k] = net.batched(node[1], C64)
+            ids[k] = net.batched(node[1], node[3])
         elif kind == "reindex":
             ids[k] = net.reindex(ids[node[1]], node[2])
         elif kind == "lib":
@@ -159,12 +161,12 @@ def massless_spinors(p):
     return {"u+": u_plus, "u-": u_minus, "ubar+": ubar_plus, "ubar-": ubar_minus}
 
 
-def eemumu_from_momenta() -> NetSpec:
+def eemumu_from_momenta(dtype: int = C64) -> NetSpec:
     """cfg2 with device-side leaf filling: the per-point inputs are the four massless momenta
     (4 x 64 B as c64 Minkowski vectors, or 4 x 32 B as f64) and the spinors vbar(p2), u(p1), ubar(p3), v(p4)
     (fixed helicities; massless v(p) of helicity h == u(p) of helicity -h) are built inside the kernel."""
-    s = NetSpec("cfg2m_eemumu_from_momenta")
-    p = [s.batched([_m(100 + k)], f"p{k + 1}") for k in range(4)]
+    s = NetSpec("cfg2m_eemumu_from_momenta" + ("_f64" if dtype != C64 else ""))
+    p = [s.batched([_m(100 + k)], f"p{k + 1}", dtype) for k in range(4)]
     sp1 = lambda k, key, a: s.function([_b(a)], lambda P, k=k, key=key: massless_spinors(P(p[k], 4))[key])
     vb = sp1(1, "ubar-", 1)   # vbar_+(p2) = ubar_-(p2)
     u = sp1(0, "u-", 2)
@@ -173,8 +175,14 @@ def eemumu_from_momenta() -> NetSpec:
     g1 = s.lib(LIB_GAMMA_WEYL, [_b(1), _b(2), _m(1)])
     g2 = s.lib(LIB_GAMMA_WEYL, [_b(3), _b(4), _m(1)])
     s.root = s.product(vb, g1, u, ub, g2, v)
-    s.algorithmic_bytes = 4 * 64 + 16
+    s.algorithmic_bytes = 4 * (64 if dtype == C64 else 32) + 16
     return s
+
+
+def eemumu_from_real_momenta() -> NetSpec:
+    from . import F64
+
+    return eemumu_from_momenta(F64)
 
 
 def massless_momenta(n_points: int, seed: int):
@@ -288,7 +296,7 @@ def one_loop_massive() -> NetSpec:
 
 
 WORKLOADS = {"cfg1": gamma_trace4, "cfg2": eemumu, "cfg3": su3_colour, "cfg5": one_loop_massive,
-             "gl03": one_loop_gl03, "cfg2m": eemumu_from_momenta}
+             "gl03": one_loop_gl03, "cfg2m": eemumu_from_momenta, "cfg2mr": eemumu_from_real_momenta}
 
 
 def synthetic_inputs(spec: NetSpec, n_points: int, seed: int, scale: float = 1.0, real: bool = False) -> List[np.ndarray]:

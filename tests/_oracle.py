@@ -445,7 +445,7 @@ def net_from_spec(spec, arrays, point: int = 0):
             net._keep.append(t)
             ids[k] = net.tensor(t)
             b_nodes.append(ids[k])
-            b_arrays.append(arrays[inp])
+            b_arrays.append(np.ascontiguousarray(arrays[inp], dtype=np.complex128))   # f64 leaves: embedded (x, 0)
         elif kind == "function":
             # device-filled leaf: the oracle side fills it on the host (numpy, test infrastructure) and treats it
             # as one more per-point tensor — the reference fills such leaves with its host evaluators

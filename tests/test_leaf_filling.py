@@ -107,3 +107,25 @@ def test_leaf_filling_vs_host_filled_oracle():
     net.compile(sp.STEPWISE)
     with pytest.raises(sp.SpensoError):
         net.evaluate([tz])
+
+
+@pytest.mark.gpu
+def test_leaf_filling_from_f64_momenta():
+    """Same network fed with f64 momenta (32 B per momentum): half the input traffic, same amplitudes."""
+    ctx = sp.Context(0)
+    n = 2048
+    momenta = [np.ascontiguousarray(m.real) for m in workloads.massless_momenta(n, 5)]
+    spec = workloads.eemumu_from_real_momenta()
+    ref, _, _ = O.eval_spec(spec, momenta)
+    net = workloads.build_engine(spec, ctx)
+    assert net.input_bytes_per_point == 128
+    ins = []
+    for node, a in zip([x for x in spec.nodes if x[0] == "batched"], momenta):
+        t = sp.BatchTensor.empty(ctx, node[1], n, sp.F64)
+        t.upload(a)
+        ins.append(t)
+    got = net.evaluate(ins).to_numpy().reshape(n, -1)
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    out = np.zeros((n, 1), dtype=np.complex128)
+    g2, _ = net.execute_host(momenta, out=out, chunk_points=500)
+    assert np.abs(g2 - ref).max() <= 1e-12 * np.abs(ref).max()
