@@ -215,3 +215,21 @@ def test_plan_json_round_trip():
                 '{"version":1,"nodes":[{"kind":"op","op":"product","children":[5]}],"root":0}'):
         with pytest.raises(sp.SpensoError):
             sp.Network.from_json(None, bad)
+
+
+def test_maximum_orders():
+    """SPN_MAX_ORDER = 16 indices per operand, 32 per result; one more is refused, not truncated."""
+    a = sp.slots([sp.Euclidean.new_slot(1 + (i % 2), 100 + i) for i in range(16)])
+    b = sp.slots([sp.Euclidean.new_slot(1 + (i % 2), 200 + i) for i in range(16)])
+    ca, cb = sp.canonicalize(a)[0], sp.canonicalize(b)[0]
+    assert O.order_structure(a)[0].tobytes() == ca.tobytes()
+    p = sp.plan_contract(ca, cb)
+    assert p.order_out == 32 and p.n_common == 0 and p.size_out == 2 ** 16
+    om = O.merge(ca, cb)
+    assert np.frombuffer(bytes(p.out_slots), dtype=sp.SLOT_DTYPE)[:32].tobytes() == om["slots"].tobytes()
+    big = sp.slots([sp.Euclidean.new_slot(1, 300 + i) for i in range(17)])
+    with pytest.raises(sp.SpensoError):
+        sp.plan_contract(sp.canonicalize(big)[0], cb)
+    # fully contracted 16-index pair -> scalar
+    p = sp.plan_contract(ca, ca)
+    assert p.order_out == 0 and p.n_common == 16 and p.size_out == 1 and p.n_contracted == 2 ** 8

@@ -703,3 +703,98 @@ def test_reference_interleaved_pairing_quirk(ctx):
             assert rel_err(ta.contract(tb).to_numpy(), quirk) <= TOL
     finally:
         ctx.set_reference_quirks(False)
+
+
+# ---- BASELINE configs 3 and 5 at their full sizes: size-independent properties ------------------------------------
+def _torch_complex(shape, seed, dev, scale=1.0, real=False):
+    import torch
+
+    g = torch.Generator(device=dev).manual_seed(seed)
+    re = (torch.rand(shape, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * scale
+    im = torch.zeros_like(re) if real else (torch.rand(shape, generator=g, device=dev, dtype=torch.float64) * 2 - 1) * scale
+    return torch.complex(re, im).contiguous()
+
+
+def test_cfg3_full_size_4M_points(ctx):
+    """Config 3 at 2^22 points (39 GB of per-point dense X and D, generated on the device): additivity in D,
+    homogeneity in X, per-point output vs fused sum, and an oracle spot check on sampled points."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * 2 ** 30:
+        pytest.skip("needs ~90 GiB of free HBM")
+    dev = torch.device("cuda:0")
+    n = 1 << 22
+    spec = workloads.su3_colour()
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    slots_x, slots_d = [x[1] for x in spec.nodes if x[0] == "batched"]
+    X = _torch_complex((n, 72), 1235, dev)
+    D = _torch_complex((n, 512), 1236, dev)
+
+    def run(x, d, want_sum=False):
+        tx = sp.BatchTensor.wrap(ctx, slots_x, n, x.data_ptr(), keepalive=x)
+        td = sp.BatchTensor.wrap(ctx, slots_d, n, d.data_ptr(), keepalive=d)
+        out = torch.empty(n, dtype=torch.complex128, device=dev)
+        to = sp.BatchTensor.wrap(ctx, net.result_slots, n, out.data_ptr(), keepalive=out)
+        s = torch.zeros(2, dtype=torch.float64, device=dev)
+        net.execute([tx, td], to, sum_out_ptr=s.data_ptr() if want_sum else 0)
+        ctx.synchronize()
+        return out, torch.view_as_complex(s.view(1, 2))[0]
+
+    base, s = run(X, D, want_sum=True)
+    assert abs(complex(s) - complex(base.sum())) <= 1e-12 * float(base.abs().sum())
+    z = 0.5 - 1.5j
+    x_only, _ = run(X, torch.zeros_like(D))
+    d_only, _ = run(torch.zeros_like(X), D)
+    assert float((x_only + d_only - base).abs().max()) <= 1e-13 * float(base.abs().max())     # X.T + D.f
+    del d_only
+    X.mul_(z)
+    scaled, _ = run(X, torch.zeros_like(D))
+    assert float((scaled - z * x_only).abs().max()) <= 1e-13 * float(x_only.abs().max())      # homogeneous in X
+    X.div_(z)
+    idx = torch.randint(0, n, (300,), generator=torch.Generator().manual_seed(3))
+    ref, _, _ = O.eval_spec(spec, [X[idx.to(dev)].cpu().numpy(), D[idx.to(dev)].cpu().numpy()])
+    assert rel_err(base[idx.to(dev)].cpu().numpy(), ref[:, 0]) <= 1e-12 * 10   # X was scaled and unscaled: 1 ulp per element
+
+
+def test_cfg5_1e8_points_streamed_sum(ctx):
+    """Config 5's batch size: 1e8 kinematic points resident on one GPU (12.8 GB).  The Monte-Carlo sum over all points
+    must equal the sum of the sums over 24 ragged point ranges, be reproducible bit for bit, and agree with the oracle
+    on a sample."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2 ** 30:
+        pytest.skip("needs ~30 GiB of free HBM")
+    dev = torch.device("cuda:0")
+    n = 100_000_000
+    spec = workloads.one_loop_massive()
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    sl = [x[1] for x in spec.nodes if x[0] == "batched"]
+    K0 = _torch_complex((n, 4), 1237, dev, scale=100.0, real=True)
+    K1 = _torch_complex((n, 4), 1238, dev, scale=100.0, real=True)
+    t0 = sp.BatchTensor.wrap(ctx, sl[0], n, K0.data_ptr(), keepalive=K0)
+    t1 = sp.BatchTensor.wrap(ctx, sl[1], n, K1.data_ptr(), keepalive=K1)
+    s = torch.zeros(32, dtype=torch.float64, device=dev)
+
+    def total(first=0, cnt=0):
+        net.execute([t0, t1], None, sum_out_ptr=s.data_ptr(), first_point=first, n_points=cnt)
+        ctx.synchronize()
+        return s.cpu().numpy().view(np.complex128).copy()
+
+    full = total()
+    assert (total() == full).all()
+    edges = np.linspace(0, n, 25).astype(np.int64)
+    edges[1:-1] += np.arange(1, 24) * 7 - 50          # ragged
+    parts = sum(total(int(a), int(b - a)) for a, b in zip(edges[:-1], edges[1:]))
+    assert np.abs(parts - full).max() <= 1e-11 * np.abs(full).max()      # two different summation trees over 1e8 terms
+    idx = torch.randint(0, n, (200,), generator=torch.Generator().manual_seed(4)).to(dev)
+    ref, _, _ = O.eval_spec(spec, [K0[idx].cpu().numpy(), K1[idx].cpu().numpy()])
+    out = torch.empty((200, 16), dtype=torch.complex128, device=dev)
+    k0s, k1s = K0[idx].contiguous(), K1[idx].contiguous()
+    a0 = sp.BatchTensor.wrap(ctx, sl[0], 200, k0s.data_ptr(), keepalive=k0s)
+    a1 = sp.BatchTensor.wrap(ctx, sl[1], 200, k1s.data_ptr(), keepalive=k1s)
+    to = sp.BatchTensor.wrap(ctx, net.result_slots, 200, out.data_ptr(), keepalive=out)
+    net.execute([a0, a1], to)
+    ctx.synchronize()
+    assert rel_err(out.cpu().numpy(), ref) <= TOL
