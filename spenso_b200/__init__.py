@@ -136,6 +136,10 @@ class Context:
     def synchronize(self):
         check(lib().spn_ctx_synchronize(self.h))
 
+    def release_cached_memory(self):
+        """Return the pooled memory of freed intermediates to the driver."""
+        check(lib().spn_ctx_release_cached_memory(self.h))
+
     def set_reference_quirks(self, emulate_interleaved_pairing: bool):
         """Parity triage: reproduce MultiContractInterleaved's un-permuted pairing (SURVEY K-note 3)."""
         check(lib().spn_ctx_set_reference_quirks(self.h, int(emulate_interleaved_pairing)))

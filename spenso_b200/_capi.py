@@ -55,6 +55,7 @@ SYMBOLS = {
     "spn_ctx_set_stream": (_I, [_P, _P]),
     "spn_ctx_synchronize": (_I, [_P]),
     "spn_ctx_set_reference_quirks": (_I, [_P, _I]),
+    "spn_ctx_release_cached_memory": (_I, [_P]),
     "spn_ctx_launch_count": (_U64, [_P]),
     "spn_ctx_sm_count": (_I, [_P]),
     "spn_tensor_batched": (_I, [_P, _P, _U32, _U64, _I, _I, C.POINTER(_P)]),

@@ -98,7 +98,16 @@ spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, in
     t->dptr = wrap;
     t->owns = false;
   } else {
-    t->dptr = dev_alloc(n_points * st.size() * t->elem_bytes());
+    // stream-ordered allocation from the device's memory pool: no implicit synchronisation, and memory freed by
+    // an earlier intermediate is reused without a round trip to the driver
+    const size_t bytes = n_points * st.size() * t->elem_bytes();
+    if (ctx && cudaMallocAsync(&t->dptr, bytes ? bytes : 16, ctx->stream) == cudaSuccess) {
+      t->pooled = true;
+      t->alloc_stream = ctx->stream;
+    } else {
+      cudaGetLastError();
+      t->dptr = dev_alloc(bytes);
+    }
     t->owns = true;
   }
   return t.release();
@@ -434,6 +443,14 @@ int spn_ctx_create(int device, spn_ctx** out) {
   c->device = device;
   cuda_check(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "device attribute");
   cuda_check(cudaFree(0), "context init");
+  {  // keep freed intermediates in the pool instead of returning them to the OS at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t keep = 4ull << 30;  // up to 4 GiB of freed intermediates stay cached across synchronisations
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   *out = c.release();
   return SPN_OK;
   API_CATCH
@@ -442,6 +459,15 @@ void spn_ctx_destroy(spn_ctx* ctx) { delete ctx; }
 int spn_ctx_set_stream(spn_ctx* ctx, void* s) {
   ctx->stream = (cudaStream_t)s;
   return SPN_OK;
+}
+int spn_ctx_release_cached_memory(spn_ctx* ctx) {
+  API_TRY
+  cuda_check(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  cudaMemPool_t pool;
+  cuda_check(cudaDeviceGetDefaultMemPool(&pool, ctx->device), "cudaDeviceGetDefaultMemPool");
+  cuda_check(cudaMemPoolTrimTo(pool, 0), "cudaMemPoolTrimTo");
+  return SPN_OK;
+  API_CATCH
 }
 int spn_ctx_set_reference_quirks(spn_ctx* ctx, int emulate_interleaved_pairing) {
   ctx->emulate_reference_pairing = emulate_interleaved_pairing != 0;

@@ -28,6 +28,8 @@ struct spn_tensor {
   uint64_t n_points = 1;
   void* dptr = nullptr;  // batched: the buffer; shared: densified Complex<f64> copy
   bool owns = false;
+  bool pooled = false;             // allocated with cudaMallocAsync on alloc_stream (results of pairwise ops)
+  cudaStream_t alloc_stream = nullptr;
   // shared tensors: host copies (canonical row major)
   std::vector<double2> host_dense;
   std::map<uint64_t, double2> entries;  // sparse only, keyed (and therefore sorted) by flat index
@@ -62,7 +64,13 @@ struct spn_tensor {
     return r;
   }
   ~spn_tensor() {
-    if (owns && dptr) cudaFree(dptr);
+    if (owns && dptr) {
+      // stream-ordered free keeps the pairwise (stepwise) path free of device-wide synchronisation
+      if (!pooled || cudaFreeAsync(dptr, alloc_stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(dptr);
+      }
+    }
   }
 };
 

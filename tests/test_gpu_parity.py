@@ -405,6 +405,8 @@ def test_cfg4_full_size_rank6_dim32(ctx):
     rows of a random contraction against cuBLAS (torch.matmul) — both checks are test infrastructure."""
     import torch
 
+    ctx.release_cached_memory()
+    torch.cuda.empty_cache()
     free, total = torch.cuda.mem_get_info()
     if free < 120 * 2 ** 30:
         pytest.skip("needs ~100 GiB of free HBM")
@@ -720,6 +722,8 @@ def test_cfg3_full_size_4M_points(ctx):
     homogeneity in X, per-point output vs fused sum, and an oracle spot check on sampled points."""
     import torch
 
+    ctx.release_cached_memory()
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 100 * 2 ** 30:
         pytest.skip("needs ~90 GiB of free HBM")
@@ -763,6 +767,8 @@ def test_cfg5_1e8_points_streamed_sum(ctx):
     on a sample."""
     import torch
 
+    ctx.release_cached_memory()
+    torch.cuda.empty_cache()
     free, _ = torch.cuda.mem_get_info()
     if free < 40 * 2 ** 30:
         pytest.skip("needs ~30 GiB of free HBM")
