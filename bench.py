@@ -35,13 +35,14 @@ WORKLOAD_DESC = {
             "Complex<f64>, 2^20 synthetic phase-space points per GPU",
     "cfg3": "cfg3: SU(3) colour-factor network X.T + D.f (Dense per point x Sparse shared)",
     "cfg5": "cfg5: one-loop numerator network (gl_03 topology, massive), Monte-Carlo sum",
+    "cfg5r": "cfg5r: cfg5 with the real loop momenta declared as f64 tensors (64 B per evaluation)",
     "cfg2m": "cfg2m: cfg2 with device-side leaf filling — inputs are the four massless momenta, the spinors are built "
              "inside the kernel (SURVEY 8f-1)",
     "cfg2mr": "cfg2mr: cfg2m with the momenta stored as f64 (32 B each): 144 B per evaluation",
     "cfg4": "cfg4: dense pairwise contraction of rank-6 c64 tensors, dim-32 indices, 3 shared (ZGEMM 32768^3, FP64 DMMA)",
 }
-DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg2m": 1 << 20, "cfg2mr": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg4": 1}
-SCALE = {"cfg2": 1.0, "cfg2m": 1.0, "cfg2mr": 1.0, "cfg3": 1.0, "cfg5": 100.0}
+DEFAULT_POINTS = {"cfg2": 1 << 20, "cfg2m": 1 << 20, "cfg2mr": 1 << 20, "cfg3": 1 << 20, "cfg5": 1 << 22, "cfg5r": 1 << 22, "cfg4": 1}
+SCALE = {"cfg2": 1.0, "cfg2m": 1.0, "cfg2mr": 1.0, "cfg3": 1.0, "cfg5": 100.0, "cfg5r": 100.0}
 
 
 def make_inputs(spec, wl, n, seed):
@@ -51,7 +52,10 @@ def make_inputs(spec, wl, n, seed):
         return workloads.massless_momenta(n, seed)
     if wl == "cfg2mr":
         return [np.ascontiguousarray(a.real) for a in workloads.massless_momenta(n, seed)]
-    return workloads.synthetic_inputs(spec, n, seed, scale=SCALE[wl], real=(wl == "cfg5"))
+    arrs = workloads.synthetic_inputs(spec, n, seed, scale=SCALE[wl], real=wl in ("cfg5", "cfg5r"))
+    if wl == "cfg5r":
+        arrs = [np.ascontiguousarray(a.real) for a in arrs]
+    return arrs
 
 
 def parse_args():
@@ -168,18 +172,25 @@ class ClockSampler:
             self.nv = None
         self.t = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def sample(self):
+        """One sample now (also called from the main thread right after the timed work is enqueued, so that even a
+        sub-millisecond timed region is observed while the GPU is busy)."""
         nv = self.nv
+        if nv is None:
+            return
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, nm in names.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def _run(self):
         while not self.stop:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-            except Exception:
-                pass
+            self.sample()
             time.sleep(0.001)
 
     def __enter__(self):
@@ -248,7 +259,7 @@ def run_b200(args):
     net = workloads.build_engine(spec, ctx, sp.STEPWISE if stepwise else sp.FUSED)
     out_size = net.result_size
     leaf_slots = [x[1] for x in spec.nodes if x[0] == "batched"]
-    want_sum = wl == "cfg5"        # Monte-Carlo estimate: no per-point store, only the sum over points
+    want_sum = wl in ("cfg5", "cfg5r")        # Monte-Carlo estimate: no per-point store, only the sum over points
 
     # synthetic kinematics: ROT rotating input sets so that consecutive steps never re-read what L2 holds
     bytes_in = sum(sz * (16 if dt == sp.C64 else 8) for (_, sz), dt in zip(spec.inputs, spec.input_dtypes)) * n
@@ -320,6 +331,7 @@ def run_b200(args):
         if want_sum:
             allreduce_partial_sums(sums)   # the one collective of the path: final Monte-Carlo sum (no-op at N=1)
         t_end.record(stream)
+        clocks.sample()                    # the timed work is in flight right now
         barrier()
     launches = (ctx.launch_count - launches0) if graph is None else K * (2 if want_sum else 1)
     elapsed_ms = t_begin.elapsed_time(t_end)

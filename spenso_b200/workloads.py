@@ -247,7 +247,7 @@ def su3_colour() -> NetSpec:
 GL03_MC, GL03_MW = 11232.0, 1231.0
 
 
-def one_loop_gl03(P0=(0.0, 1.0, 2.0, 3.0), massive: bool = False) -> NetSpec:
+def one_loop_gl03(P0=(0.0, 1.0, 2.0, 3.0), massive: bool = False, dtype: int = C64) -> NetSpec:
     """gl_03 of the reference's gamma_algebra_validate.rs: inputs K0, K1 (per point); P0, MC, MW fixed.
 
     The literal gl_03 numerator vanishes identically: P- (MC - K0slash) gamma P- kills the mass term
@@ -256,14 +256,14 @@ def one_loop_gl03(P0=(0.0, 1.0, 2.0, 3.0), massive: bool = False) -> NetSpec:
     topology: the second fermion propagator numerator V5slash becomes (MC + V5slash), which leaves
     -MC Tr[K0slash gamma^h7 P- gamma^h11 V3slash] W_{h7 h8} g^{h0 h8} != 0.
     """
-    s = NetSpec("cfg5_one_loop_massive" if massive else "gl03_literal")
+    s = NetSpec(("cfg5_one_loop_massive" if massive else "gl03_literal") + ("_f64" if dtype != C64 else ""))
     H = lambda n: n              # hedge(n)
     E = lambda a: 100 + a        # edge(a, 1)
     V11 = 201                    # vertex(1, 1)
-    K0 = {E(1): s.batched([_m(E(1))], "K0")}
+    K0 = {E(1): s.batched([_m(E(1))], "K0", dtype)}
     for lab in (E(3), E(5)):
         K0[lab] = s.reindex(K0[E(1)], [_m(lab)])
-    K1 = {E(3): s.batched([_m(E(3))], "K1")}
+    K1 = {E(3): s.batched([_m(E(3))], "K1", dtype)}
     for lab in (H(7), H(8), E(5)):
         K1[lab] = s.reindex(K1[E(3)], [_m(lab)])
     P = {lab: s.custom([_m(lab)], {(i,): P0[i] for i in range(4) if P0[i] != 0}) for lab in (H(7), H(8), E(5))}
@@ -287,7 +287,7 @@ def one_loop_gl03(P0=(0.0, 1.0, 2.0, 3.0), massive: bool = False) -> NetSpec:
         s.lib(LIB_GAMMA_WEYL, [_b(H(6)), _b(H(5)), _m(E(3))]),
         s.lib(LIB_PROJM_WEYL, [_b(H(5)), _b(H(1))]),
         s.lib(LIB_PROJM_WEYL, [_b(V11), _b(H(9))]))
-    s.algorithmic_bytes = 2 * 64
+    s.algorithmic_bytes = 2 * (64 if dtype == C64 else 32)
     return s
 
 
@@ -295,8 +295,17 @@ def one_loop_massive() -> NetSpec:
     return one_loop_gl03(massive=True)
 
 
+def one_loop_massive_real() -> NetSpec:
+    """cfg5 with the (real) loop momenta declared as f64 tensors: half the bytes, and every term that would
+    multiply an imaginary part is gone from the kernel."""
+    from . import F64
+
+    return one_loop_gl03(massive=True, dtype=F64)
+
+
 WORKLOADS = {"cfg1": gamma_trace4, "cfg2": eemumu, "cfg3": su3_colour, "cfg5": one_loop_massive,
-             "gl03": one_loop_gl03, "cfg2m": eemumu_from_momenta, "cfg2mr": eemumu_from_real_momenta}
+             "gl03": one_loop_gl03, "cfg2m": eemumu_from_momenta, "cfg2mr": eemumu_from_real_momenta,
+             "cfg5r": one_loop_massive_real}
 
 
 def synthetic_inputs(spec: NetSpec, n_points: int, seed: int, scale: float = 1.0, real: bool = False) -> List[np.ndarray]:

@@ -804,3 +804,27 @@ def test_cfg5_1e8_points_streamed_sum(ctx):
     net.execute([a0, a1], to)
     ctx.synchronize()
     assert rel_err(out.cpu().numpy(), ref) <= TOL
+
+
+def test_cfg5_real_momenta_variant(ctx):
+    """cfg5r: the loop momenta as f64 tensors — same numerator, half the bytes, fewer instructions."""
+    import torch
+
+    spec = workloads.one_loop_massive_real()
+    n = 1500
+    arrays = [np.ascontiguousarray(a.real) for a in
+              workloads.synthetic_inputs(workloads.one_loop_massive(), n, 77, scale=100.0, real=True)]
+    ref, ref_sum, _ = O.eval_spec(spec, arrays)
+    net = workloads.build_engine(spec, ctx)
+    assert net.input_bytes_per_point == 64
+    ins = []
+    for node, a in zip([x for x in spec.nodes if x[0] == "batched"], arrays):
+        t = sp.BatchTensor.empty(ctx, node[1], n, sp.F64)
+        t.upload(a)
+        ins.append(t)
+    out = sp.BatchTensor.empty(ctx, net.result_slots, n)
+    s = torch.zeros(32, dtype=torch.float64, device="cuda:0")
+    net.execute(ins, out, sum_out_ptr=s.data_ptr())
+    ctx.synchronize()
+    assert rel_err(out.to_numpy().reshape(n, -1), ref) <= TOL
+    assert rel_err(s.cpu().numpy().view(np.complex128), ref_sum) <= TOL
