@@ -179,7 +179,7 @@ enum { SPN_OP_PRODUCT = 3, SPN_OP_SUM = 4, SPN_OP_NEG = 5, SPN_OP_POWER = 6, SPN
 /* built-in library tensors, spenso-hep-lib/src/lib.rs:27-387 (argument order bis i, bis j[, mink mu]) */
 enum {
   SPN_LIB_GAMMA_WEYL = 0, SPN_LIB_GAMMA_DIRAC = 1, SPN_LIB_GAMMA0_WEYL = 2, SPN_LIB_GAMMA5_WEYL = 3,
-  SPN_LIB_PROJM_WEYL = 4, SPN_LIB_PROJP_WEYL = 5, SPN_LIB_METRIC = 6
+  SPN_LIB_PROJM_WEYL = 4, SPN_LIB_PROJP_WEYL = 5, SPN_LIB_METRIC = 6, SPN_LIB_GAMMA_CONJ_WEYL = 7, SPN_LIB_GAMMA_ADJ_WEYL = 8
 };
 enum { SPN_EXEC_FUSED = 0 /* one JIT-specialised sm_100a kernel per network */,
        SPN_EXEC_STEPWISE = 1 /* one pairwise kernel per contraction, intermediates in HBM */ };

@@ -260,6 +260,8 @@ void* orc_lib_builtin(int which) {
     case 3: return new LibTensor(gamma5_weyl());
     case 4: return new LibTensor(projm_weyl());
     case 5: return new LibTensor(projp_weyl());
+    case 7: return new LibTensor(gamma_conj_weyl());
+    case 8: return new LibTensor(gamma_adj_weyl());
     default: return nullptr;
   }
 }

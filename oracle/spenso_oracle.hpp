@@ -1871,6 +1871,22 @@ inline LibTensor gamma_weyl() {  // lib.rs:66-102
                            {{0, 3, 2}, cni}, {{1, 2, 2}, ci}, {{2, 1, 2}, ci}, {{3, 0, 2}, cni},
                            {{0, 2, 3}, c1}, {{1, 3, 3}, cn1}, {{2, 0, 3}, cn1}, {{3, 1, 3}, c1}});
 }
+inline LibTensor gamma_conj_weyl() {  // lib.rs:144-153: gamma_data_weyl with every entry conjugated
+  const C c1{1, 0}, cn1{-1, 0}, ci{0, 1}, cni{0, -1};
+  return lib_from_entries({bis(4, 0), bis(4, 0), mink(4, 0)},
+                          {{{0, 2, 0}, c1}, {{1, 3, 0}, c1}, {{2, 0, 0}, c1}, {{3, 1, 0}, c1},
+                           {{0, 3, 1}, c1}, {{1, 2, 1}, c1}, {{2, 1, 1}, cn1}, {{3, 0, 1}, cn1},
+                           {{0, 3, 2}, ci}, {{1, 2, 2}, cni}, {{2, 1, 2}, cni}, {{3, 0, 2}, ci},
+                           {{0, 2, 3}, c1}, {{1, 3, 3}, cn1}, {{2, 0, 3}, cn1}, {{3, 1, 3}, c1}});
+}
+inline LibTensor gamma_adj_weyl() {  // lib.rs:155-166: gamma_transpose_weyl (lib.rs:103-141) conjugated
+  const C c1{1, 0}, cn1{-1, 0}, ci{0, 1}, cni{0, -1};
+  return lib_from_entries({bis(4, 0), bis(4, 0), mink(4, 0)},
+                          {{{2, 0, 0}, c1}, {{3, 1, 0}, c1}, {{0, 2, 0}, c1}, {{1, 3, 0}, c1},
+                           {{3, 0, 1}, c1}, {{2, 1, 1}, c1}, {{1, 2, 1}, cn1}, {{0, 3, 1}, cn1},
+                           {{3, 0, 2}, ci}, {{2, 1, 2}, cni}, {{1, 2, 2}, cni}, {{0, 3, 2}, ci},
+                           {{2, 0, 3}, c1}, {{3, 1, 3}, cn1}, {{0, 2, 3}, cn1}, {{1, 3, 3}, c1}});
+}
 inline LibTensor gamma_dirac() {  // lib.rs:27-63
   const C c1{1, 0}, cn1{-1, 0}, ci{0, 1}, cni{0, -1};
   return lib_from_entries({bis(4, 0), bis(4, 0), mink(4, 0)},

@@ -37,6 +37,7 @@ BATCHED, SHARED_DENSE, SHARED_SPARSE = 0, 1, 2
 OP_PRODUCT, OP_SUM, OP_NEG, OP_POWER, OP_CONJ = 3, 4, 5, 6, 7
 FUSED, STEPWISE = 0, 1
 LIB_GAMMA_WEYL, LIB_GAMMA_DIRAC, LIB_GAMMA0_WEYL, LIB_GAMMA5_WEYL, LIB_PROJM_WEYL, LIB_PROJP_WEYL, LIB_METRIC = range(7)
+LIB_GAMMA_CONJ_WEYL, LIB_GAMMA_ADJ_WEYL = 7, 8
 
 
 # ---- index structure --------------------------------------------------------------------------------

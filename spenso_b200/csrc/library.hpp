@@ -54,6 +54,10 @@ inline LibraryData builtin_library(int which, const std::vector<spn_slot>& args)
     case SPN_LIB_PROJM_WEYL: tab = kProjMWeyl; n = 2; rank = 2; break;
     case SPN_LIB_PROJP_WEYL: tab = kProjPWeyl; n = 2; rank = 2; break;
     case SPN_LIB_METRIC: rank = 2; break;
+    // gamma_conj_data_weyl (lib.rs:144-153): entry-wise complex conjugate of gamma;
+    // gamma_adj_data_weyl (lib.rs:155-166): conjugate of gamma_transpose_weyl (lib.rs:103-141) = gamma^dagger
+    case SPN_LIB_GAMMA_CONJ_WEYL:
+    case SPN_LIB_GAMMA_ADJ_WEYL: tab = kGammaWeyl; n = 16; rank = 3; break;
     default: throw Error(SPN_ERR_INVALID, "unknown library tensor");
   }
   if ((int)args.size() != rank) throw Error(SPN_ERR_STRUCTURE, "library tensor: wrong number of indices");
@@ -70,9 +74,13 @@ inline LibraryData builtin_library(int which, const std::vector<spn_slot>& args)
   for (int r = 0; r < rank; ++r)
     if (args[r].dim != 4) throw Error(SPN_ERR_DIMENSION, "library tensor: expected dimension 4");
   for (int e = 0; e < n; ++e) {
+    uint8_t idx[3] = {tab[e].idx[0], tab[e].idx[1], tab[e].idx[2]};
+    double im = tab[e].im;
+    if (which == SPN_LIB_GAMMA_ADJ_WEYL) std::swap(idx[0], idx[1]);  // transpose the bispinor indices ...
+    if (which == SPN_LIB_GAMMA_CONJ_WEYL || which == SPN_LIB_GAMMA_ADJ_WEYL) im = -im;  // ... and conjugate
     uint64_t f = 0;
-    for (int r = 0; r < rank; ++r) f += tab[e].idx[r] * st[r];
-    d.nz.push_back({f, make_double2(tab[e].re, tab[e].im)});
+    for (int r = 0; r < rank; ++r) f += idx[r] * st[r];
+    d.nz.push_back({f, make_double2(tab[e].re, im)});
   }
   return d;
 }

@@ -312,6 +312,7 @@ class OTensor:
 
 class OLib:
     GAMMA_WEYL, GAMMA_DIRAC, GAMMA0, GAMMA5, PROJM, PROJP = range(6)
+    GAMMA_CONJ, GAMMA_ADJ = 7, 8
 
     def __init__(self, handle):
         self.h = handle

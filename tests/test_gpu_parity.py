@@ -828,3 +828,38 @@ def test_cfg5_real_momenta_variant(ctx):
     ctx.synchronize()
     assert rel_err(out.to_numpy().reshape(n, -1), ref) <= TOL
     assert rel_err(s.cpu().numpy().view(np.complex128), ref_sum) <= TOL
+
+
+def test_gamma_adjoint_identities_on_device(ctx):
+    """spenso-hep-lib/tests/gamma_algebra_validate.rs:87-105 as networks of library tensors only:
+    gamma0 gamma^mu gamma0 - gammaconj^T = 0,  gammaadj - gamma0 gamma gamma0 = 0,  gammaadj - gammaconj^T = 0."""
+    b = lambda a: sp.Bispinor.new_slot(4, a)
+    m = sp.Minkowski.new_slot(4, 1)
+    for mode in (sp.FUSED, sp.STEPWISE):
+        for build in (
+            lambda n: n.sum(n.product(n.library(sp.LIB_GAMMA0_WEYL, [b(1), b(2)]), n.library(sp.LIB_GAMMA_WEYL, [b(2), b(3), m]),
+                                      n.library(sp.LIB_GAMMA0_WEYL, [b(3), b(4)])),
+                            n.neg(n.library(sp.LIB_GAMMA_CONJ_WEYL, [b(4), b(1), m]))),
+            lambda n: n.sum(n.library(sp.LIB_GAMMA_ADJ_WEYL, [b(1), b(2), m]),
+                            n.neg(n.product(n.library(sp.LIB_GAMMA0_WEYL, [b(1), b(3)]),
+                                            n.library(sp.LIB_GAMMA_WEYL, [b(3), b(4), m]),
+                                            n.library(sp.LIB_GAMMA0_WEYL, [b(4), b(2)])))),
+            lambda n: n.sum(n.library(sp.LIB_GAMMA_ADJ_WEYL, [b(1), b(2), m]),
+                            n.neg(n.library(sp.LIB_GAMMA_CONJ_WEYL, [b(2), b(1), m]))),
+        ):
+            net = sp.Network(ctx)
+            net.set_root(build(net))
+            net.compile(mode)
+            out = sp.BatchTensor.empty(ctx, net.result_slots, 2)
+            out.upload(np.ones((2, 64), dtype=complex))
+            net.execute([], out)
+            ctx.synchronize()
+            assert net.result_size == 64 and not out.to_numpy().any()
+    # and a non-trivial constant network: gamma^mu gamma_mu = 4 * identity
+    net = sp.Network(ctx)
+    net.set_root(net.product(net.library(sp.LIB_GAMMA_WEYL, [b(1), b(2), m]), net.library(sp.LIB_GAMMA_WEYL, [b(2), b(3), m])))
+    net.compile(sp.FUSED)
+    out = sp.BatchTensor.empty(ctx, net.result_slots, 3)
+    net.execute([], out)
+    ctx.synchronize()
+    assert (out.to_numpy() == 4 * np.eye(4)).all()

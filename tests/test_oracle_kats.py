@@ -367,3 +367,19 @@ def test_eval_batch_matches_single():
     ref = np.einsum("na,nc,aij,bjk,ckl,dli->nbd", P @ eta, Q @ eta, g, g, g, g).reshape(n, 16)
     assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
     assert np.abs(s - ref.sum(0)).max() <= 1e-11 * np.abs(ref).max()
+
+
+def test_gamma_conj_and_adj_identities():
+    # spenso-hep-lib/tests/gamma_algebra_validate.rs:87-105:
+    #   gamma0(1,2) gamma(2,3,mu) gamma0(3,4) - gammaconj(4,1,mu) = 0      (gamma0 gamma gamma0 = gamma^dagger)
+    #   gammaadj(1,2,mu) - gamma0(1,3) gamma(3,4,mu) gamma0(4,2) = 0
+    #   gammaadj(1,2,mu) - gammaconj(2,1,mu) = 0
+    args = slots(("bis", 4, 1), ("bis", 4, 2), ("mink", 4, 3))
+    g = OLib.builtin(OLib.GAMMA_WEYL).instantiate(args).to_dense()
+    gc = OLib.builtin(OLib.GAMMA_CONJ).instantiate(args).to_dense()
+    ga = OLib.builtin(OLib.GAMMA_ADJ).instantiate(args).to_dense()
+    g0 = OLib.builtin(OLib.GAMMA0).instantiate(slots(("bis", 4, 1), ("bis", 4, 2))).to_dense()
+    assert (gc == g.conj()).all()
+    assert (ga == np.transpose(g.conj(), (1, 0, 2))).all()
+    assert (np.einsum("ab,bcm,cd->adm", g0, g, g0) == ga).all()
+    assert (ga == np.transpose(gc, (1, 0, 2))).all()
