@@ -182,7 +182,8 @@ enum {
   SPN_LIB_PROJM_WEYL = 4, SPN_LIB_PROJP_WEYL = 5, SPN_LIB_METRIC = 6, SPN_LIB_GAMMA_CONJ_WEYL = 7, SPN_LIB_GAMMA_ADJ_WEYL = 8
 };
 enum { SPN_EXEC_FUSED = 0 /* one JIT-specialised sm_100a kernel per network */,
-       SPN_EXEC_STEPWISE = 1 /* one pairwise kernel per contraction, intermediates in HBM */ };
+       SPN_EXEC_STEPWISE = 1 /* one pairwise kernel per contraction, intermediates in HBM */,
+       SPN_EXEC_AUTO = 2 /* fused unless the network's intermediates are too large for straight-line code */ };
 
 typedef struct spn_net spn_net;
 int spn_net_create(spn_ctx* ctx, spn_net** out);
@@ -233,6 +234,8 @@ int spn_net_from_json(spn_ctx* ctx, const char* json, spn_net** out);
 /* Run the graph walk, merge and schedule ONCE (they are identical for every point), then build
  * the device program. */
 int spn_net_compile(spn_net* net, int exec_mode);
+/* the mode the compiled network runs in (resolves SPN_EXEC_AUTO) */
+int spn_net_exec_mode(const spn_net* net);
 /* result structure (canonical) — valid after compile */
 uint32_t spn_net_result_order(const spn_net* net);
 int spn_net_result_slots(const spn_net* net, spn_slot* out);

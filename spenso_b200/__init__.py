@@ -26,7 +26,7 @@ __all__ = [
     "Representation", "Euclidean", "Minkowski", "Lorentz", "Bispinor", "SpinFundamental", "ColorAdjoint",
     "ColorFundamental", "ColorSextet", "Slot", "slots", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
     "Network", "SpensoError", "canonicalize", "plan_contract", "build_library",
-    "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE",
+    "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE", "AUTO",
 ]
 
 REP_DUMMY, REP_SELF_DUAL, REP_INLINE_METRIC, REP_DUALIZABLE = 0, 1, 2, 3
@@ -35,7 +35,7 @@ F64, C64 = 0, 1
 POINT_MAJOR, COMPONENT_MAJOR = 0, 1
 BATCHED, SHARED_DENSE, SHARED_SPARSE = 0, 1, 2
 OP_PRODUCT, OP_SUM, OP_NEG, OP_POWER, OP_CONJ = 3, 4, 5, 6, 7
-FUSED, STEPWISE = 0, 1
+FUSED, STEPWISE, AUTO = 0, 1, 2
 LIB_GAMMA_WEYL, LIB_GAMMA_DIRAC, LIB_GAMMA0_WEYL, LIB_GAMMA5_WEYL, LIB_PROJM_WEYL, LIB_PROJP_WEYL, LIB_METRIC = range(7)
 LIB_GAMMA_CONJ_WEYL, LIB_GAMMA_ADJ_WEYL = 7, 8
 
@@ -487,6 +487,10 @@ class Network:
         return self
 
     # compiled-plan inspection
+    @property
+    def exec_mode(self) -> int:
+        return int(lib().spn_net_exec_mode(self.h))
+
     @property
     def result_slots(self) -> np.ndarray:
         out = np.zeros(int(lib().spn_net_result_order(self.h)), dtype=SLOT_DTYPE)

@@ -97,6 +97,7 @@ SYMBOLS = {
     "spn_net_to_json": (C.c_char_p, [_P]),
     "spn_net_from_json": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
     "spn_net_compile": (_I, [_P, _I]),
+    "spn_net_exec_mode": (_I, [_P]),
     "spn_net_result_order": (_U32, [_P]),
     "spn_net_result_slots": (_I, [_P, _P]),
     "spn_net_result_size": (_U64, [_P]),

@@ -1419,7 +1419,36 @@ int spn_net_compile(spn_net* net, int exec_mode) {
   NET_TRY
   check_uncompiled(net);
   if (net->root < 0) throw Error(SPN_ERR_INVALID, "network has no root");
-  if (exec_mode != SPN_EXEC_FUSED && exec_mode != SPN_EXEC_STEPWISE) throw Error(SPN_ERR_INVALID, "unknown exec mode");
+  if (exec_mode != SPN_EXEC_FUSED && exec_mode != SPN_EXEC_STEPWISE && exec_mode != SPN_EXEC_AUTO)
+    throw Error(SPN_ERR_INVALID, "unknown exec mode");
+  if (exec_mode == SPN_EXEC_AUTO) {
+    // Try the fused compiler first (symbolic replay only: milliseconds).  Straight-line code stops paying off when
+    // the network has large intermediates: beyond ~20k FP64 instructions per point the kernel spills and NVRTC takes
+    // minutes, so such networks run one pairwise kernel per step instead.  Function leaves exist only in fused mode.
+    bool has_function_leaf = false;
+    for (auto& nd : net->nodes) has_function_leaf = has_function_leaf || nd.kind == LEAF_FUNCTION;
+    exec_mode = SPN_EXEC_FUSED;
+    if (!has_function_leaf) {
+      const size_t n_nodes_before = net->nodes.size();
+      try {
+        net->nodes.resize(n_nodes_before);
+        net->values.clear();
+        net->steps.clear();
+        net->schedule.clear();
+        net->prog = Program();
+        net->trial = 0;
+        std::map<int, int> memo;
+        net->result_value = net->build(net->root, memo);
+        net->node_value = memo;
+        net->compile_fused();
+        if (net->stats.n_fp > 20000) exec_mode = SPN_EXEC_STEPWISE;
+      } catch (const Error& e) {
+        if (e.code != SPN_ERR_INVALID) throw;
+        exec_mode = SPN_EXEC_STEPWISE;  // "too large for the fused executor"
+      }
+      net->nodes.resize(n_nodes_before);
+    }
+  }
   net->exec_mode = exec_mode;
   const size_t n_nodes0 = net->nodes.size();
   auto build_with = [&](int trial) {
@@ -1467,6 +1496,7 @@ int spn_net_compile(spn_net* net, int exec_mode) {
   NET_CATCH(false)
 }
 
+int spn_net_exec_mode(const spn_net* net) { return net->exec_mode; }
 uint32_t spn_net_result_order(const spn_net* net) {
   return net->compiled ? net->values[(size_t)net->result_value].st.order() : 0;
 }

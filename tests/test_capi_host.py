@@ -233,3 +233,16 @@ def test_maximum_orders():
     # fully contracted 16-index pair -> scalar
     p = sp.plan_contract(ca, ca)
     assert p.order_out == 0 and p.n_common == 16 and p.size_out == 1 and p.n_contracted == 2 ** 8
+
+
+def test_exec_mode_auto():
+    """AUTO = fused for the physics-sized networks, stepwise when intermediates are too large for straight-line code."""
+    net = workloads.build_engine(workloads.eemumu(), None, sp.AUTO)
+    assert net.exec_mode == sp.FUSED and "spn_fused_net_" in net.cuda_source
+    big = sp.Network(None)
+    e = sp.Euclidean
+    a = big.batched([e.new_slot(16, 1), e.new_slot(16, 2), e.new_slot(16, 3)])
+    b = big.batched([e.new_slot(16, 3), e.new_slot(16, 4), e.new_slot(16, 5)])
+    big.set_root(big.product(a, b))          # 65536-component result, 16 terms each
+    big.compile(sp.AUTO)
+    assert big.exec_mode == sp.STEPWISE and big.result_size == 16 ** 4
