@@ -360,7 +360,7 @@ def run_b200(args):
     host_out = None if want_sum else host_out_t.numpy().view(np.complex128).reshape(n, out_size)
     h2d = sum(int(p.numel()) * 8 for p in host_sets[0])
     d2h = 16 * out_size if want_sum else n * out_size * 16
-    e2e_chunk = max(n // 16, 1 << 14)
+    e2e_chunk = max(n // 8, 1 << 16)   # 128 Ki points for cfg2: measured sweet spot (tools/e2e_sweep.py)
 
     e2e_net = net if not stepwise else workloads.build_engine(spec, ctx, sp.FUSED)   # execute_host is the fused path
 
