@@ -84,6 +84,7 @@ struct JitKernel {
   cudaKernel_t kernel = nullptr;
   int blocks_per_sm = 0;
   int num_regs = 0;
+  size_t smem_bytes = 0;  // dynamic shared memory (prefetch ring)
   ~JitKernel() {
     if (lib) cudaLibraryUnload(lib);
   }
@@ -212,10 +213,17 @@ void jit_load(JitKernel& k, int block) {
   cuda_check(cudaLibraryGetKernel(&k.kernel, k.lib, k.name.c_str()), "cudaLibraryGetKernel");
   cudaFuncAttributes attr{};
   if (cudaFuncGetAttributes(&attr, (const void*)k.kernel) == cudaSuccess) k.num_regs = attr.numRegs;
+  if (k.smem_bytes > 48 * 1024) {
+    int dev = 0;
+    cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+    cuda_check(cudaKernelSetAttributeForDevice(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, dev),
+               "cudaKernelSetAttributeForDevice(MaxDynamicSharedMemorySize)");
+  }
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k.kernel, block, 0) != cudaSuccess || nb <= 0) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)k.kernel, block, k.smem_bytes) != cudaSuccess || nb <= 0) {
     cudaGetLastError();
     nb = k.num_regs > 0 ? std::max(1, 65536 / (k.num_regs * block)) : 4;
+    if (k.smem_bytes) nb = std::max(1, std::min(nb, (int)(200 * 1024 / k.smem_bytes)));
   }
   k.blocks_per_sm = nb;
 }
@@ -740,6 +748,34 @@ struct spn_net {
   // variant key: per input 'p' (point major, 32-byte aligned: 256-bit loads allowed) / 'q' (point
   // major, 16-byte aligned only) / 'c' (component major); then out: 'n' none, 'p', 'c'
   // (+ 'r' = real output); then 's' when the sum over points is wanted
+  // How a kernel variant hides the latency of its input loads.  Compute-heavy networks (FP64 time per point
+  // comparable to its HBM time: cfg5) hold many live registers and run at ~2 warps per scheduler, so the loads of
+  // FUTURE points must be in flight while the current one is computed:
+  //   RING  each thread cp.async-copies its next kRingDepth-1 points into a private shared-memory ring
+  //         (conflict-free [slot][load][thread] layout; no block barrier: a thread only reads what it wrote)
+  //   REGS  register double buffering of the next point (when the ring would not fit in shared memory)
+  //   NONE  bandwidth-bound networks at high occupancy (cfg2): loads are placed lazily next to their first use
+  enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2 };
+  static constexpr int kRingDepth = 4;
+  struct PrefetchPlan {
+    int mode = PF_NONE;
+    uint32_t n_loads = 0;
+    size_t smem_bytes = 0;
+  };
+  PrefetchPlan plan_prefetch(const std::string& variant) const {
+    PrefetchPlan pf;
+    const char out_mode = variant[n_inputs];
+    const uint64_t size_out = result_el.size();
+    const double t_fp = (double)stats.n_fp / (64.0 * 148.0 * 1.9e9);
+    const double t_hbm = (double)(stats.n_load_bytes + (out_mode == 'n' ? 0 : 16 * size_out)) / 6.5e12;
+    if (stats.n_load_bytes == 0 || stats.n_load_bytes > 512 || t_fp <= 0.5 * t_hbm || getenv("SPN_NO_PREFETCH")) return pf;
+    for (auto& i : prog.ins) pf.n_loads += (i.op == I_LOADC || i.op == I_LOADR);
+    pf.smem_bytes = (size_t)kRingDepth * pf.n_loads * (size_t)kBlock * 16;
+    pf.mode = (pf.smem_bytes <= 96 * 1024 && !getenv("SPN_NO_RING")) ? PF_RING : PF_REGS;
+    if (pf.mode != PF_RING) pf.smem_bytes = 0;
+    return pf;
+  }
+
   std::string gen_source(const std::string& variant, const std::string& kname) const {
     const uint64_t size_out = result_el.size();
     const char out_mode = variant[n_inputs];
@@ -754,6 +790,10 @@ struct spn_net {
     o << "__device__ __forceinline__ double ld8(const double* p) { return __ldg(p); }\n";
     o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
          "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
+    o << "__device__ __forceinline__ void cp_async16(void* s, const double* g) {\n"
+         "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 16;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g));\n}\n";
+    o << "__device__ __forceinline__ void cp_async8(void* s, const double* g) {\n"
+         "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 8;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g));\n}\n";
     o << "extern \"C\" __global__ void __launch_bounds__(" << kBlock << (kMinBlocks ? ", " + std::to_string(kMinBlocks) : std::string()) << ") " << kname << "(";
     for (uint32_t k = 0; k < n_inputs; ++k) o << "const double* __restrict__ in" << k << ", ull cs" << k << ", ";
     o << "double* __restrict__ out, ull ocs, double2* __restrict__ block_sums, ull n_points) {\n";
@@ -807,10 +847,8 @@ struct spn_net {
            << "ull) * 2);\n";
       }
     };
-    // Compute-heavy networks (FP64 time per point comparable to its HBM time) run at low occupancy (many live
-    // registers), so the input loads of the NEXT point are issued before the arithmetic of the current one.
-    const double t_fp = (double)stats.n_fp / (64.0 * 148.0 * 1.9e9), t_hbm = (double)(stats.n_load_bytes + (out_mode == 'n' ? 0 : 16 * size_out)) / 6.5e12;
-    const bool prefetch = stats.n_load_bytes > 0 && stats.n_load_bytes <= 512 && t_fp > 0.5 * t_hbm && !getenv("SPN_NO_PREFETCH");
+    const PrefetchPlan pf = plan_prefetch(variant);
+    const bool prefetch = pf.mode != PF_NONE;
     for (const Ins& i : prog.ins) {
       if (i.op == I_LOADC) {
         name[(size_t)i.dst] = "l" + std::to_string(i.dst) + ".x";
@@ -819,7 +857,45 @@ struct spn_net {
         name[(size_t)i.dst] = "l" + std::to_string(i.dst);
       }
     }
-    if (prefetch) {
+    // source address (in doubles) of one load at point `pv`
+    auto load_addr = [&](const Ins& i, const std::string& pv) {
+      const Node& n = nodes[input_nodes[(size_t)i.in]];
+      std::ostringstream a;
+      const int w = i.op == I_LOADC ? 2 : 1;
+      if (variant[(size_t)i.in] == 'c')
+        a << "in" << i.in << " + (" << i.flat << "ull * cs" << i.in << " + " << pv << ") * " << w;
+      else
+        a << "in" << i.in << " + (" << pv << " * " << n.st.size() << "ull + " << i.flat << "ull) * " << w;
+      return a.str();
+    };
+    if (pf.mode == PF_RING) {
+      o << "  extern __shared__ __align__(16) double2 ring[];   // [" << kRingDepth << " slots][" << pf.n_loads << " loads]["
+        << kBlock << " threads]\n";
+      o << "  ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x;\n  const ull stride = (ull)gridDim.x * " << kBlock << ";\n";
+      // issue(pp, slot): this thread's loads of point pp -> ring slot
+      o << "  auto issue = [&](ull pp, int slot) {\n";
+      uint32_t e = 0;
+      for (const Ins& i : prog.ins)
+        if (i.op == I_LOADC || i.op == I_LOADR) {
+          o << "    cp_async" << (i.op == I_LOADC ? 16 : 8) << "(&ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock
+            << " + threadIdx.x], " << load_addr(i, "pp") << ");\n";
+          ++e;
+        }
+      o << "  };\n";
+      o << "  for (int d = 0; d < " << kRingDepth << "; ++d) {\n    if (p + d * stride < n_points) issue(p + d * stride, d);\n"
+           "    asm volatile(\"cp.async.commit_group;\" ::);\n  }\n";
+      o << "  for (int it = 0; p < n_points; p += stride, ++it) {\n    const int slot = it & " << (kRingDepth - 1) << ";\n";
+      o << "    asm volatile(\"cp.async.wait_group " << (kRingDepth - 1) << ";\" ::: \"memory\");\n";
+      e = 0;
+      for (const Ins& i : prog.ins)
+        if (i.op == I_LOADC || i.op == I_LOADR) {
+          if (i.op == I_LOADC)
+            o << "    const double2 l" << i.dst << " = ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock << " + threadIdx.x];\n";
+          else
+            o << "    const double l" << i.dst << " = ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock << " + threadIdx.x].x;\n";
+          ++e;
+        }
+    } else if (pf.mode == PF_REGS) {
       o << "  ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x;\n  const ull stride = (ull)gridDim.x * " << kBlock << ";\n";
       for (const Ins& i : prog.ins) {
         if (i.op == I_LOADC) o << "  double2 l" << i.dst << " = make_double2(0.0, 0.0), n" << i.dst << " = make_double2(0.0, 0.0);\n";
@@ -910,9 +986,12 @@ struct spn_net {
       else
         o << "    reinterpret_cast<double2*>(out)[" << idx << "] = make_double2(" << re << ", " << im << ");\n";
     }
-    if (prefetch)
+    if (pf.mode == PF_REGS)
       for (const Ins& i : prog.ins)
         if (i.op == I_LOADC || i.op == I_LOADR) o << "    l" << i.dst << " = n" << i.dst << ";\n";
+    if (pf.mode == PF_RING)  // refill the slot just consumed with the point kRingDepth iterations ahead
+      o << "    if (p + " << kRingDepth << " * stride < n_points) issue(p + " << kRingDepth << " * stride, slot);\n"
+           "    asm volatile(\"cp.async.commit_group;\" ::);\n";
     o << "  }\n";
     if (want_sum) {
       // per-block partial of the Monte-Carlo sum: fixed shuffle tree + fixed order over warps
@@ -941,6 +1020,7 @@ struct spn_net {
     std::snprintf(nm, sizeof nm, "spn_fused_net_%08x_%s", (unsigned)(fnv1a(probe) & 0xffffffffu), variant.c_str());
     k->name = nm;
     k->source = gen_source(variant, k->name);
+    k->smem_bytes = plan_prefetch(variant).smem_bytes;
     jit_compile(*k);
     JitKernel& ref = *k;
     variants[variant].k = std::move(k);
@@ -1620,7 +1700,7 @@ int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t 
     args.push_back(&ocs);
     args.push_back(&partial);
     args.push_back(&np);
-    cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), 0, st),
+    cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), k.smem_bytes, st),
                "launch fused network kernel");
     ctx->launches++;
     if (host_sum) {
@@ -1759,7 +1839,7 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   args.push_back(&ocs);
   args.push_back(&partial);
   args.push_back(&np);
-  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), 0, ctx->stream),
+  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), k.smem_bytes, ctx->stream),
              "launch fused network kernel");
   ctx->launches++;
   if (sum_out_device) {
