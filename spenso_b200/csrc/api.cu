@@ -260,6 +260,11 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
   if (kt.off_a.size() > (size_t)1 << 24) throw Error(SPN_ERR_INVALID, "contracted volume too large for the table path");
 
   const bool a_sp = a->sparse(), b_sp = b->sparse();
+  if (any_batched && contract_small_jit(ctx, plan, kt, a, b, res.get(), n_points)) {
+    // physics-sized per-point tensors: a kernel specialised for this stride plan (same rounding as below)
+    *out = res.release();
+    return;
+  }
   if (a_sp != b_sp) {
     // K2: one shared sparse operand -> CSR gather over the stored entries only
     const spn_tensor* sp = a_sp ? a : b;

@@ -5,11 +5,16 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "kernels.cuh"
 #include "structure.hpp"
+
+namespace spn {
+struct JitKernel;
+}
 
 struct spn_ctx {
   int device = 0;
@@ -17,6 +22,8 @@ struct spn_ctx {
   uint64_t launches = 0;
   int sm_count = 148;
   bool emulate_reference_pairing = false;  // SURVEY K-note 3, see build_k_tables
+  // specialised pairwise kernels (pairwise_jit.cu), keyed by a hash of (plan, storage, dtype, layout)
+  std::map<uint64_t, std::shared_ptr<spn::JitKernel>> pair_kernels;
 };
 
 struct spn_tensor {
@@ -97,6 +104,10 @@ DevOutMap out_map_of(const spn_contract_plan& p);
 spn_tensor* new_shared_dense(spn_ctx* ctx, const Structure& st, const double2* data);
 spn_tensor* new_shared_sparse(spn_ctx* ctx, const Structure& st, const std::map<uint64_t, double2>& entries);
 spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, int dtype, int layout, void* wrap);
+
+// pairwise_jit.cu: launch a kernel specialised for this contraction (small per-point tensors); false = not applicable
+bool contract_small_jit(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
+                        const spn_tensor* b, spn_tensor* res, uint64_t n_points);
 
 // the Contract trait: result in *out (new tensor)
 void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out);

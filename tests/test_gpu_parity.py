@@ -863,3 +863,38 @@ def test_gamma_adjoint_identities_on_device(ctx):
     net.execute([], out)
     ctx.synchronize()
     assert (out.to_numpy() == 4 * np.eye(4)).all()
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_specialised_pairwise_kernels_bit_exact(ctx, seed):
+    """Batches large enough to take the JIT-specialised pairwise kernels (pairwise_jit.cu): results must be
+    bit-identical to the oracle (same operation order, no FMA), for dense x dense, dense x sparse (both receiver
+    orders), f64 operands and both layouts."""
+    rng = np.random.default_rng(7000 + seed)
+    n_points, done = 2048, 0
+    for it in range(10):
+        a, b = _cases.random_pair(rng, max_free=2, max_common=2)
+        layout = sp.POINT_MAJOR if it % 2 == 0 else sp.COMPONENT_MAJOR
+        ta, oa, da = dense_pair(ctx, rng, a, n_points, layout)
+        sparse_b = it % 3 == 2
+        if sparse_b:
+            cb = O.order_structure(b)[0] if len(b) else b
+            ent = _cases.random_sparse_entries(rng, [int(d) for d in cb["dim"]])
+            tb, ob = sp.SparseTensor.from_entries(ctx, cb, ent), [O.OTensor.sparse(cb, ent)] * n_points
+        else:
+            tb, ob, _ = dense_pair(ctx, rng, b, n_points, layout)
+        swap = it % 4 == 3
+        sample = rng.choice(n_points, 40, replace=False)
+        try:
+            refs = [(ob[p].contract(oa[p]) if swap else oa[p].contract(ob[p])) for p in sample]
+        except O.OracleError:
+            continue
+        before = ctx.launch_count
+        c = tb.contract(ta) if swap else ta.contract(tb)
+        assert ctx.launch_count == before + 1
+        got = c.to_numpy()[sample]
+        want = np.stack([r.to_dense() for r in refs])
+        assert c.slots.tobytes() == refs[0].slots.tobytes()
+        assert (got == want).all(), f"case {it}: specialised kernel is not bit-identical"
+        done += 1
+    assert done >= 5

@@ -1,0 +1,64 @@
+"""Achieved HBM bandwidth of the pairwise (Contract-trait) kernels on batched physics-sized tensors.
+Usage (on a GPU box): python tools/pairwise_bench.py [n_points]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spenso_b200 as sp  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+stream = torch.cuda.current_stream()
+ctx = sp.Context(0, stream=stream.cuda_stream)
+b = lambda a: sp.Bispinor.new_slot(4, a)
+m = lambda a: sp.Minkowski.new_slot(4, a)
+
+
+def rand_batch(sl, layout=sp.POINT_MAJOR):
+    size = int(np.prod([s.dim for s in sl])) if sl else 1
+    t = sp.BatchTensor.empty(ctx, sl, n, sp.C64, layout)
+    x = torch.rand(n * size * 2, dtype=torch.float64, device="cuda")
+    sp.check(sp.lib().spn_tensor_upload  # device->device copy through a host bounce is avoided: write in place
+             (t.h, None, 0, 0)) if False else None
+    import ctypes
+    ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(t.device_ptr), ctypes.c_void_p(x.data_ptr()),
+                                              ctypes.c_size_t(n * size * 16), 3)
+    return t, size
+
+
+def timeit(fn, iters=20):
+    for _ in range(3):
+        r = fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        r = fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters, r
+
+
+gamma = None
+cases = []
+A, sa = rand_batch([b(1), b(2), m(3)])
+P, sp_ = rand_batch([m(3)])
+cases.append(("dense[bis,bis,mink] x dense[mink] -> [bis,bis]   (K1)", lambda: A.contract(P), (sa + sp_ + 16) * 16))
+M1, s1 = rand_batch([b(1), b(2)])
+M2, s2 = rand_batch([b(2), b(3)])
+cases.append(("dense[bis,bis] x dense[bis,bis] -> [bis,bis]      (K1)", lambda: M1.contract(M2), (s1 + s2 + 16) * 16))
+ent = {(0, 2, 0): 1, (1, 3, 0): 1, (2, 0, 0): 1, (3, 1, 0): 1, (0, 3, 1): 1, (1, 2, 1): 1, (2, 1, 1): -1, (3, 0, 1): -1,
+       (0, 3, 2): -1j, (1, 2, 2): 1j, (2, 1, 2): 1j, (3, 0, 2): -1j, (0, 2, 3): 1, (1, 3, 3): -1, (2, 0, 3): -1, (3, 1, 3): 1}
+G = sp.SparseTensor.from_entries(ctx, [b(1), b(2), m(3)], ent)
+cases.append(("sparse gamma (shared) x dense[mink] -> [bis,bis]   (K2)", lambda: G.contract(P), (sp_ + 16) * 16))
+V, sv = rand_batch([b(2)])
+cases.append(("dense[bis,bis] x dense[bis] -> [bis]              (K1)", lambda: M1.contract(V), (s1 + sv + 4) * 16))
+cases.append(("dense[bis,bis] + dense[bis,bis]              (add)", lambda: M1 + M1, 3 * 16 * 16))
+W, sw = rand_batch([b(1), b(2)])
+cases.append(("dense[bis,bis] x dense[bis,bis] -> scalar (multi, K5)", lambda: M1.contract(W), (s1 + sw + 1) * 16))
+for name, fn, bytes_pp in cases:
+    ms, r = timeit(fn)
+    print(f"{name:62s} {ms*1e3:8.1f} us  {bytes_pp*n/ms/1e6:7.0f} GB/s  ({bytes_pp} B/point)", flush=True)
