@@ -546,9 +546,6 @@ def test_network_power_conj_scalars(ctx, mode):
     m1, m2 = [sp.Minkowski.new_slot(4, 1)], [sp.Minkowski.new_slot(4, 2)]
     P, Q = _cases.random_complex(rng, (n, 4)), _cases.random_complex(rng, (n, 4))
 
-    class Both:  # the two builders share method names except conj/power/scalar
-        pass
-
     def conj(net, x):
         return net.conj(x) if isinstance(net, sp.Network) else net.op(O.N_CONJ, [x])
 

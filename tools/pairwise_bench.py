@@ -21,9 +21,8 @@ def rand_batch(sl, layout=sp.POINT_MAJOR):
     size = int(np.prod([s.dim for s in sl])) if sl else 1
     t = sp.BatchTensor.empty(ctx, sl, n, sp.C64, layout)
     x = torch.rand(n * size * 2, dtype=torch.float64, device="cuda")
-    sp.check(sp.lib().spn_tensor_upload  # device->device copy through a host bounce is avoided: write in place
-             (t.h, None, 0, 0)) if False else None
     import ctypes
+    # fill in place with a device-to-device copy (no host bounce)
     ctypes.CDLL("libcudart.so.12").cudaMemcpy(ctypes.c_void_p(t.device_ptr), ctypes.c_void_p(x.data_ptr()),
                                               ctypes.c_size_t(n * size * 16), 3)
     return t, size
@@ -42,7 +41,6 @@ def timeit(fn, iters=20):
     return e0.elapsed_time(e1) / iters, r
 
 
-gamma = None
 cases = []
 A, sa = rand_batch([b(1), b(2), m(3)])
 P, sp_ = rand_batch([m(3)])
