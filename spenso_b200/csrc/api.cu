@@ -260,11 +260,19 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
   if (kt.off_a.size() > (size_t)1 << 24) throw Error(SPN_ERR_INVALID, "contracted volume too large for the table path");
 
   const bool a_sp = a->sparse(), b_sp = b->sparse();
+  static const char* kind_name[] = {"FirstBeforeSecond", "SecondBeforeFirst", "Interleaved"};
+  const char* how = plan.n_common == 0 ? "exterior" : (plan.n_common == 1 ? "single" : "multi");
   if (any_batched && contract_small_jit(ctx, plan, kt, a, b, res.get(), n_points)) {
     // physics-sized per-point tensors: a kernel specialised for this stride plan (same rounding as below)
+    SPN_TRACE_LOG("contract %s %s: size_out=%llu n_k=%zu points=%llu -> specialised kernel", how, kind_name[plan.merge_kind],
+                  (unsigned long long)plan.size_out, kt.off_a.size(), (unsigned long long)n_points);
     *out = res.release();
     return;
   }
+  SPN_TRACE_LOG("contract %s %s: size_out=%llu n_k=%zu points=%llu -> %s", how, kind_name[plan.merge_kind],
+                (unsigned long long)plan.size_out, kt.off_a.size(), (unsigned long long)n_points,
+                a_sp != b_sp ? "CSR gather kernel"
+                             : (zgemm_applicable(plan, a, b, res.get(), n_points, kt) ? "DMMA ZGEMM kernel" : "generic dense kernel"));
   if (a_sp != b_sp) {
     // K2: one shared sparse operand -> CSR gather over the stored entries only
     const spn_tensor* sp = a_sp ? a : b;

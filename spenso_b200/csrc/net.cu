@@ -1413,6 +1413,9 @@ int spn_net_compile(spn_net* net, int exec_mode) {
       }
     }
     build_with(best_trial);
+    SPN_TRACE_LOG("network compile: %zu pairwise steps, schedule trial %d of %d, %llu fp64 instr/point, %llu input bytes/point",
+                  net->steps.size(), best_trial, trials, (unsigned long long)net->stats.n_fp,
+                  (unsigned long long)net->stats.n_load_bytes);
   }
   net->const_tensors.resize(net->values.size());
   if (exec_mode == SPN_EXEC_FUSED) {

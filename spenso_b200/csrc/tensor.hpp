@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
@@ -92,6 +94,21 @@ inline void cuda_check(cudaError_t e, const char* what) {
     throw Error(code, std::string(what) + ": " + cudaGetErrorString(e));
   }
 }
+
+// SPN_TRACE=1: one line per dispatch decision on stderr (the counterpart of the reference's log::trace! calls in
+// contraction.rs:157,174,192 and multicontract.rs:39,95,161,217)
+inline bool trace_enabled() {
+  static const bool on = getenv("SPN_TRACE") != nullptr;
+  return on;
+}
+#define SPN_TRACE_LOG(...)                 \
+  do {                                     \
+    if (spn::trace_enabled()) {            \
+      std::fprintf(stderr, "[spenso_b200] "); \
+      std::fprintf(stderr, __VA_ARGS__);   \
+      std::fprintf(stderr, "\n");          \
+    }                                      \
+  } while (0)
 
 // host-side helpers shared by the pairwise API and the network compiler
 struct KTables {
