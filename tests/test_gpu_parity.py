@@ -895,3 +895,38 @@ def test_specialised_pairwise_kernels_bit_exact(ctx, seed):
         assert (got == want).all(), f"case {it}: specialised kernel is not bit-identical"
         done += 1
     assert done >= 5
+
+
+@pytest.mark.parametrize("mode", [sp.FUSED, sp.STEPWISE])
+def test_reference_graph_addition_expression(ctx, mode):
+    """The expression of the reference's own graph test (spenso/src/network/graph.rs:1530-1584):
+        t3b * (t + t2) * s2 * (s + 0) * (t3 * (t + t2) * s * (1 + 0))
+    with t, t2 on [mink1|2, mink2|2], t3 on [lor1|2, euc2|2], t3b on [lor_dual1|2, euc2|1], s = 2, s2 = 3 — nested
+    products inside products (merge_ops), sums of tensors, sums of scalars, scalar leaves, dim-1 slots, a
+    Lorentz/dual pair and two Minkowski pairs contracted across the nesting."""
+    rng = np.random.default_rng(17)
+    n = 64
+    mk = lambda rep, d, a: rep.new_slot(d, a)
+    s_t = [mk(sp.Minkowski, 1, 2), mk(sp.Minkowski, 2, 2)]
+    s_t3 = [mk(sp.Euclidean, 2, 2), mk(sp.Lorentz, 1, 2)]                # canonical order (self-dual before dualizable)
+    s_t3b = [mk(sp.Euclidean, 2, 1), mk(sp.Lorentz.dual(), 1, 2)]
+    T, T2 = _cases.random_complex(rng, (n, 2)), _cases.random_complex(rng, (n, 2))
+    T3, T3b = _cases.random_complex(rng, (n, 2)), _cases.random_complex(rng, (n, 2))
+    slots_list = [s_t, s_t, s_t, s_t, s_t3, s_t3b]        # every leaf is entered once per use, like the reference's graph
+    arrays = [T, T2, T, T2, T3, T3b]
+
+    def build(net, l):
+        t_a, t2_a, t_b, t2_b, t3, t3b = l
+        s, s2, zero, one = net.scalar(2.0), net.scalar(3.0), net.scalar(0.0), net.scalar(1.0)
+        inner = net.product(t3, net.sum(t_b, t2_b), s, net.sum(one, net.scalar(0.0)))
+        return net.product(t3b, net.sum(t_a, t2_a), s2, net.sum(s, zero), inner)
+
+    got, want = _net_pair(ctx, build, arrays, slots_list, mode)
+    assert got.shape == want.shape == (n, 4)      # free indices: euc2|1, euc2|2
+    assert rel_err(got, want) <= TOL
+    # closed form: ((t+t2).(t+t2) with the Minkowski metric) * t3b[e1] * t3[e2] * 3 * 2 * 2 * 1
+    u = T + T2
+    dot = u[:, 0] * u[:, 0] - u[:, 1] * u[:, 1]       # dim-1 slot: index 0 only (+); dim-2 slot: (+,-)
+    # [mink1|2] has a single component (sign +); [mink2|2]: components (+,-); data layout [mink1, mink2] -> 2 values
+    cf = 12.0 * dot[:, None, None] * T3b[:, :, None] * T3[:, None, :]
+    assert rel_err(got.reshape(n, 2, 2), cf) <= 1e-12
