@@ -73,6 +73,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dim", type=int, default=32, help="cfg4: index dimension (32 = the BASELINE config)")
+    ap.add_argument("--real", action="store_true", help="cfg4: f64 tensors (DGEMM) instead of Complex<f64> (ZGEMM)")
     return ap.parse_args()
 
 
@@ -470,13 +471,18 @@ def run_cfg4(args):
     stream = torch.cuda.current_stream()
     ctx = sp.Context(local_rank, stream=stream.cuda_stream)
     g = torch.Generator(device=dev).manual_seed(1236)
-    mk = lambda r: torch.complex(torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1,
-                                 torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
+    if args.real:
+        mk = lambda r: torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    else:
+        mk = lambda r: torch.complex(torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1,
+                                     torch.rand(r, n, generator=g, device=dev, dtype=torch.float64) * 2 - 1)
+    edt = sp.F64 if args.real else sp.C64
     B = mk(n)                                       # same seed on every rank: B is replicated
     A = mk(max(rows, 1))
     sa = [sp.Euclidean.new_slot(d1 if i == 1 else d, i) for i in (1, 2, 3, 4, 5, 6)]
-    ta = sp.BatchTensor.wrap(ctx, sa, 1, A.data_ptr(), keepalive=A)
-    tb = sp.BatchTensor.wrap(ctx, [sp.Euclidean.new_slot(d, i) for i in (4, 5, 6, 7, 8, 9)], 1, B.data_ptr(), keepalive=B)
+    ta = sp.BatchTensor.wrap(ctx, sa, 1, A.data_ptr(), dtype=edt, keepalive=A)
+    tb = sp.BatchTensor.wrap(ctx, [sp.Euclidean.new_slot(d, i) for i in (4, 5, 6, 7, 8, 9)], 1, B.data_ptr(), dtype=edt,
+                             keepalive=B)
     K, W = min(args.steps, 3), 3 if d < 32 else 1
 
     def barrier():
@@ -501,12 +507,13 @@ def run_cfg4(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    flops = 8.0 * n * n * n
+    fpm = 2.0 if args.real else 8.0      # flops per multiply-add of the element type
+    flops = fpm * n * n * n
     del c
-    # denominator: cuBLAS ZGEMM measured here (best of 4), 8192^3 complex
+    # denominator: cuBLAS ZGEMM / DGEMM measured here (best of 4), 8192^3
     m = 8192
-    X = torch.randn(m, m, dtype=torch.complex128, device=dev)
-    Y = torch.randn(m, m, dtype=torch.complex128, device=dev)
+    X = torch.randn(m, m, dtype=torch.float64 if args.real else torch.complex128, device=dev)
+    Y = torch.randn(m, m, dtype=torch.float64 if args.real else torch.complex128, device=dev)
     best = 1e30
     for _ in range(4):
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -515,19 +522,20 @@ def run_cfg4(args):
         a1.record()
         torch.cuda.synchronize()
         best = min(best, a0.elapsed_time(a1))
-    cublas_tf = 8.0 * m ** 3 / (best * 1e-3) / 1e12
+    cublas_tf = fpm * m ** 3 / (best * 1e-3) / 1e12
     achieved = flops / world / (ms * 1e-3) / 1e12      # per GPU
     if rank == 0:
         line = {
             "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC["cfg4"], "dim": d, "M=N=K": n,
-                       "l2": f"operands {2 * n * n * 16 / 2**30:.0f} GiB >> 126 MB L2",
+                       "element": "f64" if args.real else "Complex<f64>",
+                       "l2": f"operands {2 * n * n * (8 if args.real else 16) / 2**30:.0f} GiB >> 126 MB L2",
                        "parallelism": f"rows of A/C cut into {world} block(s), B replicated, no collective"},
             "gpu_launches": int(ctx.launch_count - launches0),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": cublas_tf, "unit": "TFLOP/s",
-                         "frac": achieved / cublas_tf, "traffic": None, "kernel": "contract_zgemm_kernel",
-                         "peak_source": f"cuBLAS ZGEMM {m}^3 measured in this run (FP64 tensor pipe; tcgen05 has no f64 kind)",
+                         "frac": achieved / cublas_tf, "traffic": None, "kernel": "contract_dgemm_kernel" if args.real else "contract_zgemm_kernel",
+                         "peak_source": f"cuBLAS {'DGEMM' if args.real else 'ZGEMM'} {m}^3 measured in this run (FP64 tensor pipe; tcgen05 has no f64 kind)",
                          "flops_per_eval": flops, "per_gpu": True},
             "clocks": clocks.summary(),
         }

@@ -182,7 +182,8 @@ static bool zgemm_applicable(const spn_contract_plan& p, const spn_tensor* a, co
                              uint64_t n_points, const KTables& kt) {
   if (getenv("SPN_NO_ZGEMM")) return false;
   if (a->sparse() || b->sparse()) return false;
-  if (a->dtype != SPN_C64 || b->dtype != SPN_C64 || res->dtype != SPN_C64) return false;
+  // complex x complex -> ZGEMM, real x real -> DGEMM; mixed operands take the streaming kernel
+  if (a->dtype != b->dtype || a->dtype != res->dtype) return false;
   if (p.n_partition != p.order_out || p.n_common == 0) return false;
   // element stride 1 within a point (point-major batched, or shared)
   if (a->operand().fs != 1 || b->operand().fs != 1 || res->operand().fs != 1) return false;
@@ -229,11 +230,18 @@ static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KT
   DevArray<long long> d_row_a(row_a, ctx->stream), d_out_row(out_row, ctx->stream), d_col_b(col_b, ctx->stream),
       d_out_col(out_col, ctx->stream), d_k_a(k_a, ctx->stream), d_k_b(k_b, ctx->stream);
   DevArray<double> d_ks(ks, ctx->stream);
-  cuda_check(launch_contract_zgemm(static_cast<const double2*>(a->dptr), static_cast<const double2*>(b->dptr),
-                                   static_cast<double2*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
-                                   d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
-                                   a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
-             "contract_zgemm_kernel");
+  if (a->dtype == SPN_C64)
+    cuda_check(launch_contract_zgemm(static_cast<const double2*>(a->dptr), static_cast<const double2*>(b->dptr),
+                                     static_cast<double2*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
+                                     d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
+                                     a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
+               "contract_zgemm_kernel");
+  else
+    cuda_check(launch_contract_dgemm(static_cast<const double*>(a->dptr), static_cast<const double*>(b->dptr),
+                                     static_cast<double*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
+                                     d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
+                                     a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
+               "contract_dgemm_kernel");
   ctx->launches++;
 }
 

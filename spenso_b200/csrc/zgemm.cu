@@ -203,7 +203,174 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
   }
 }
 
+// ---- real (f64 x f64) variant: DGEMM on the same pipe -------------------------------------------------------------
+// CTA tile 128x128, 8 warps of 32(m) x 64(n), BK = 8, 4-stage cp.async pipeline of 8-byte gathers; 64-bit fragment
+// loads with conflict-free strides (A: BK+4 = 12, B: 128+4 = 132 doubles, both == 4 mod 16).
+constexpr int DBM = 128, DBN = 128, DSA = BK + 4, DSB = DBN + 4;
+
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
+}
+
+template <bool SIGN>
+__global__ void __launch_bounds__(256, 1)
+contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                      const ll* __restrict__ row_a, const ll* __restrict__ k_a, const ll* __restrict__ col_b,
+                      const ll* __restrict__ k_b, const ll* __restrict__ out_row, const ll* __restrict__ out_col,
+                      const double* __restrict__ ksign, ll M, ll N, ll K, ll ps_a, ll ps_b, ll ps_c) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* As = reinterpret_cast<double*>(smem_raw);            // [STAGES][DBM][DSA]
+  double* Bs = As + STAGES * DBM * DSA;                         // [STAGES][BK][DSB]
+  ll* s_row = reinterpret_cast<ll*>(Bs + STAGES * BK * DSB);    // [DBM]
+  ll* s_col = s_row + DBM;                                      // [DBN]
+
+  const ll tiles_m = (M + DBM - 1) / DBM, tiles_n = (N + DBN - 1) / DBN;
+  const ll pid = blockIdx.x;
+  const ll group = pid / (GROUP_M * tiles_n);
+  const ll first_m = group * GROUP_M;
+  const ll gsz = min((ll)GROUP_M, tiles_m - first_m);
+  const ll tile_m = first_m + (pid % (GROUP_M * tiles_n)) % gsz;
+  const ll tile_n = (pid % (GROUP_M * tiles_n)) / gsz;
+  const ll m0 = tile_m * DBM, n0 = tile_n * DBN;
+  const ll p = blockIdx.y;
+  A += p * ps_a;
+  B += p * ps_b;
+  C += p * ps_c;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
+  if (tid < DBM) s_row[tid] = (m0 + tid < M) ? __ldg(row_a + m0 + tid) : -1;
+  if (tid >= 128) s_col[tid - 128] = (n0 + tid - 128 < N) ? __ldg(col_b + n0 + tid - 128) : -1;
+  __syncthreads();
+
+  // loaders: A tile 128 rows x 8 k -> 4 elements per thread (k fastest); B tile 8 k x 128 n -> 4 per thread (n fastest)
+  const int a_kk = tid & 7, a_r0 = tid >> 3;       // rows a_r0 + 32 i
+  const int b_n = tid & 127, b_k0 = tid >> 7;      // k rows b_k0 + 2 i
+  const ll KT = (K + BK - 1) / BK;
+  ll ka_next = 0, kb_next[4] = {0, 0, 0, 0};
+  auto fetch_koffs = [&](ll kt) {
+    const ll kbase = kt * BK;
+    const ll k = kbase + a_kk;
+    ka_next = (kt < KT && k < K) ? __ldg(k_a + k) : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const ll kk = kbase + b_k0 + 2 * i;
+      kb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
+    }
+  };
+  auto load_tile = [&](int stage, ll kt) {
+    const ll kbase = kt * BK;
+    double* as = As + stage * DBM * DSA;
+    double* bs = Bs + stage * BK * DSB;
+    const bool kv = kbase + a_kk < K;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = a_r0 + 32 * i;
+      const ll ro = s_row[r];
+      const bool v = kv && ro >= 0;
+      cp_async8(as + r * DSA + a_kk, A + (v ? ro + ka_next : 0), v);
+    }
+    const ll co = s_col[b_n];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = b_k0 + 2 * i;
+      const bool v = kbase + kk < K && co >= 0;
+      cp_async8(bs + kk * DSB + b_n, B + (v ? co + kb_next[i] : 0), v);
+    }
+  };
+
+  double c[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    fetch_koffs(s);
+    if (s < KT) load_tile(s, s);
+    cp_async_commit();
+  }
+  fetch_koffs(STAGES - 1);
+
+  const int fr = lane >> 2, fk = lane & 3;
+  for (ll kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const ll nxt = kt + STAGES - 1;
+      if (nxt < KT) load_tile((int)(nxt % STAGES), nxt);
+      cp_async_commit();
+      fetch_koffs(nxt + 1);
+    }
+    const int stage = (int)(kt % STAGES);
+    const double* as = As + stage * DBM * DSA;
+    const double* bs = Bs + stage * BK * DSB;
+#pragma unroll
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      double a[4], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = as[(wm + 8 * i + fr) * DSA + k4 * 4 + fk];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = bs[(k4 * 4 + fk) * DSB + wn + 8 * j + fr];
+      if (SIGN) {
+        const ll k = kt * BK + k4 * 4 + fk;
+        const double sg = (k < K) ? __ldg(ksign + k) : 1.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] *= sg;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const ll r = m0 + wm + 8 * i + fr;
+    if (r >= M) continue;
+    const ll orow = __ldg(out_row + r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const ll cc = n0 + wn + 8 * j + 2 * fk + e;
+        if (cc < N) C[orow + __ldg(out_col + cc)] = c[i][j][e];
+      }
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_contract_dgemm(const double* A, const double* B, double* C, const long long* row_a,
+                                  const long long* k_a, const long long* col_b, const long long* k_b,
+                                  const long long* out_row, const long long* out_col, const double* ksign,
+                                  long long M, long long N, long long K, long long ps_a, long long ps_b,
+                                  long long ps_c, unsigned long long n_points, cudaStream_t stream) {
+  if (M == 0 || N == 0 || n_points == 0) return cudaSuccess;
+  const ll tiles = ((M + DBM - 1) / DBM) * ((N + DBN - 1) / DBN);
+  if (tiles > 0x7fffffffLL || n_points > 65535) return cudaErrorInvalidConfiguration;
+  const size_t smem = (size_t)STAGES * (DBM * DSA + BK * DSB) * sizeof(double) + (DBM + DBN) * sizeof(long long);
+  dim3 grid((unsigned)tiles, (unsigned)n_points);
+  cudaError_t e;
+  if (ksign) {
+    e = cudaFuncSetAttribute(contract_dgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    contract_dgemm_kernel<true><<<grid, 256, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, ksign, M,
+                                                            N, K, ps_a, ps_b, ps_c);
+  } else {
+    e = cudaFuncSetAttribute(contract_dgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    contract_dgemm_kernel<false><<<grid, 256, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, nullptr,
+                                                             M, N, K, ps_a, ps_b, ps_c);
+  }
+  return cudaGetLastError();
+}
 
 size_t zgemm_smem_bytes() {
   return (size_t)STAGES * (BM * SA + BK * SB) * sizeof(double2) + (BM + BN) * sizeof(long long);

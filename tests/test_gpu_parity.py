@@ -930,3 +930,25 @@ def test_reference_graph_addition_expression(ctx, mode):
     # [mink1|2] has a single component (sign +); [mink2|2]: components (+,-); data layout [mink1, mink2] -> 2 values
     cf = 12.0 * dot[:, None, None] * T3b[:, :, None] * T3[:, None, :]
     assert rel_err(got.reshape(n, 2, 2), cf) <= 1e-12
+
+
+@pytest.mark.parametrize("case", range(len(GEMM_CASES)))
+def test_dgemm_path_vs_oracle(ctx, case):
+    """f64 x f64 GEMM-shaped contractions take the real DMMA kernel (contract_dgemm_kernel); result stays f64."""
+    rng = np.random.default_rng(600 + case)
+    a, b = (O.slots(*x) for x in GEMM_CASES[case])
+    ca, cb = O.order_structure(a)[0], O.order_structure(b)[0]
+    n_points = 2
+    da = rng.uniform(-1, 1, size=[n_points] + [int(d) for d in ca["dim"]])
+    db = rng.uniform(-1, 1, size=[n_points] + [int(d) for d in cb["dim"]])
+    ta = sp.BatchTensor.empty(ctx, ca, n_points, sp.F64)
+    ta.upload(da.reshape(n_points, -1))
+    tb = sp.BatchTensor.empty(ctx, cb, n_points, sp.F64)
+    tb.upload(db.reshape(n_points, -1))
+    c = ta.contract(tb)
+    assert c.dtype == sp.F64
+    refs = [O.OTensor.dense(ca, da[p].astype(complex), canonicalize=False).contract(
+        O.OTensor.dense(cb, db[p].astype(complex), canonicalize=False)) for p in range(n_points)]
+    want = np.stack([r.to_dense() for r in refs])
+    assert c.slots.tobytes() == refs[0].slots.tobytes()
+    assert not want.imag.any() and rel_err(c.to_numpy(), want.real) <= TOL
