@@ -236,12 +236,20 @@ static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KT
                                      d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
                                      a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
                "contract_zgemm_kernel");
-  else
+  else {
+    // 16-byte gathers when both tables are pairwise contiguous, every base offset is even and everything is aligned
+    bool vec = g.N % 2 == 0 && k_a.size() % 2 == 0 && a->operand().ps % 2 == 0 && b->operand().ps % 2 == 0 &&
+               (uintptr_t)a->dptr % 16 == 0 && (uintptr_t)b->dptr % 16 == 0;
+    for (size_t k = 0; vec && k + 1 < k_a.size(); k += 2) vec = k_a[k] % 2 == 0 && k_a[k + 1] == k_a[k] + 1;
+    for (size_t c = 0; vec && c + 1 < col_b.size(); c += 2) vec = col_b[c] % 2 == 0 && col_b[c + 1] == col_b[c] + 1;
+    for (size_t r = 0; vec && r < row_a.size(); ++r) vec = row_a[r] % 2 == 0;
+    for (size_t k = 0; vec && k < k_b.size(); ++k) vec = k_b[k] % 2 == 0;
     cuda_check(launch_contract_dgemm(static_cast<const double*>(a->dptr), static_cast<const double*>(b->dptr),
                                      static_cast<double*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
                                      d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
-                                     a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
+                                     a->operand().ps, b->operand().ps, res->operand().ps, n_points, vec, ctx->stream),
                "contract_dgemm_kernel");
+  }
   ctx->launches++;
 }
 

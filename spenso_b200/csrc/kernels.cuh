@@ -56,12 +56,13 @@ cudaError_t launch_contract_zgemm(const double2* A, const double2* B, double2* C
                                   long long M, long long N, long long K, long long ps_a, long long ps_b,
                                   long long ps_c, unsigned long long n_points, cudaStream_t stream);
 
-// the same for f64 x f64 -> f64 operands (DGEMM)
+// the same for f64 x f64 -> f64 operands (DGEMM).  vec: the tables are pairwise contiguous and even (see zgemm.cu),
+// operands and point strides 16-byte aligned -> 16-byte gathers
 cudaError_t launch_contract_dgemm(const double* A, const double* B, double* C, const long long* row_a,
                                   const long long* k_a, const long long* col_b, const long long* k_b,
                                   const long long* out_row, const long long* out_col, const double* ksign,
                                   long long M, long long N, long long K, long long ps_a, long long ps_b,
-                                  long long ps_c, unsigned long long n_points, cudaStream_t stream);
+                                  long long ps_c, unsigned long long n_points, bool vec, cudaStream_t stream);
 
 // element-wise (algebra/add_assign.rs, sub_assign.rs, neg.rs, scalar_mul.rs; FUN_LIB conj)
 enum EwOp { EW_ADD = 0, EW_SUB = 1, EW_NEG = 2, EW_SCALE = 3, EW_CONJ = 4, EW_COPY = 5, EW_RECIP = 6 };

@@ -214,7 +214,9 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool val
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gmem), "r"(bytes));
 }
 
-template <bool SIGN>
+// VEC: the gather tables are pairwise contiguous and even (k_a[2j+1] = k_a[2j] + 1, col_b[2j+1] = col_b[2j] + 1, all
+// base offsets even), so operands move with 16-byte cp.async — half the copy instructions of the 8-byte gather.
+template <bool SIGN, bool VEC>
 __global__ void __launch_bounds__(256, 1)
 contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                       const ll* __restrict__ row_a, const ll* __restrict__ k_a, const ll* __restrict__ col_b,
@@ -260,10 +262,42 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
       kb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
     }
   };
+  // VEC loaders: A 128 rows x 4 k-pairs -> 2 copies per thread; B 8 k x 64 n-pairs -> 2 copies per thread
+  const int va_kp = tid & 3, va_r0 = tid >> 2;     // rows va_r0 + 64 i, k = 2 va_kp
+  const int vb_np = tid & 63, vb_k0 = tid >> 6;    // k rows vb_k0 + 4 i, n = 2 vb_np
+  ll vka_next = 0, vkb_next[2] = {0, 0};
+  auto fetch_koffs_vec = [&](ll kt) {
+    const ll kbase = kt * BK;
+    const ll k = kbase + 2 * va_kp;
+    vka_next = (kt < KT && k < K) ? __ldg(k_a + k) : 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const ll kk = kbase + vb_k0 + 4 * i;
+      vkb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
+    }
+  };
   auto load_tile = [&](int stage, ll kt) {
     const ll kbase = kt * BK;
     double* as = As + stage * DBM * DSA;
     double* bs = Bs + stage * BK * DSB;
+    if (VEC) {
+      const bool kv = kbase + 2 * va_kp < K;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = va_r0 + 64 * i;
+        const ll ro = s_row[r];
+        const bool v = kv && ro >= 0;
+        cp_async16(as + r * DSA + 2 * va_kp, A + (v ? ro + vka_next : 0), v);
+      }
+      const ll co = s_col[2 * vb_np];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int kk = vb_k0 + 4 * i;
+        const bool v = kbase + kk < K && co >= 0;
+        cp_async16(bs + kk * DSB + 2 * vb_np, B + (v ? co + vkb_next[i] : 0), v);
+      }
+      return;
+    }
     const bool kv = kbase + a_kk < K;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -280,6 +314,12 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
       cp_async8(bs + kk * DSB + b_n, B + (v ? co + kb_next[i] : 0), v);
     }
   };
+  auto fetch = [&](ll kt) {
+    if (VEC)
+      fetch_koffs_vec(kt);
+    else
+      fetch_koffs(kt);
+  };
 
   double c[4][8][2];
 #pragma unroll
@@ -289,11 +329,11 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    fetch_koffs(s);
+    fetch(s);
     if (s < KT) load_tile(s, s);
     cp_async_commit();
   }
-  fetch_koffs(STAGES - 1);
+  fetch(STAGES - 1);
 
   const int fr = lane >> 2, fk = lane & 3;
   for (ll kt = 0; kt < KT; ++kt) {
@@ -303,7 +343,7 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
       const ll nxt = kt + STAGES - 1;
       if (nxt < KT) load_tile((int)(nxt % STAGES), nxt);
       cp_async_commit();
-      fetch_koffs(nxt + 1);
+      fetch(nxt + 1);
     }
     const int stage = (int)(kt % STAGES);
     const double* as = As + stage * DBM * DSA;
@@ -351,24 +391,24 @@ cudaError_t launch_contract_dgemm(const double* A, const double* B, double* C, c
                                   const long long* k_a, const long long* col_b, const long long* k_b,
                                   const long long* out_row, const long long* out_col, const double* ksign,
                                   long long M, long long N, long long K, long long ps_a, long long ps_b,
-                                  long long ps_c, unsigned long long n_points, cudaStream_t stream) {
+                                  long long ps_c, unsigned long long n_points, bool vec, cudaStream_t stream) {
   if (M == 0 || N == 0 || n_points == 0) return cudaSuccess;
   const ll tiles = ((M + DBM - 1) / DBM) * ((N + DBN - 1) / DBN);
   if (tiles > 0x7fffffffLL || n_points > 65535) return cudaErrorInvalidConfiguration;
   const size_t smem = (size_t)STAGES * (DBM * DSA + BK * DSB) * sizeof(double) + (DBM + DBN) * sizeof(long long);
   dim3 grid((unsigned)tiles, (unsigned)n_points);
-  cudaError_t e;
+  cudaError_t e = cudaSuccess;
+#define SPN_LAUNCH_DGEMM(SG, VC)                                                                                          \
+  e = cudaFuncSetAttribute(contract_dgemm_kernel<SG, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+  if (e != cudaSuccess) return e;                                                                                         \
+  contract_dgemm_kernel<SG, VC><<<grid, 256, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, ksign, M, N, \
+                                                             K, ps_a, ps_b, ps_c)
   if (ksign) {
-    e = cudaFuncSetAttribute(contract_dgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    contract_dgemm_kernel<true><<<grid, 256, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, ksign, M,
-                                                            N, K, ps_a, ps_b, ps_c);
+    if (vec) { SPN_LAUNCH_DGEMM(true, true); } else { SPN_LAUNCH_DGEMM(true, false); }
   } else {
-    e = cudaFuncSetAttribute(contract_dgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    contract_dgemm_kernel<false><<<grid, 256, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, nullptr,
-                                                             M, N, K, ps_a, ps_b, ps_c);
+    if (vec) { SPN_LAUNCH_DGEMM(false, true); } else { SPN_LAUNCH_DGEMM(false, false); }
   }
+#undef SPN_LAUNCH_DGEMM
   return cudaGetLastError();
 }
 
