@@ -569,9 +569,8 @@ static void do_upload(spn_tensor* t, const void* host, uint64_t first_point, uin
     void* stage = nullptr;
     cuda_check(cudaMallocAsync(&stage, n_points * sz * eb + 16, ctx->stream), "upload staging");
     cuda_check(cudaMemcpyAsync(stage, host, n_points * sz * eb, cudaMemcpyHostToDevice, ctx->stream), "upload");
-    DevOperand src{stage, (long long)sz, 1, t->dtype == SPN_C64};
-    DevOut dst{(char*)t->dptr + first_point * eb, 1, (long long)t->n_points, t->dtype == SPN_C64};
-    cuda_check(launch_elementwise(EW_COPY, src, src, dst, make_double2(0, 0), sz, n_points, true, ctx->stream),
+    // staged [point][flat] -> resident [flat][point]
+    cuda_check(launch_transpose(stage, (char*)t->dptr + first_point * eb, n_points, sz, sz, t->n_points, (int)eb, ctx->stream),
                "layout transpose");
     ctx->launches++;
     cudaFreeAsync(stage, ctx->stream);
@@ -609,9 +608,8 @@ int spn_tensor_download(const spn_tensor* t, void* host, uint64_t first_point, u
   } else {
     void* stage = nullptr;
     cuda_check(cudaMallocAsync(&stage, n_points * sz * eb + 16, ctx->stream), "download staging");
-    DevOperand src{(const char*)t->dptr + first_point * eb, 1, (long long)t->n_points, t->dtype == SPN_C64};
-    DevOut dst{stage, (long long)sz, 1, t->dtype == SPN_C64};
-    cuda_check(launch_elementwise(EW_COPY, src, src, dst, make_double2(0, 0), sz, n_points, false, ctx->stream),
+    // resident [flat][point] -> staged [point][flat]
+    cuda_check(launch_transpose((const char*)t->dptr + first_point * eb, stage, sz, n_points, t->n_points, sz, (int)eb, ctx->stream),
                "layout transpose");
     ctx->launches++;
     cuda_check(cudaMemcpyAsync(host, stage, n_points * sz * eb, cudaMemcpyDeviceToHost, ctx->stream), "download");

@@ -168,6 +168,27 @@ elementwise_kernel(int op, DevOperand a, DevOperand b, DevOut out, double2 s, ul
   }
 }
 
+// ---- layout conversion [point][flat] <-> [flat][point]: shared-memory tiled transpose, both sides coalesced ----------
+template <class T>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const T* __restrict__ in, T* __restrict__ out, ull rows, ull cols, ull in_ld, ull out_ld) {
+  __shared__ T tile[32][33];
+  const ull tiles_c = (cols + 31) / 32;
+  const ull r0 = ((ull)blockIdx.x / tiles_c) * 32, c0 = ((ull)blockIdx.x % tiles_c) * 32;
+  const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (unsigned j = 0; j < 32; j += 8) {
+    const ull r = r0 + ty + j, c = c0 + tx;
+    if (r < rows && c < cols) tile[ty + j][tx] = in[r * in_ld + c];
+  }
+  __syncthreads();
+#pragma unroll
+  for (unsigned j = 0; j < 32; j += 8) {
+    const ull c = c0 + ty + j, r = r0 + tx;
+    if (r < rows && c < cols) out[c * out_ld + r] = tile[tx][ty + j];
+  }
+}
+
 // ---- K8: trace over one repeated pair ------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 trace_kernel(const __grid_constant__ DevOutMap map, DevOperand a, DevOut out, ll diag_stride, unsigned dim,
@@ -314,6 +335,21 @@ cudaError_t launch_elementwise(int op, DevOperand a, DevOperand b, DevOut out, d
   if (total == 0) return cudaSuccess;
   unsigned grid = grid_for(total, 256, 8);
   elementwise_kernel<<<grid, 256, 0, stream>>>(op, a, b, out, scalar, size, n_points, point_fastest ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_transpose(const void* in, void* out, ull rows, ull cols, ull in_ld, ull out_ld, int elem_bytes,
+                             cudaStream_t stream) {
+  if (rows == 0 || cols == 0) return cudaSuccess;
+  const ull tiles = ((rows + 31) / 32) * ((cols + 31) / 32);
+  if (tiles > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+  dim3 grid((unsigned)tiles);
+  if (elem_bytes == 16)
+    transpose_kernel<double2><<<grid, 256, 0, stream>>>(static_cast<const double2*>(in), static_cast<double2*>(out), rows, cols,
+                                                        in_ld, out_ld);
+  else
+    transpose_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(in), static_cast<double*>(out), rows, cols,
+                                                       in_ld, out_ld);
   return cudaGetLastError();
 }
 

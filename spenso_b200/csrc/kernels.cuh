@@ -70,6 +70,11 @@ cudaError_t launch_elementwise(int op, DevOperand a, DevOperand b, DevOut out, d
                                unsigned long long size, unsigned long long n_points, bool point_fastest,
                                cudaStream_t stream);
 
+// out[c * out_ld + r] = in[r * in_ld + c] for r < rows, c < cols (elements of 8 or 16 bytes): the layout conversion
+// between point-major and component-major batched tensors
+cudaError_t launch_transpose(const void* in, void* out, unsigned long long rows, unsigned long long cols,
+                             unsigned long long in_ld, unsigned long long out_ld, int elem_bytes, cudaStream_t stream);
+
 // K8 trace: out[o] = sum_i sign(i) a[base(o) + i*diag_stride]
 cudaError_t launch_trace(const DevOutMap& map, DevOperand a, DevOut out, long long diag_stride, unsigned dim,
                          int metric, unsigned long long n_points, bool point_fastest, cudaStream_t stream);
