@@ -713,7 +713,15 @@ int spn_tensor_trace(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const spn_
                              ctx->stream),
              "download shared result");
   cuda_check(cudaStreamSynchronize(ctx->stream), "download shared result");
-  *out = new_shared_dense(ctx, rs, host.data());
+  if (a->sparse()) {
+    // Trace for SparseTensor keeps the result sparse and drops exact zeros (contraction/trace.rs:41-83, :59)
+    std::map<uint64_t, double2> ent;
+    for (uint64_t f = 0; f < host.size(); ++f)
+      if (host[f].x != 0.0 || host[f].y != 0.0) ent[f] = host[f];
+    *out = new_shared_sparse(ctx, rs, ent);
+  } else {
+    *out = new_shared_dense(ctx, rs, host.data());
+  }
   return SPN_OK;
   API_CATCH
 }

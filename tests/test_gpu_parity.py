@@ -952,3 +952,27 @@ def test_dgemm_path_vs_oracle(ctx, case):
     want = np.stack([r.to_dense() for r in refs])
     assert c.slots.tobytes() == refs[0].slots.tobytes()
     assert not want.imag.any() and rel_err(c.to_numpy(), want.real) <= TOL
+
+
+def test_trace_of_shared_tensors_keeps_storage(ctx):
+    """Trace::internal_contract on one-point tensors: dense stays dense, sparse stays sparse with exact zeros dropped
+    (contraction/trace.rs:12-83); values and the stored index set equal the oracle's."""
+    rng = np.random.default_rng(23)
+    raw = O.slots(("mink", 4, 5), ("euc", 3, 1), ("mink", 4, 5))
+    shape = [4, 3, 4]
+    ent = {(0, 0, 0): 2.0, (1, 0, 1): 2.0, (3, 2, 3): 1.5 - 1j, (2, 1, 0): 7.0, (1, 1, 1): 0.5j, (0, 1, 0): 0.5j}
+    dense = np.zeros(shape, dtype=complex)
+    for k, v in ent.items():
+        dense[k] = v
+    holder_slots = np.array([(1, 0, 0, d, 900 + i) for i, d in enumerate(shape)], dtype=sp.SLOT_DTYPE)
+    # sparse holder: entries keyed in the holder's (already canonical) order
+    st = [12, 4, 1]
+    hs = sp.SparseTensor.from_entries(ctx, holder_slots, ent)
+    hd = sp.DenseTensor.from_data(ctx, holder_slots, dense)
+    ts, td = hs.trace(raw), hd.trace(raw)
+    h = O.lib().orc_tensor_dense_raw(O._ptr(raw), len(raw), O._ptr(np.ascontiguousarray(dense).view(np.float64)))
+    want = O.OTensor(h).trace().to_dense()
+    assert ts.is_sparse and not td.is_sparse
+    assert (td.to_numpy() == want).all() and (ts.to_numpy() == want).all()
+    # euc index 0: 2 - 2 = 0 exactly -> dropped; index 1: 0.5i - 0.5i = 0 -> dropped; index 2: -(1.5 - i)
+    assert set(ts.entries()) == {2} and ts.entries()[2] == -(1.5 - 1j)
