@@ -964,9 +964,9 @@ def test_trace_of_shared_tensors_keeps_storage(ctx):
     dense = np.zeros(shape, dtype=complex)
     for k, v in ent.items():
         dense[k] = v
-    holder_slots = np.array([(1, 0, 0, d, 900 + i) for i, d in enumerate(shape)], dtype=sp.SLOT_DTYPE)
-    # sparse holder: entries keyed in the holder's (already canonical) order
-    st = [12, 4, 1]
+    # holder structure whose canonical order equals the written order (self-dual rep ids 0 < 1 < 2), so that the data
+    # stays row major over `raw`
+    holder_slots = np.array([(1, 0, i, d, 900 + i) for i, d in enumerate(shape)], dtype=sp.SLOT_DTYPE)
     hs = sp.SparseTensor.from_entries(ctx, holder_slots, ent)
     hd = sp.DenseTensor.from_data(ctx, holder_slots, dense)
     ts, td = hs.trace(raw), hd.trace(raw)
