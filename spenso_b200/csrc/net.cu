@@ -93,6 +93,8 @@ struct spn_net {
   std::vector<std::pair<int, int>> schedule;  // (node a, node b) of every pairwise contraction, -1 = intermediate
   int result_value = -1;
   std::map<int, int> node_value;  // node id -> value id of the compiled schedule
+  std::vector<int> input_nodes_all;  // ids of every LEAF_BATCHED node, including re-indexed views
+  std::map<int, std::unique_ptr<spn_net>> function_leaf_nets;  // stepwise: per function leaf, its own fused kernel
   // fused
   Program prog;
   std::vector<CE> result_el;
@@ -940,7 +942,31 @@ void run_stepwise(spn_net* net, const spn_tensor* const* inputs, spn_tensor* out
     const Value& V = net->values[v];
     if (V.leaf < 0) continue;
     const Node& n = net->nodes[(size_t)V.leaf];
-    if (n.kind == LEAF_FUNCTION) throw Error(SPN_ERR_INVALID, "function leaves need the fused executor");
+    if (n.kind == LEAF_FUNCTION) {
+      // materialise the device-filled leaf with a small fused kernel of its own (same inputs, root = the leaf)
+      auto& aux = net->function_leaf_nets[V.leaf];
+      if (!aux) {
+        aux = std::make_unique<spn_net>();
+        aux->ctx = ctx;
+        for (int id : net->input_nodes_all) {   // every batched leaf (and re-indexed view), same ids as in `net`
+          while ((int)aux->nodes.size() < id) aux->nodes.emplace_back();   // placeholders keep node ids aligned
+          aux->nodes.push_back(net->nodes[(size_t)id]);
+        }
+        while ((int)aux->nodes.size() < V.leaf) aux->nodes.emplace_back();
+        aux->nodes.push_back(n);
+        aux->n_inputs = net->n_inputs;
+        aux->input_nodes = net->input_nodes;
+        aux->root = V.leaf;
+        int rc = spn_net_compile(aux.get(), SPN_EXEC_FUSED);
+        if (rc != SPN_OK) throw Error(rc, spn_last_error());
+      }
+      uint64_t np = net->n_inputs ? inputs[0]->n_points : 1;
+      owned[v].reset(new_batched(ctx, n.st, np, SPN_C64, SPN_POINT_MAJOR, nullptr));
+      int rc = spn_net_execute(aux.get(), inputs, net->n_inputs, owned[v].get(), nullptr, 0, 0);
+      if (rc != SPN_OK) throw Error(rc, spn_last_error());
+      val[v] = owned[v].get();
+      continue;
+    }
     if (n.kind == LEAF_BATCHED) {
       if (v_is_alias(net, n)) {
         if (!n.flat_map.empty())
@@ -1024,6 +1050,7 @@ int spn_net_leaf_batched(spn_net* net, const spn_slot* slots, uint32_t n, int dt
   nd.dtype = dtype;
   net->nodes.push_back(std::move(nd));
   net->input_nodes.push_back((int)net->nodes.size() - 1);
+  net->input_nodes_all.push_back((int)net->nodes.size() - 1);
   return (int)net->nodes.size() - 1;
   NET_CATCH(true)
 }
@@ -1066,6 +1093,7 @@ int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t
   }
   if (identity) nd.flat_map.clear();
   net->nodes.push_back(std::move(nd));
+  net->input_nodes_all.push_back((int)net->nodes.size() - 1);
   return (int)net->nodes.size() - 1;
   NET_CATCH(true)
 }

@@ -976,3 +976,33 @@ def test_trace_of_shared_tensors_keeps_storage(ctx):
     assert (td.to_numpy() == want).all() and (ts.to_numpy() == want).all()
     # euc index 0: 2 - 2 = 0 exactly -> dropped; index 1: 0.5i - 0.5i = 0 -> dropped; index 2: -(1.5 - i)
     assert set(ts.entries()) == {2} and ts.entries()[2] == -(1.5 - 1j)
+
+
+def test_special_values_follow_ieee_like_the_reference(ctx):
+    """NaN, +-inf, signed zeros and denormals: the pairwise kernels use the reference's operation order with IEEE ops
+    (no FMA, no fast-math), so special values propagate exactly as on the CPU — compared bit for bit (any NaN == NaN)."""
+    sl_a = O.order_structure(O.slots(("bis", 4, 1), ("mink", 4, 2)))[0]
+    sl_b = O.order_structure(O.slots(("mink", 4, 2), ("bis", 4, 3)))[0]
+    rng = np.random.default_rng(41)
+    specials = np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 5e-324, -2.2e-308, 1.7e308, 1.0, -1.0])
+    for n_points in (3, 2048):          # generic kernel and specialised kernel
+        A = rng.choice(specials, size=(n_points, 16)) + 1j * rng.choice(specials, size=(n_points, 16))
+        B = rng.choice(specials, size=(n_points, 16)) + 1j * rng.choice(specials, size=(n_points, 16))
+        keep = rng.random((n_points, 16)) < 0.6       # mostly ordinary numbers, some special
+        A = np.where(keep, _cases.random_complex(rng, (n_points, 16)), A)
+        B = np.where(keep, _cases.random_complex(rng, (n_points, 16)), B)
+        ta = sp.BatchTensor.empty(ctx, sl_a, n_points)
+        ta.upload(A)
+        tb = sp.BatchTensor.empty(ctx, sl_b, n_points)
+        tb.upload(B)
+        with np.errstate(all="ignore"):
+            got = ta.contract(tb).to_numpy().reshape(n_points, -1)
+            sample = range(n_points) if n_points <= 8 else rng.choice(n_points, 64, replace=False)
+            for p in sample:
+                want = O.OTensor.dense(sl_a, A[p], canonicalize=False).contract(
+                    O.OTensor.dense(sl_b, B[p], canonicalize=False)).to_dense().reshape(-1)
+                for part in ("real", "imag"):
+                    g, w = getattr(got[p], part), getattr(want, part)
+                    assert (np.isnan(g) == np.isnan(w)).all()
+                    ok = ~np.isnan(w)
+                    assert (g[ok].view(np.uint64) == w[ok].view(np.uint64)).all()      # incl. the sign of zeros and infinities

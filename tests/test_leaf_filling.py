@@ -100,13 +100,18 @@ def test_leaf_filling_vs_host_filled_oracle():
     F = np.stack([_expr_eval.evaluate(c, {z: Z}) for c in comps], axis=1)
     want = 3.0 * (F * W).sum(axis=1)
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
-    # the stepwise executor refuses function leaves
-    net = sp.Network(ctx)
-    z = net.batched([sp.Euclidean.new_slot(3, 1)])
-    net.set_root(net.function([sp.Euclidean.new_slot(3, 2)], X.Param.vector(z, 3)))
-    net.compile(sp.STEPWISE)
-    with pytest.raises(sp.SpensoError):
-        net.evaluate([tz])
+    # the stepwise executor materialises a function leaf with a small fused kernel of its own, then proceeds pairwise
+    net2 = sp.Network(ctx)
+    z2 = net2.batched([sp.Euclidean.new_slot(3, 1)])
+    P2 = X.Param.vector(z2, 3)
+    comps2 = [P2[0] * P2[1] / P2[2] - P2[0].conj(), X.sqrt(X.re(P2[0]) * X.im(P2[1])) + 2.5j,
+              -(P2[2] / X.re(P2[1])) + 1.0 / P2[0], X.im(P2[2]) - 3.0]
+    f2 = net2.function([sp.Bispinor.new_slot(4, 5)], comps2)
+    w2 = net2.batched([sp.Bispinor.new_slot(4, 5)])
+    net2.set_root(net2.sum(net2.product(f2, w2), net2.product(net2.scalar(2.0), f2, w2)))
+    net2.compile(sp.STEPWISE)
+    got2 = net2.evaluate([tz, tw]).to_numpy().reshape(-1)
+    assert np.abs(got2 - want).max() <= 1e-12 * np.abs(want).max()
 
 
 @pytest.mark.gpu
