@@ -948,12 +948,13 @@ void run_stepwise(spn_net* net, const spn_tensor* const* inputs, spn_tensor* out
       if (!aux) {
         aux = std::make_unique<spn_net>();
         aux->ctx = ctx;
-        for (int id : net->input_nodes_all) {   // every batched leaf (and re-indexed view), same ids as in `net`
-          while ((int)aux->nodes.size() < id) aux->nodes.emplace_back();   // placeholders keep node ids aligned
-          aux->nodes.push_back(net->nodes[(size_t)id]);
-        }
-        while ((int)aux->nodes.size() < V.leaf) aux->nodes.emplace_back();
-        aux->nodes.push_back(n);
+        // same node ids as in `net`: every batched leaf (and re-indexed view) plus the function leaf; the other
+        // slots stay empty placeholders that nothing references
+        int max_id = V.leaf;
+        for (int id : net->input_nodes_all) max_id = std::max(max_id, id);
+        aux->nodes.resize((size_t)max_id + 1);
+        for (int id : net->input_nodes_all) aux->nodes[(size_t)id] = net->nodes[(size_t)id];
+        aux->nodes[(size_t)V.leaf] = n;
         aux->n_inputs = net->n_inputs;
         aux->input_nodes = net->input_nodes;
         aux->root = V.leaf;
