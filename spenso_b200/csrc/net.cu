@@ -395,6 +395,7 @@ struct spn_net {
     if (sz > kMaxFusedElems) throw Error(SPN_ERR_INVALID, "tensor too large for the fused executor; use SPN_EXEC_STEPWISE");
     std::vector<CE> el(sz);
     if (n.kind == LEAF_CONST) {
+      if (n.dense.size() != sz) throw Error(SPN_ERR_INVALID, "constant leaf without data");
       for (uint64_t f = 0; f < sz; ++f) el[f] = CE{rr_const(n.dense[f].x), rr_const(n.dense[f].y)};
     } else {
       // loads are created lazily at the first use (el holds placeholders resolved in sym_get)
