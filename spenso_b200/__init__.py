@@ -25,7 +25,7 @@ from ._capi import SLOT_DTYPE, ContractPlan, SpensoError, build_library, check, 
 __all__ = [
     "Representation", "Euclidean", "Minkowski", "Lorentz", "Bispinor", "SpinFundamental", "ColorAdjoint",
     "ColorFundamental", "ColorSextet", "Slot", "slots", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
-    "Network", "SpensoError", "canonicalize", "plan_contract", "build_library",
+    "Network", "NetExpr", "SpensoError", "canonicalize", "plan_contract", "build_library",
     "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE", "AUTO",
 ]
 
@@ -384,6 +384,47 @@ class BatchTensor(_Tensor):
 
 
 # ---- network ------------------------------------------------------------------------------------------------
+class NetExpr:
+    """A node of a Network with the reference's operator syntax (*, +, -, unary -, ** n, .conj())."""
+
+    def __init__(self, net: "Network", node: int):
+        self.net, self.node = net, int(node)
+
+    def __int__(self):
+        return self.node
+
+    __index__ = __int__
+
+    def _lift(self, o) -> int:
+        if isinstance(o, NetExpr):
+            return o.node
+        if isinstance(o, (int, float, complex)) and not isinstance(o, bool):
+            return self.net.scalar(complex(o))
+        raise TypeError(f"cannot combine a network expression with {type(o).__name__}")
+
+    def __mul__(self, o):
+        return NetExpr(self.net, self.net.product(self.node, self._lift(o)))
+
+    __rmul__ = __mul__
+
+    def __add__(self, o):
+        return NetExpr(self.net, self.net.sum(self.node, self._lift(o)))
+
+    __radd__ = __add__
+
+    def __neg__(self):
+        return NetExpr(self.net, self.net.neg(self.node))
+
+    def __sub__(self, o):
+        return self + (-(o if isinstance(o, NetExpr) else NetExpr(self.net, self._lift(o))))
+
+    def __pow__(self, n: int):
+        return NetExpr(self.net, self.net.power(self.node, int(n)))
+
+    def conj(self):
+        return NetExpr(self.net, self.net.conj(self.node))
+
+
 class Network:
     """Expression graph of Sum/Neg/Product/Power/Function(conj) ops over tensor, library and scalar
     leaves (spenso/src/network.rs:47-51, network/graph.rs).  compile() resolves index matching,
@@ -479,8 +520,19 @@ class Network:
     def conj(self, child) -> int:
         return self.op(OP_CONJ, [child])
 
-    def set_root(self, node: int):
-        check(lib().spn_net_set_root(self.h, node))
+    def set_root(self, node):
+        check(lib().spn_net_set_root(self.h, int(node)))
+
+    # expression style of the reference: Network::from_tensor(a) * Network::from_tensor(b) + ... (network.rs:335-351, 585-607)
+    def from_tensor(self, t, sl=None, dtype: int = C64) -> "NetExpr":
+        """A leaf as an expression node: a shared tensor (DenseTensor / SparseTensor), or — given slots — a per-point
+        input (the k-th call with slots declares the k-th input of execute())."""
+        if sl is not None:
+            return NetExpr(self, self.batched(sl, dtype))
+        return NetExpr(self, self.tensor(t))
+
+    def expr(self, node: int) -> "NetExpr":
+        return NetExpr(self, node)
 
     def compile(self, mode: int = FUSED):
         check(lib().spn_net_compile(self.h, mode))

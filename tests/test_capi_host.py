@@ -246,3 +246,22 @@ def test_exec_mode_auto():
     big.set_root(big.product(a, b))          # 65536-component result, 16 terms each
     big.compile(sp.AUTO)
     assert big.exec_mode == sp.STEPWISE and big.result_size == 16 ** 4
+
+
+def test_network_expression_operators():
+    """Reference-style expression building (Network::from_tensor(a) * ... + ...) compiles to the same kernel as the
+    explicit node calls."""
+    m1, m2 = [sp.Minkowski.new_slot(4, 1)], [sp.Minkowski.new_slot(4, 2)]
+    a = sp.Network(None)
+    p, q = a.from_tensor(None, m1), a.from_tensor(None, m1)
+    r = a.from_tensor(None, m2)
+    a.set_root((p * q) * r * 2.0 - (q * q) ** 2 * r.conj())
+    a.compile()
+    b = sp.Network(None)
+    bp, bq, br = b.batched(m1), b.batched(m1), b.batched(m2)
+    b.set_root(b.sum(b.product(b.product(b.product(bp, bq), br), b.scalar(2.0)),
+                     b.neg(b.product(b.power(b.product(bq, bq), 2), b.conj(br)))))
+    b.compile()
+    assert a.cuda_source == b.cuda_source and a.result_size == 4
+    with pytest.raises(TypeError):
+        p * "x"
