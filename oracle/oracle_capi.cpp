@@ -129,6 +129,43 @@ int64_t orc_flat_iter(const Slot* s, int n, const uint8_t* free_mask, int mode, 
   ORC_CATCH(-1)
 }
 
+// Same iterator driven by raw dims in the order GIVEN (row-major strides of that order, no
+// canonical sort): the reference's legacy snapshot tests (tests.rs:174-269) iterate fibres of
+// unsorted structures; the iterators themselves only see strides and shape.
+int64_t orc_flat_iter_dims(const uint64_t* dims, int n, const uint8_t* free_mask, int mode, int use_single,
+                           uint64_t shift, uint64_t* out, int64_t cap) {
+  ORC_TRY
+  std::vector<size_t> shape(dims, dims + n), strides(n, 1);
+  for (int i = n - 1; i-- > 0;) strides[i] = strides[i + 1] * shape[i + 1];
+  std::vector<uint8_t> fr(free_mask, free_mask + n);
+  FlatIt it;
+  if (mode <= 1) {
+    int nfree = 0, pos = -1;
+    for (int i = 0; i < n; ++i)
+      if (fr[i]) {
+        nfree++;
+        pos = i;
+      }
+    if (use_single && nfree == 1)
+      it = flat_it_single(strides, (size_t)pos, shape, mode == 1);
+    else
+      it = flat_it_multi(strides, shape, fr, mode == 1);
+  } else {
+    auto pr = flat_it_paired_conjugates(strides, shape, fr);
+    it = mode == 2 ? pr.first : pr.second;
+  }
+  it.shift(shift);
+  int64_t c = 0;
+  size_t f;
+  while (it.next(f)) {
+    if (c < cap) out[c] = f;
+    c++;
+    if (c > (int64_t)1 << 26) break;
+  }
+  return c;
+  ORC_CATCH(-1)
+}
+
 int64_t orc_metric_iter(const Slot* s, int n, const uint8_t* free_mask, int conj, const int64_t* order, int norder,
                         uint64_t* out, uint8_t* neg, int64_t cap) {
   ORC_TRY

@@ -180,6 +180,21 @@ def flat_iter(sl, free_mask, mode, use_single=False, shift=0, cap=1 << 20):
     return out[: min(n, cap)].astype(np.int64), n
 
 
+def flat_iter_dims(dims, free_mask, mode, use_single=False, shift=0, cap=1 << 20):
+    """flat_iter over raw dims in the given (unsorted) order — legacy snapshot tests."""
+    L = lib()
+    d = np.ascontiguousarray(dims, dtype=np.uint64)
+    fm = np.ascontiguousarray(free_mask, dtype=np.uint8)
+    out = np.zeros(cap, dtype=np.uint64)
+    L.orc_flat_iter_dims.restype = C.c_int64
+    L.orc_flat_iter_dims.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p,
+                                     C.c_int64]
+    n = L.orc_flat_iter_dims(_ptr(d), len(d), _ptr(fm), mode, int(use_single), shift, _ptr(out), cap)
+    if n < 0:
+        raise OracleError(-1, L.orc_last_error().decode())
+    return out[: min(n, cap)].astype(np.int64), n
+
+
 def metric_iter(sl, free_mask, conj=False, order=(), cap=1 << 20):
     L = lib()
     sl = np.ascontiguousarray(sl, dtype=SLOT_DTYPE)
