@@ -16,9 +16,11 @@
 //   complex product spenso/src/algebra/complex/mul.rs:16-21.
 // FMA contraction and a different summation order are allowed by the 1e-12 parity tolerance.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -71,6 +73,9 @@ struct Program {
   int n_vals = 0;
   // lazily created loads: (input, flat) -> value id of the real part
   std::map<std::pair<int, uint64_t>, int> loaded;
+  // emitted sums by canonical term list -> (value id, factor): sum == norm * factor * value(id)
+  std::map<std::vector<double>, std::pair<int, double>> cse;
+  bool cse_enabled = !getenv("SPN_NO_CSE");  // A/B switch for measurements
 
   int fresh(int n = 1) {
     int v = n_vals;
@@ -156,7 +161,23 @@ struct Program {
     }
     if (bil.empty() && lin.empty()) return rr_const(cst);
     if (bil.empty() && lin.size() == 1 && cst == 0.0) return RR{lin[0].x, lin[0].k};
-    const double s = std::fabs(bil.empty() ? lin[0].k : bil[0].k);
+    // value numbering: a sum is identified by its term set in canonical order, normalised so that the
+    // leading coefficient is +1.  The same sum (or an exact multiple of it: the transposed entry of a
+    // symmetric outer product, a sign-flipped copy, ...) is emitted once and re-used with a coefficient.
+    auto by_vars = [](const Term& a, const Term& b) { return a.x != b.x ? a.x < b.x : a.y < b.y; };
+    std::sort(bil.begin(), bil.end(), by_vars);
+    std::sort(lin.begin(), lin.end(), by_vars);
+    const double norm = bil.empty() ? lin[0].k : bil[0].k;
+    std::vector<double> key;
+    key.reserve(3 * (bil.size() + lin.size()) + 1);
+    for (auto& t : bil) { key.push_back(t.x); key.push_back(t.y); key.push_back(t.k / norm); }
+    for (auto& t : lin) { key.push_back(t.x); key.push_back(-1); key.push_back(t.k / norm); }
+    key.push_back(cst / norm);
+    if (cse_enabled) {
+      auto hit = cse.find(key);
+      if (hit != cse.end()) return RR{hit->second.first, norm * hit->second.second};
+    }
+    const double s = std::fabs(norm);
     int av = -1, as = 1;  // running accumulator: as * value(av)
     for (auto& t : bil) {
       Ins i;
@@ -208,6 +229,8 @@ struct Program {
       av = i.dst;
       as = 1;
     }
+    // value(av) * as == (sum / s) == (sum / norm) * sign(norm)
+    cse[key] = std::make_pair(av, (norm < 0 ? -1.0 : 1.0) * as);
     return RR{av, s * as};
   }
 

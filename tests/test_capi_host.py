@@ -265,3 +265,20 @@ def test_network_expression_operators():
     assert a.cuda_source == b.cuda_source and a.result_size == 4
     with pytest.raises(TypeError):
         p * "x"
+
+
+def test_merge_missed_match_is_restated_literally():
+    """SURVEY K-note 4 (ordered.rs:717-836): the sort key is (rep, dim, aind) but match_cmp compares
+    (dim, rep, aind), so when one operand mixes dualizable reps of different dimensions the monotone scan
+    can stop before the matching dual.  The oracle and the engine keep that behaviour (no "fix")."""
+    b = O.order_structure(O.slots(("cof", 3, 2), ("euc", 2, 5)))[0]
+    a_mixed = O.order_structure(O.slots(("lor_d", 4, 1), ("coaf", 3, 2)))[0]
+    a_plain = O.order_structure(O.slots(("coaf", 3, 2),))[0]
+    for x, y in ((a_mixed, b), (b, a_mixed)):
+        om, p = O.merge(x, y), sp.plan_contract(x, y)
+        assert om["common_a"].sum() == 0 and p.n_common == 0 and p.order_out == 4     # match missed
+        assert _plan_fields(p, len(x), len(y))["slots"].tobytes() == om["slots"].tobytes()
+    for x, y in ((a_plain, b), (b, a_plain)):
+        om, p = O.merge(x, y), sp.plan_contract(x, y)
+        assert om["common_a"].sum() == 1 and p.n_common == 1 and p.order_out == 1     # match found
+        assert _plan_fields(p, len(x), len(y))["slots"].tobytes() == om["slots"].tobytes()

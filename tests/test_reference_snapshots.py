@@ -353,3 +353,81 @@ def test_device_multi_contract_snapshot(ctx):
                 arr = f.to_numpy().reshape([n_points] + [int(d) for d in f.slots["dim"]])
                 for p in (0, n_points - 1):
                     assert (by_label(f.slots["aind"], arr[p], [6, 5]) == want).all(), (n_points, layout)
+
+
+# ---- the reference's 1000-seed sweeps (tests.rs:585-632 all_single_contractions, :800-851
+#      all_multi_contractions): same seeded inputs; the reference asserts the storage combinations agree,
+#      here they must also equal numpy.einsum (exact integers) ------------------------------------------------
+def sweep_case(s: int, multi: bool):
+    rng = R.Xoroshiro64Star(s)
+    if multi:
+        nc = rng.gen_range_i32(2, 5)
+        common = R.test_structure_with_id(range(1, nc + 1), s)
+        dual = R.test_structure_with_id([-i for i in range(1, nc + 1)], s)
+        sa = R.test_structure_with_id([nc + 1], s)
+        sb = R.test_structure_with_id([nc + 2], s)
+        free_b, free_a = [nc + 2], [nc + 1]
+    else:
+        common = R.test_structure_with_id([1], s)
+        dual = R.test_structure_with_id([-1], s)
+        sa = R.test_structure_with_id([2], s)
+        sb = R.test_structure_with_id([-3, 4], s)
+        free_b, free_a = [3, 4], [2]
+    for c, dc in zip(common, dual):
+        sa.insert(rng.gen_range_usize(0, len(sa)), c)
+        sb.insert(rng.gen_range_usize(0, len(sb)), dc)
+    sha, shb = [d for _, d, _ in sa], [d for _, d, _ in sb]
+    ea = R.test_tensor(int(np.prod(sha)), s + 3, "i32", -1000, 1000)
+    eb = R.test_tensor(int(np.prod(shb)), s + 4, "i32", -1000, 1000)
+    L = "abcdefghijkl"
+    out = free_b + free_a
+    expr = "".join(L[a] for _, _, a in sb) + "," + "".join(L[a] for _, _, a in sa) + "->" + "".join(L[a] for a in out)
+    want = np.einsum(expr, dense_of(eb, shb), dense_of(ea, sha))
+    return sa, sha, ea, sb, shb, eb, out, want
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_oracle_reference_seed_sweeps_equal_einsum(multi):
+    mk = {
+        "s": lambda sl, sh, e: O.OTensor.sparse(oslots(sl), unflatten(e, sh)),
+        "d": lambda sl, sh, e: O.OTensor.dense(oslots(sl), dense_of(e, sh)),
+    }
+    for s in range(0, 1000, 4 if multi else 2):
+        sa, sha, ea, sb, shb, eb, out, want = sweep_case(s, multi)
+        if max(np.prod(sha), np.prod(shb)) > 20000:
+            continue
+        for ka, kb in (("d", "d"), ("s", "s"), ("s", "d"), ("d", "s")):
+            try:
+                f = mk[kb](sb, shb, eb).contract(mk[ka](sa, sha, ea))
+            except O.OracleError:
+                # the reference unwrap_or(zeros) there too: empty sparse operand (singlecontract.rs:153-159)
+                assert (len(ea) == 0 or len(eb) == 0) and "s" in (ka, kb)
+                assert not want.any()
+                continue
+            got = by_label(f.slots["aind"], f.to_dense(), out)
+            assert (got == want).all(), (s, ka, kb)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("multi", [False, True])
+def test_device_reference_seed_sweeps_equal_einsum(ctx, multi):
+    import spenso_b200 as sp
+    mk = {
+        "s": lambda sl, sh, e: sp.SparseTensor.from_entries(ctx, eslots(sl), unflatten(e, sh)),
+        "d": lambda sl, sh, e: sp.DenseTensor.from_data(ctx, eslots(sl), dense_of(e, sh)),
+    }
+    done = 0
+    for s in range(0, 1000, 16 if multi else 8):
+        sa, sha, ea, sb, shb, eb, out, want = sweep_case(s, multi)
+        if max(np.prod(sha), np.prod(shb)) > 20000:
+            continue
+        for ka, kb in (("d", "d"), ("s", "s"), ("s", "d"), ("d", "s")):
+            try:
+                f = mk[kb](sb, shb, eb).contract(mk[ka](sa, sha, ea))
+            except sp.SpensoError:
+                assert (len(ea) == 0 or len(eb) == 0) and "s" in (ka, kb)
+                continue
+            arr = f.to_numpy().reshape([int(d) for d in f.slots["dim"]])
+            assert (by_label(f.slots["aind"], arr, out) == want).all(), (s, ka, kb)
+            done += 1
+    assert done > 100
