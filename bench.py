@@ -69,6 +69,10 @@ def parse_args():
     ap.add_argument("--layout", default="point", choices=["point", "component"])
     ap.add_argument("--exec", dest="exec_mode", default="fused", choices=["fused", "stepwise"],
                     help="stepwise = one pairwise kernel per contraction with intermediates in HBM (comparison only)")
+    ap.add_argument("--mc-sum", default="final", choices=["final", "step"],
+                    help="sum workloads at N>1: exchange the Monte-Carlo partial sums once after the K steps, or every step")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="the exchange: peer = csrc/comm.cu (one kernel over NVLink peer memory), nccl = torch.distributed")
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,7 +243,7 @@ def run_b200(args):
 
     import spenso_b200 as sp
     from spenso_b200 import workloads
-    from spenso_b200.sharding import allreduce_partial_sums, shard_range
+    from spenso_b200.sharding import allreduce_partial_sums, connect_peers, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -284,9 +288,16 @@ def run_b200(args):
     out = None if want_sum else sp.BatchTensor.empty(ctx, net.result_slots, n, sp.C64, layout)
     sums = torch.zeros(2 * out_size, dtype=torch.float64, device=dev)
     sum_ptr = sums.data_ptr() if want_sum else 0
+    # the one collective of the path (sum workloads, N > 1): Monte-Carlo partial sums over NVLink peer memory
+    comm = connect_peers(ctx, max_f64=max(2 * out_size, 2)) if (want_sum and world > 1 and args.allreduce == "peer") else None
+    per_step = want_sum and world > 1 and args.mc_sum == "step"
+    if per_step and comm is not None:
+        net.set_comm(comm)       # every step: network kernel + ONE fold/exchange kernel
 
     def step(i):
         net.execute(dev_sets[i % rot], out, sum_out_ptr=sum_ptr)
+        if per_step and comm is None:
+            allreduce_partial_sums(sums)
 
     def barrier():
         if world > 1:
@@ -332,8 +343,11 @@ def run_b200(args):
         else:
             for i in range(K):
                 step(i)
-        if want_sum:
-            allreduce_partial_sums(sums)   # the one collective of the path: final Monte-Carlo sum (no-op at N=1)
+        if want_sum and not per_step:      # the final Monte-Carlo sum (no-op at N=1)
+            if comm is not None:
+                comm.allreduce_sum(sums.data_ptr(), 2 * out_size)
+            else:
+                allreduce_partial_sums(sums)
         t_end.record(stream)
         clocks.sample()                    # the timed work is in flight right now
         barrier()
@@ -427,7 +441,10 @@ def run_b200(args):
             "config": {"workload": WORKLOAD_DESC[wl], "points_per_gpu_per_step": n, "layout": args.layout + "-major",
                        "result": "sum over points" if want_sum else "per-point tensor", "exec": args.exec_mode,
                        "l2": f"{rot} rotating input sets of {bytes_in / 1e6:.0f} MB (> 126 MB L2 between reuses)",
-                       "parallelism": f"points sharded, {world} rank(s), no data-path collective"},
+                       "parallelism": f"points sharded, {world} rank(s), no data-path collective"
+                                      + (f"; Monte-Carlo sum exchanged {'every step' if per_step else 'once after the K steps'} "
+                                         f"via {'NVLink peer-memory kernel (csrc/comm.cu)' if comm is not None else 'NCCL all-reduce'}"
+                                         if (want_sum and world > 1) else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": KE, "ms_per_step": e2e_ms / KE, "api": "spn_net_execute_host (chunked H2D/kernel/D2H pipeline)",
                     "chunk_points": e2e_chunk},
@@ -439,6 +456,9 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            net.set_comm(None)
+            comm.close()
         dist.destroy_process_group()
     return line
 

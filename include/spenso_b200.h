@@ -271,6 +271,34 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
  * Synchronous: host_out / host_sum are complete on return. */
 int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
                          void* host_out, double* host_sum, uint64_t chunk_points);
+/* ---- Monte-Carlo sum exchange between the GPUs of one node ----------------------------------
+ * The one collective of the path: the all-reduce (SUM) of the per-rank Monte-Carlo partial sums,
+ * 2*result_size doubles.  Nothing in the reference corresponds to it (it is single-process); its callers
+ * add the per-point results on the host.  One process per GPU; every rank owns a mailbox in its HBM that
+ * its peers write through NVLink peer mappings (CUDA IPC), so the exchange is ONE single-CTA kernel
+ * (fold of the per-CTA partials + push + flag wait + rank-ordered sum) with no library collective.
+ * Every rank obtains bit-identical sums (contributions are added in rank order).
+ *   1. spn_comm_create on every rank; 2. publish spn_comm_handle (SPN_COMM_HANDLE_BYTES) to all ranks by any
+ *   host channel (torch.distributed / MPI / a file); 3. spn_comm_connect with the world's handles in rank order.
+ * Calls are collective: every rank must issue the same sequence.  They are enqueued on the context's stream
+ * and are CUDA-graph capturable.  A peer that never arrives trips a device-side timeout (default 10 s,
+ * SPN_COMM_TIMEOUT_S) instead of hanging the GPU: spn_comm_status returns 1 + its rank. */
+typedef struct spn_comm spn_comm;
+#define SPN_COMM_HANDLE_BYTES 64
+int spn_comm_create(spn_ctx* ctx, int rank, int world, uint32_t max_f64, spn_comm** out);
+int spn_comm_handle(const spn_comm* comm, void* handle_out);
+int spn_comm_connect(spn_comm* comm, const void* all_handles);
+/* in place: inout_device[0..n_f64) := sum over ranks */
+int spn_comm_allreduce_sum(spn_comm* comm, double* inout_device, uint32_t n_f64);
+/* 0 = ok; 1 + r = timed out waiting for rank r (host-visible without synchronising) */
+int spn_comm_status(const spn_comm* comm);
+/* call after a host barrier: no peer may still be inside an exchange */
+void spn_comm_destroy(spn_comm* comm);
+/* Attach (or detach with NULL) a communicator to a compiled network: spn_net_execute's sum_out_device then
+ * receives the sum over the points of ALL ranks, produced by the fused fold + exchange kernel (one launch
+ * after the network kernel instead of a fold kernel plus a library all-reduce). */
+int spn_net_set_comm(spn_net* net, spn_comm* comm);
+
 /* pinned host memory for the host-buffer entry points (cudaHostAlloc / cudaFreeHost) */
 void* spn_host_alloc(uint64_t bytes);
 void spn_host_free(void* p);

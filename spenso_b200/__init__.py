@@ -25,7 +25,7 @@ from ._capi import SLOT_DTYPE, ContractPlan, SpensoError, build_library, check, 
 __all__ = [
     "Representation", "Euclidean", "Minkowski", "Lorentz", "Bispinor", "SpinFundamental", "ColorAdjoint",
     "ColorFundamental", "ColorSextet", "Slot", "slots", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
-    "Network", "NetExpr", "SpensoError", "canonicalize", "plan_contract", "build_library",
+    "Network", "NetExpr", "PeerComm", "SpensoError", "canonicalize", "plan_contract", "build_library",
     "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE", "AUTO",
 ]
 
@@ -383,6 +383,43 @@ class BatchTensor(_Tensor):
         return out.cpu().numpy().view(np.complex128).reshape(self.shape)
 
 
+class PeerComm:
+    """Monte-Carlo sum exchange between the GPUs of one node over NVLink peer memory (csrc/comm.cu,
+    include/spenso_b200.h spn_comm_*): one single-CTA kernel, no library collective, bit-identical sums on
+    every rank.  `exchange(handle_bytes) -> [handle_bytes of every rank, in rank order]` is any host-side
+    all-gather (spenso_b200.sharding.connect_peers uses torch.distributed)."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx: Context, rank: int, world: int, exchange=None, max_f64: int = 512):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        check(lib().spn_comm_create(ctx.h, rank, world, max_f64, C.byref(h)))
+        self.h = h
+        if world > 1:
+            mine = np.zeros(self.HANDLE_BYTES, dtype=np.uint8)
+            check(lib().spn_comm_handle(self.h, ptr(mine)))
+            everyone = exchange(mine.tobytes())
+            if len(everyone) != world or any(len(b) != self.HANDLE_BYTES for b in everyone):
+                raise ValueError("exchange() must return one 64-byte handle per rank, in rank order")
+            table = np.frombuffer(b"".join(everyone), dtype=np.uint8).copy()
+            check(lib().spn_comm_connect(self.h, ptr(table)))
+
+    def allreduce_sum(self, device_ptr: int, n_f64: int):
+        """in place on the context's stream: device f64[n] := sum over ranks"""
+        check(lib().spn_comm_allreduce_sum(self.h, C.c_void_p(device_ptr), n_f64))
+
+    @property
+    def status(self) -> int:
+        return int(lib().spn_comm_status(self.h))
+
+    def close(self):
+        """Call after a host barrier (no peer may still be inside an exchange)."""
+        if getattr(self, "h", None):
+            lib().spn_comm_destroy(self.h)
+            self.h = None
+
+
 # ---- network ------------------------------------------------------------------------------------------------
 class NetExpr:
     """A node of a Network with the reference's operator syntax (*, +, -, unary -, ** n, .conj())."""
@@ -533,6 +570,12 @@ class Network:
 
     def expr(self, node: int) -> "NetExpr":
         return NetExpr(self, node)
+
+    def set_comm(self, comm: Optional["PeerComm"]):
+        """With a communicator attached, execute(sum_out_ptr=...) yields the sum over the points of ALL ranks
+        (fused fold + NVLink exchange kernel)."""
+        check(lib().spn_net_set_comm(self.h, comm.h if comm is not None else None))
+        self._comm = comm
 
     def compile(self, mode: int = FUSED):
         check(lib().spn_net_compile(self.h, mode))

@@ -111,6 +111,13 @@ SYMBOLS = {
     "spn_net_execute_host": (_I, [_P, _P, _U32, _U64, _P, _P, _U64]),
     "spn_host_alloc": (_P, [_U64]),
     "spn_host_free": (None, [_P]),
+    "spn_comm_create": (_I, [_P, _I, _I, _U32, C.POINTER(_P)]),
+    "spn_comm_handle": (_I, [_P, _P]),
+    "spn_comm_connect": (_I, [_P, _P]),
+    "spn_comm_allreduce_sum": (_I, [_P, _P, _U32]),
+    "spn_comm_status": (_I, [_P]),
+    "spn_comm_destroy": (None, [_P]),
+    "spn_net_set_comm": (_I, [_P, _P]),
 }
 
 _lib = None

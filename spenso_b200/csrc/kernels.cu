@@ -245,19 +245,14 @@ reduce_points_kernel(DevOperand a, ull size, ull n_points, double2* __restrict__
     partial[(ull)blockIdx.x * size + c] = s;
   }
 }
-__global__ void reduce_partials_kernel(const double2* __restrict__ partial, int n_blocks, ull size,
-                                       double2* __restrict__ out) {
-  // one warp per component: fixed summation tree => run-to-run deterministic Monte-Carlo sums
-  const ull c = (ull)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= size) return;
-  double2 acc = make_double2(0.0, 0.0);
-  for (int b = threadIdx.x & 31; b < n_blocks; b += 32) {
-    double2 v = partial[(ull)b * size + c];
-    acc.x += v.x;
-    acc.y += v.y;
-  }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) out[c] = acc;
+constexpr unsigned kFoldComps = 16;  // components per CTA of reduce_partials_kernel (16 row groups of 16 threads)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const double2* __restrict__ partial, int n_blocks, ull size, double2* __restrict__ out) {
+  __shared__ double2 s_part[256], s_out[kFoldComps];
+  const unsigned c0 = blockIdx.x * kFoldComps;
+  const unsigned n_c = (unsigned)min((ull)kFoldComps, size - c0);
+  fold_partials_block(partial, n_blocks, size, c0, n_c, s_part, s_out);
+  if (threadIdx.x < n_c) out[c0 + threadIdx.x] = s_out[threadIdx.x];
 }
 
 int g_sm_count = 0;
@@ -365,7 +360,7 @@ cudaError_t launch_trace(const DevOutMap& map, DevOperand a, DevOut out, ll diag
 cudaError_t launch_reduce_partials(const double2* partial, int n_blocks, ull size, double2* out,
                                    cudaStream_t stream) {
   if (size == 0) return cudaSuccess;
-  unsigned grid = (unsigned)((size + 7) / 8);
+  unsigned grid = (unsigned)((size + kFoldComps - 1) / kFoldComps);
   reduce_partials_kernel<<<grid, 256, 0, stream>>>(partial, n_blocks, size, out);
   return cudaGetLastError();
 }

@@ -87,4 +87,47 @@ cudaError_t launch_reduce_points(DevOperand a, unsigned long long size, unsigned
 cudaError_t launch_reduce_partials(const double2* partial, int n_blocks, unsigned long long size, double2* out,
                                    cudaStream_t stream);
 
+#ifdef __CUDACC__
+// Fold of per-CTA partial sums partial[b * size + c] (b < n_blocks) for the n_c <= 256 components starting at c0, by
+// ONE CTA of 256 threads: thread = (row group g, component c); rows are read coalesced with four independent loads
+// in flight per thread (the fold is pure load latency), then the groups are added in a fixed order => run-to-run
+// deterministic Monte-Carlo sums.  s_part: 256 double2 of shared memory; the result for component c0 + c is in
+// s_out[c] (shared) after the call.
+__device__ __forceinline__ void fold_partials_block(const double2* __restrict__ partial, int n_blocks,
+                                                    unsigned long long size, unsigned c0, unsigned n_c,
+                                                    double2* s_part, double2* s_out) {
+  const unsigned tid = threadIdx.x;
+  const unsigned G = 256u / n_c;
+  const unsigned g = tid / n_c, c = tid - g * n_c;
+  if (g < G) {
+    const double2* col = partial + c0 + c;
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, a2 = a0, a3 = a0;
+    int b = (int)g;
+    for (; b + 3 * (int)G < n_blocks; b += 4 * (int)G) {
+      const double2 v0 = col[(unsigned long long)b * size], v1 = col[(unsigned long long)(b + (int)G) * size];
+      const double2 v2 = col[(unsigned long long)(b + 2 * (int)G) * size], v3 = col[(unsigned long long)(b + 3 * (int)G) * size];
+      a0.x += v0.x; a0.y += v0.y;
+      a1.x += v1.x; a1.y += v1.y;
+      a2.x += v2.x; a2.y += v2.y;
+      a3.x += v3.x; a3.y += v3.y;
+    }
+    for (; b < n_blocks; b += (int)G) {
+      const double2 v = col[(unsigned long long)b * size];
+      a0.x += v.x; a0.y += v.y;
+    }
+    s_part[g * n_c + c] = make_double2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+  }
+  __syncthreads();
+  if (tid < n_c) {
+    double2 s = s_part[tid];
+    for (unsigned k = 1; k < G; ++k) {
+      s.x += s_part[k * n_c + tid].x;
+      s.y += s_part[k * n_c + tid].y;
+    }
+    s_out[tid] = s;
+  }
+  __syncthreads();
+}
+#endif
+
 }  // namespace spn

@@ -105,6 +105,7 @@ struct spn_net {
   std::map<std::string, Variant> variants;
   std::string default_source, json;
   double2* sum_scratch = nullptr;  // per-block partials of the fused Monte-Carlo sum
+  spn_comm* comm = nullptr;        // optional: sums are exchanged with the peer GPUs (comm.cu)
   size_t sum_scratch_elems = 0;
   // host-buffer pipeline (spn_net_execute_host): kPipe slots, each with its own stream and device staging
   static constexpr int kPipe = 3;
@@ -1622,6 +1623,12 @@ void spn_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+int spn_net_set_comm(spn_net* net, spn_comm* comm) {
+  if (!net) return SPN_ERR_INVALID;
+  net->comm = comm;
+  return SPN_OK;
+}
+
 int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_inputs, spn_tensor* out,
                     double* sum_out_device, uint64_t first_point, uint64_t n_points) {
   NET_TRY
@@ -1723,7 +1730,10 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), k.smem_bytes, ctx->stream),
              "launch fused network kernel");
   ctx->launches++;
-  if (sum_out_device) {
+  if (sum_out_device && net->comm) {
+    // multi-GPU Monte-Carlo sum: fold the per-CTA partials and exchange with the peers in ONE kernel (comm.cu)
+    comm_exchange(net->comm, partial, (int)grid, sum_out_device, (uint32_t)(2 * size_out));
+  } else if (sum_out_device) {
     cuda_check(launch_reduce_partials(partial, (int)grid, size_out, reinterpret_cast<double2*>(sum_out_device),
                                       ctx->stream),
                "reduce_partials_kernel");

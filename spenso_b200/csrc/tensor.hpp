@@ -126,6 +126,10 @@ spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, in
 bool contract_small_jit(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
                         const spn_tensor* b, spn_tensor* res, uint64_t n_points);
 
+// comm.cu: fold the per-CTA partials (or take inout as the local sum when partial == nullptr) and exchange with
+// the peers in one launch on the context's stream
+void comm_exchange(spn_comm* c, const double2* partial, int n_blocks, double* inout_device, uint32_t n_f64);
+
 // the Contract trait: result in *out (new tensor)
 void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out);
 void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out);

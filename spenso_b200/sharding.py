@@ -24,3 +24,28 @@ def allreduce_partial_sums(partial, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     return partial
+
+
+def connect_peers(ctx, group=None, max_f64: int = 512):
+    """PeerComm over the ranks of the (initialised) torch.distributed group: the 64-byte mailbox handles are
+    all-gathered through torch.distributed; the exchange itself is csrc/comm.cu, not NCCL.
+    Without a process group: a world of one."""
+    import torch
+    import torch.distributed as dist
+
+    from . import PeerComm
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return PeerComm(ctx, 0, 1, max_f64=max_f64)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+
+    def exchange(mine: bytes):
+        dev = f"cuda:{ctx.device}" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=group)
+        return [bytes(o.cpu().tolist()) for o in out]
+
+    comm = PeerComm(ctx, rank, world, exchange, max_f64=max_f64)
+    dist.barrier(group)      # every rank has mapped every mailbox before the first exchange
+    return comm
