@@ -224,6 +224,32 @@ using DenseTensor = Tensor;
 using SparseTensor = Tensor;
 using BatchTensor = Tensor;
 
+// ---- Monte-Carlo sum exchange between the GPUs of one node (one process per GPU) ----------------------------------
+// all_gather(mine) -> the 64-byte handles of every rank, in rank order, over any host channel (MPI, sockets, a file)
+class PeerComm {
+ public:
+  template <class AllGather>
+  PeerComm(const Context& ctx, int rank, int world, uint32_t max_f64, AllGather&& all_gather) {
+    check(spn_comm_create(ctx.raw(), rank, world, max_f64, &h_));
+    if (world > 1) {
+      std::vector<unsigned char> mine(SPN_COMM_HANDLE_BYTES);
+      check(spn_comm_handle(h_, mine.data()));
+      std::vector<unsigned char> all = all_gather(mine);
+      if (all.size() != (size_t)world * SPN_COMM_HANDLE_BYTES) throw ContractionError(SPN_ERR_INVALID, "PeerComm: bad handle table");
+      check(spn_comm_connect(h_, all.data()));
+    }
+  }
+  ~PeerComm() { spn_comm_destroy(h_); }
+  PeerComm(const PeerComm&) = delete;
+  PeerComm& operator=(const PeerComm&) = delete;
+  void allreduce_sum(double* inout_device, uint32_t n_f64) { check(spn_comm_allreduce_sum(h_, inout_device, n_f64)); }
+  int status() const { return spn_comm_status(h_); }
+  spn_comm* raw() const { return h_; }
+
+ private:
+  spn_comm* h_ = nullptr;
+};
+
 // ---- network ------------------------------------------------------------------------------------------------------
 // Network::from_tensor(t1) * Network::from_tensor(t2) + ... then execute(): the expression is recorded, compiled
 // once and evaluated for every point by the device executor.
@@ -274,6 +300,8 @@ class Network {
     return out;
   }
   spn_net* raw() const { return h_.get(); }
+  // with a communicator attached, sums over points are sums over the points of all ranks (spn_net_set_comm)
+  void set_comm(spn_comm* comm) { check(spn_net_set_comm(h_.get(), comm)); }
 
  private:
   const Context* ctx_;

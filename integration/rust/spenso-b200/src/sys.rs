@@ -23,6 +23,10 @@ pub struct spn_tensor {
 pub struct spn_net {
     _p: [u8; 0],
 }
+#[repr(C)]
+pub struct spn_comm {
+    _p: [u8; 0],
+}
 
 pub const SPN_OK: c_int = 0;
 pub const SPN_ERR_EMPTY_SPARSE: c_int = 1;
@@ -86,4 +90,14 @@ unsafe extern "C" {
                                 host_out: *mut c_void, host_sum: *mut c_double, chunk_points: u64) -> c_int;
     pub fn spn_host_alloc(bytes: u64) -> *mut c_void;
     pub fn spn_host_free(p: *mut c_void);
+    // Monte-Carlo sum exchange between the GPUs of one node (NVLink peer memory, no collective library)
+    pub fn spn_comm_create(ctx: *mut spn_ctx, rank: c_int, world: c_int, max_f64: u32, out: *mut *mut spn_comm) -> c_int;
+    pub fn spn_comm_handle(comm: *const spn_comm, handle_out: *mut c_void) -> c_int;
+    pub fn spn_comm_connect(comm: *mut spn_comm, all_handles: *const c_void) -> c_int;
+    pub fn spn_comm_allreduce_sum(comm: *mut spn_comm, inout_device: *mut c_double, n_f64: u32) -> c_int;
+    pub fn spn_comm_status(comm: *const spn_comm) -> c_int;
+    pub fn spn_comm_destroy(comm: *mut spn_comm);
+    pub fn spn_net_set_comm(net: *mut spn_net, comm: *mut spn_comm) -> c_int;
 }
+
+pub const SPN_COMM_HANDLE_BYTES: usize = 64;
