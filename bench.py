@@ -458,7 +458,7 @@ def run_b200(args):
         dist.barrier()
         if comm is not None:
             net.set_comm(None)
-            comm.close()
+            comm.close(dist.barrier)
         dist.destroy_process_group()
     return line
 

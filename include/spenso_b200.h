@@ -292,7 +292,10 @@ int spn_comm_connect(spn_comm* comm, const void* all_handles);
 int spn_comm_allreduce_sum(spn_comm* comm, double* inout_device, uint32_t n_f64);
 /* 0 = ok; 1 + r = timed out waiting for rank r (host-visible without synchronising) */
 int spn_comm_status(const spn_comm* comm);
-/* call after a host barrier: no peer may still be inside an exchange */
+/* Teardown is two-phase because an exported mailbox must outlive its peers' mappings:
+ *   host barrier (nobody is inside an exchange) -> spn_comm_disconnect on every rank (unmaps the peers' mailboxes)
+ *   -> host barrier -> spn_comm_destroy (frees this rank's mailbox; disconnects first if that was skipped). */
+int spn_comm_disconnect(spn_comm* comm);
 void spn_comm_destroy(spn_comm* comm);
 /* Attach (or detach with NULL) a communicator to a compiled network: spn_net_execute's sum_out_device then
  * receives the sum over the points of ALL ranks, produced by the fused fold + exchange kernel (one launch

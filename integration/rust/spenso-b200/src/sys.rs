@@ -96,6 +96,7 @@ unsafe extern "C" {
     pub fn spn_comm_connect(comm: *mut spn_comm, all_handles: *const c_void) -> c_int;
     pub fn spn_comm_allreduce_sum(comm: *mut spn_comm, inout_device: *mut c_double, n_f64: u32) -> c_int;
     pub fn spn_comm_status(comm: *const spn_comm) -> c_int;
+    pub fn spn_comm_disconnect(comm: *mut spn_comm) -> c_int;
     pub fn spn_comm_destroy(comm: *mut spn_comm);
     pub fn spn_net_set_comm(net: *mut spn_net, comm: *mut spn_comm) -> c_int;
 }

@@ -413,9 +413,16 @@ class PeerComm:
     def status(self) -> int:
         return int(lib().spn_comm_status(self.h))
 
-    def close(self):
-        """Call after a host barrier (no peer may still be inside an exchange)."""
+    def close(self, barrier=None):
+        """Two-phase teardown (an exported mailbox must outlive its peers' mappings): barrier, unmap the peers,
+        barrier, free.  `barrier` is the host barrier of the job (e.g. torch.distributed.barrier); a world of one
+        needs none."""
         if getattr(self, "h", None):
+            if barrier is not None:
+                barrier()
+            check(lib().spn_comm_disconnect(self.h))
+            if barrier is not None:
+                barrier()
             lib().spn_comm_destroy(self.h)
             self.h = None
 

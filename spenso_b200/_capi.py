@@ -116,6 +116,7 @@ SYMBOLS = {
     "spn_comm_connect": (_I, [_P, _P]),
     "spn_comm_allreduce_sum": (_I, [_P, _P, _U32]),
     "spn_comm_status": (_I, [_P]),
+    "spn_comm_disconnect": (_I, [_P]),
     "spn_comm_destroy": (None, [_P]),
     "spn_net_set_comm": (_I, [_P, _P]),
 }

@@ -259,12 +259,25 @@ int spn_comm_status(const spn_comm* c) {
   return *reinterpret_cast<volatile int*>(c->status_host);
 }
 
+int spn_comm_disconnect(spn_comm* c) {
+  COMM_TRY
+  if (!c) throw Error(SPN_ERR_INVALID, "spn_comm_disconnect: null argument");
+  cuda_check(cudaSetDevice(c->ctx->device), "cudaSetDevice");
+  cuda_check(cudaDeviceSynchronize(), "spn_comm_disconnect");
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer[(size_t)r]) {
+      cudaIpcCloseMemHandle(c->peer[(size_t)r]);
+      c->peer[(size_t)r] = nullptr;
+    }
+  cudaGetLastError();
+  c->connected = false;
+  return SPN_OK;
+  COMM_CATCH
+}
+
 void spn_comm_destroy(spn_comm* c) {
   if (!c) return;
-  cudaSetDevice(c->ctx->device);
-  cudaDeviceSynchronize();
-  for (int r = 0; r < c->world; ++r)
-    if (r != c->rank && c->peer[(size_t)r]) cudaIpcCloseMemHandle(c->peer[(size_t)r]);
+  spn_comm_disconnect(c);
   if (c->peer_dev) cudaFree(c->peer_dev);
   if (c->local) cudaFree(c->local);
   if (c->status_host) cudaFreeHost(c->status_host);

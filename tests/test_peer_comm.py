@@ -17,7 +17,7 @@ def test_comm_symbols_and_argument_checks():
     import spenso_b200 as sp
     from spenso_b200._capi import lib
 
-    for name in ("spn_comm_create", "spn_comm_handle", "spn_comm_connect", "spn_comm_allreduce_sum", "spn_comm_status",
+    for name in ("spn_comm_create", "spn_comm_handle", "spn_comm_connect", "spn_comm_allreduce_sum", "spn_comm_status", "spn_comm_disconnect",
                  "spn_comm_destroy", "spn_net_set_comm"):
         assert hasattr(lib(), name)
     assert sp.PeerComm.HANDLE_BYTES == 64
@@ -150,9 +150,8 @@ def _worker(rank, world, port, q):
         scale = float(ref.abs().max())
         ok &= float((total - ref).abs().max()) <= 1e-12 * scale
         ok &= comm.status == 0
-        dist.barrier()
         net.set_comm(None)
-        comm.close()
+        comm.close(dist.barrier)
         dist.destroy_process_group()
         q.put((rank, bool(ok), ""))
     except Exception as e:  # noqa: BLE001

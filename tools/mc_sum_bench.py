@@ -144,7 +144,7 @@ def main():
     barrier()
     if rank == 0:
         print(json.dumps(res), flush=True)
-    comm.close()
+    comm.close(dist.barrier if world > 1 else None)
     if world > 1:
         dist.destroy_process_group()
 
