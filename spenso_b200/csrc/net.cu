@@ -614,6 +614,48 @@ struct spn_net {
     uint32_t n_loads = 0;
     size_t smem_bytes = 0;
   };
+  // widest vector (in doubles) the REAL loads of input `in` may use in this variant: a 32-byte aligned point-major
+  // tensor whose per-point size is a multiple of 4 (2) doubles keeps every aligned quad (pair) inside one sector
+  int real_vec(const std::string& variant, int in) const {
+    if (variant[(size_t)in] != 'p' || getenv("SPN_NO_WIDE_REAL_LOADS")) return 1;
+    // measured (cfg2mr, 32-byte points): 256-bit loads of four reals run at 0.81 of HBM, 128-bit and 64-bit loads at
+    // 0.865 — unlike the complex inputs of cfg2 (64-byte points), where 256-bit loads win; so pairs by default.  The
+    // prefetch ring moves 16-byte units either way (cfg5r: +3.7 % over 8-byte cp.async).
+    const int vmax = getenv("SPN_REAL_VEC_MAX") ? atoi(getenv("SPN_REAL_VEC_MAX")) : 2;
+    const uint64_t sz = nodes[input_nodes[(size_t)in]].st.size();
+    if (vmax >= 4 && sz % 4 == 0 && jit_has_256bit_loads()) return 4;
+    return (vmax >= 2 && sz % 2 == 0) ? 2 : 1;
+  }
+  // one 16-byte (or 8-byte) slot of the shared-memory prefetch ring
+  struct RingUnit {
+    int kind;            // 0: complex component (16 B), 1: aligned pair of real components (16 B), 2: one real (8 B)
+    int in;
+    uint64_t flat;       // first component covered
+    int dst0, dst1;      // value ids receiving .x / .y (kind 0: dst0 is the double2; -1: not live)
+  };
+  std::vector<RingUnit> ring_units(const std::string& variant) const {
+    std::vector<RingUnit> u;
+    std::map<std::pair<int, uint64_t>, size_t> pair_of;
+    for (const Ins& i : prog.ins) {
+      if (i.op == I_LOADC) {
+        u.push_back({0, i.in, i.flat, i.dst, -1});
+      } else if (i.op == I_LOADR) {
+        if (real_vec(variant, i.in) >= 2) {
+          const uint64_t base = i.flat & ~1ull;
+          auto it = pair_of.find({i.in, base});
+          if (it == pair_of.end()) {
+            pair_of[{i.in, base}] = u.size();
+            u.push_back({1, i.in, base, -1, -1});
+            it = pair_of.find({i.in, base});
+          }
+          (i.flat & 1ull ? u[it->second].dst1 : u[it->second].dst0) = i.dst;
+        } else {
+          u.push_back({2, i.in, i.flat, i.dst, -1});
+        }
+      }
+    }
+    return u;
+  }
   PrefetchPlan plan_prefetch(const std::string& variant) const {
     PrefetchPlan pf;
     const char out_mode = variant[n_inputs];
@@ -621,7 +663,7 @@ struct spn_net {
     const double t_fp = (double)stats.n_fp / (64.0 * 148.0 * 1.9e9);
     const double t_hbm = (double)(stats.n_load_bytes + (out_mode == 'n' ? 0 : 16 * size_out)) / 6.5e12;
     if (stats.n_load_bytes == 0 || stats.n_load_bytes > 512 || t_fp <= 0.5 * t_hbm || getenv("SPN_NO_PREFETCH")) return pf;
-    for (auto& i : prog.ins) pf.n_loads += (i.op == I_LOADC || i.op == I_LOADR);
+    pf.n_loads = (uint32_t)ring_units(variant).size();
     pf.smem_bytes = (size_t)kRingDepth * pf.n_loads * (size_t)kBlock * 16;
     pf.mode = (pf.smem_bytes <= 96 * 1024 && !getenv("SPN_NO_RING")) ? PF_RING : PF_REGS;
     if (pf.mode != PF_RING) pf.smem_bytes = 0;
@@ -642,6 +684,8 @@ struct spn_net {
     o << "__device__ __forceinline__ double ld8(const double* p) { return __ldg(p); }\n";
     o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
          "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
+    o << "__device__ __forceinline__ void ld32r(const double* p, double& a, double& b, double& c, double& d) {\n"
+         "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a), \"=d\"(b), \"=d\"(c), \"=d\"(d) : \"l\"(p));\n}\n";
     o << "__device__ __forceinline__ void cp_async16(void* s, const double* g) {\n"
          "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 16;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g));\n}\n";
     o << "__device__ __forceinline__ void cp_async8(void* s, const double* g) {\n"
@@ -665,13 +709,52 @@ struct spn_net {
     std::map<std::pair<int, uint64_t>, int> load_dst;
     for (auto& i : prog.ins)
       if (i.op == I_LOADC) load_dst[{i.in, i.flat}] = i.dst;
-    std::set<std::pair<int, uint64_t>> done_pair;
+    std::map<std::pair<int, uint64_t>, int> rload_dst;
+    for (auto& i : prog.ins)
+      if (i.op == I_LOADR) rload_dst[{i.in, i.flat}] = i.dst;
+    std::set<std::pair<int, uint64_t>> done_pair, done_rgroup;
     // one load statement: `pre` is the variable prefix ("l" current point, "n" prefetched next point),
     // `decl` says whether the statement also declares its variables
     auto emit_load = [&](std::ostream& os, const Ins& i, const std::string& pv, const std::string& pre, bool decl) {
       const Node& n = nodes[input_nodes[(size_t)i.in]];
       const uint64_t sz = n.st.size();
       const char lay = variant[(size_t)i.in];
+      if (i.op == I_LOADR && lay == 'p' && real_vec(variant, i.in) >= 2) {
+        // sector-wide loads of real components: one 256-bit load per 32-byte sector holding >= 2 live components,
+        // else one 128-bit load per live aligned pair (dead lanes land in scratch registers: same sector, no traffic)
+        const int V = real_vec(variant, i.in);
+        auto dst_of = [&](uint64_t f) { auto it = rload_dst.find({i.in, f}); return it == rload_dst.end() ? -1 : it->second; };
+        const uint64_t b4 = i.flat & ~3ull, b2 = i.flat & ~1ull;
+        int live4 = 0;
+        for (uint64_t f = b4; f < b4 + 4; ++f) live4 += dst_of(f) >= 0;
+        if (V == 4 && live4 >= 2) {
+          if (done_rgroup.count({i.in, b4})) return;
+          done_rgroup.insert({i.in, b4});
+          std::string nm[4], scratch;
+          for (int k = 0; k < 4; ++k) {
+            const int d = dst_of(b4 + (uint64_t)k);
+            if (d >= 0) {
+              nm[k] = pre + std::to_string(d);
+              if (decl) os << "double " << nm[k] << "; ";
+            } else {
+              nm[k] = "z" + std::to_string(k);
+              scratch += (scratch.empty() ? "double " : ", ") + nm[k];
+            }
+          }
+          os << "{ " << (scratch.empty() ? std::string() : scratch + "; ") << "ld32r(in" << i.in << " + " << pv << " * " << sz << "ull + "
+             << b4 << "ull, " << nm[0] << ", " << nm[1] << ", " << nm[2] << ", " << nm[3] << "); }\n";
+          return;
+        }
+        if (dst_of(b2) >= 0 && dst_of(b2 + 1) >= 0) {
+          if (done_rgroup.count({i.in, b2})) return;
+          done_rgroup.insert({i.in, b2});
+          const std::string a = pre + std::to_string(dst_of(b2)), b = pre + std::to_string(dst_of(b2 + 1));
+          if (decl) os << "double " << a << ", " << b << "; ";
+          os << "{ const double2 t = ld16(in" << i.in << " + " << pv << " * " << sz << "ull + " << b2 << "ull); " << a << " = t.x; "
+             << b << " = t.y; }\n";
+          return;
+        }
+      }
       if (i.op == I_LOADR) {
         os << (decl ? "const double " : "") << pre << i.dst << " = ld8(in" << i.in;
         if (lay != 'c')
@@ -726,27 +809,39 @@ struct spn_net {
       o << "  ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x;\n  const ull stride = (ull)gridDim.x * " << kBlock << ";\n";
       // issue(pp, slot): this thread's loads of point pp -> ring slot
       o << "  auto issue = [&](ull pp, int slot) {\n";
-      uint32_t e = 0;
-      for (const Ins& i : prog.ins)
-        if (i.op == I_LOADC || i.op == I_LOADR) {
-          o << "    cp_async" << (i.op == I_LOADC ? 16 : 8) << "(&ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock
-            << " + threadIdx.x], " << load_addr(i, "pp") << ");\n";
-          ++e;
-        }
+      const std::vector<RingUnit> units = ring_units(variant);
+      auto unit_addr = [&](const RingUnit& u, const std::string& pv) {
+        const Node& n = nodes[input_nodes[(size_t)u.in]];
+        std::ostringstream a;
+        const int w = u.kind == 0 ? 2 : 1;
+        if (variant[(size_t)u.in] == 'c')
+          a << "in" << u.in << " + (" << u.flat << "ull * cs" << u.in << " + " << pv << ") * " << w;
+        else
+          a << "in" << u.in << " + (" << pv << " * " << n.st.size() << "ull + " << u.flat << "ull) * " << w;
+        return a.str();
+      };
+      for (size_t e = 0; e < units.size(); ++e)
+        o << "    cp_async" << (units[e].kind == 2 ? 8 : 16) << "(&ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock
+          << " + threadIdx.x], " << unit_addr(units[e], "pp") << ");\n";
       o << "  };\n";
       o << "  for (int d = 0; d < " << kRingDepth << "; ++d) {\n    if (p + d * stride < n_points) issue(p + d * stride, d);\n"
            "    asm volatile(\"cp.async.commit_group;\" ::);\n  }\n";
       o << "  for (int it = 0; p < n_points; p += stride, ++it) {\n    const int slot = it & " << (kRingDepth - 1) << ";\n";
       o << "    asm volatile(\"cp.async.wait_group " << (kRingDepth - 1) << ";\" ::: \"memory\");\n";
-      e = 0;
-      for (const Ins& i : prog.ins)
-        if (i.op == I_LOADC || i.op == I_LOADR) {
-          if (i.op == I_LOADC)
-            o << "    const double2 l" << i.dst << " = ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock << " + threadIdx.x];\n";
-          else
-            o << "    const double l" << i.dst << " = ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock << " + threadIdx.x].x;\n";
-          ++e;
+      for (size_t e = 0; e < units.size(); ++e) {
+        const RingUnit& u = units[e];
+        std::ostringstream slot_ref;
+        slot_ref << "ring[(slot * " << pf.n_loads << " + " << e << ") * " << kBlock << " + threadIdx.x]";
+        if (u.kind == 0) {
+          o << "    const double2 l" << u.dst0 << " = " << slot_ref.str() << ";\n";
+        } else if (u.kind == 2) {
+          o << "    const double l" << u.dst0 << " = " << slot_ref.str() << ".x;\n";
+        } else {
+          o << "    const double2 u" << e << " = " << slot_ref.str() << ";\n";
+          if (u.dst0 >= 0) o << "    const double l" << u.dst0 << " = u" << e << ".x;\n";
+          if (u.dst1 >= 0) o << "    const double l" << u.dst1 << " = u" << e << ".y;\n";
         }
+      }
     } else if (pf.mode == PF_REGS) {
       o << "  ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x;\n  const ull stride = (ull)gridDim.x * " << kBlock << ";\n";
       for (const Ins& i : prog.ins) {
@@ -761,6 +856,7 @@ struct spn_net {
           if (!t.str().empty()) o << "    " << t.str();
         }
       done_pair.clear();
+      done_rgroup.clear();
       o << "  }\n  for (; p < n_points; p += stride) {\n    const ull pn = p + stride;\n    if (pn < n_points) {\n";
       for (const Ins& i : prog.ins)
         if (i.op == I_LOADC || i.op == I_LOADR) {
