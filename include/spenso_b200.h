@@ -162,7 +162,11 @@ int spn_tensor_sparse_entries(const spn_tensor* t, uint64_t* flat, double* reim)
 /* a.contract(&b): contraction.rs:126-227.  Result storage: batched dense if either operand is
  * batched; else shared — Dense unless both are Sparse (contraction.rs:219-224). */
 int spn_tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out);
-/* element-wise: algebra/add_assign.rs, sub_assign.rs, neg.rs, scalar_mul.rs */
+/* element-wise: algebra/add_assign.rs, sub_assign.rs, neg.rs, scalar_mul.rs.
+ * `subtract` is a bit set: SPN_ADD_SUBTRACT = a - b; SPN_ADD_FALLIBLE = the semantics of add_fallible / sub_fallible
+ * (algebra/fallible_add.rs:105-135, fallible_sub.rs:112-150): a Sparse (+/-) Sparse result does not store values
+ * that are exactly zero (smart_set, tensors/data/sparse.rs:712-724), where `+=` keeps them as explicit zeros. */
+enum { SPN_ADD_SUBTRACT = 1, SPN_ADD_FALLIBLE = 2 };
 int spn_tensor_add(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, int subtract, spn_tensor** out);
 int spn_tensor_neg(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
 int spn_tensor_scalar_mul(spn_ctx* ctx, const spn_tensor* a, double re, double im, spn_tensor** out);

@@ -188,6 +188,9 @@ class Tensor {
     check(spn_tensor_conj(ctx_->raw(), raw(), &out));
     return Tensor(*ctx_, out);
   }
+  // FallibleAdd / FallibleSub (algebra/fallible_add.rs, fallible_sub.rs): Sparse (+/-) Sparse does not store exact zeros
+  Tensor add_fallible(const Tensor& o) const { return binary(o, SPN_ADD_FALLIBLE); }
+  Tensor sub_fallible(const Tensor& o) const { return binary(o, SPN_ADD_FALLIBLE | SPN_ADD_SUBTRACT); }
   const Context& context() const { return *ctx_; }
 
  private:

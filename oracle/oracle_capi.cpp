@@ -248,10 +248,15 @@ int orc_contract(void* a, void* b, void** out, int emulate_reference_pairing) {
   return 0;
   ORC_CATCH(ERR_OTHER)
 }
-int orc_add(void* a, void* b, void** out, int subtract) {
+// mode: bit 0 = subtract; bit 1 = FallibleAdd/FallibleSub semantics (fresh tensor, smart_set drops exact zeros)
+int orc_add(void* a, void* b, void** out, int mode) {
   ORC_TRY
+  if (mode & 2) {
+    *out = new Tensor(add_fallible(*(Tensor*)a, *(Tensor*)b, (mode & 1) != 0));
+    return 0;
+  }
   Tensor t = *(Tensor*)a;
-  add_assign(t, *(Tensor*)b, subtract != 0);
+  add_assign(t, *(Tensor*)b, (mode & 1) != 0);
   *out = new Tensor(std::move(t));
   return 0;
   ORC_CATCH(ERR_OTHER)

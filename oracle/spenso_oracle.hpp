@@ -1389,6 +1389,35 @@ inline void add_assign(Tensor& self, const Tensor& rhs, bool subtract = false) {
     }
   }
 }
+// FallibleAdd / FallibleSub (algebra/fallible_add.rs:17-135, fallible_sub.rs:19-150): the same sums, but the result is
+// a fresh tensor — Dense unless BOTH operands are Sparse — and Sparse (+/-) Sparse writes through smart_set
+// (tensors/data/sparse.rs:712-724): a value that is exactly zero is not stored (tests.rs:1108-1141 sparse_sub).
+// Operands here share one canonical slot order, so the reference's find_permutation is the identity.
+inline Tensor add_fallible(const Tensor& self, const Tensor& rhs, bool subtract = false) {
+  if (self.st.order() != rhs.st.order() || self.size() != rhs.size())
+    throw ContractionError(ERR_STRUCTURE, "add_fallible: structure mismatch");
+  if (!(self.sparse && rhs.sparse)) {
+    Tensor t = self;
+    add_assign(t, rhs, subtract);  // densifies a sparse receiver first, like the Dense outputs of :17-103
+    return t;
+  }
+  Tensor out = Tensor::sparse_empty(self.st);
+  auto smart_set = [&](size_t flat, C v) {
+    if (v.re == 0.0 && v.im == 0.0)
+      out.elems.erase(flat);
+    else
+      out.elems[flat] = v;
+  };
+  for (auto& kv : self.elems) {
+    auto it = rhs.elems.find(kv.first);
+    C v = kv.second;
+    if (it != rhs.elems.end()) subtract ? csub(v, it->second) : cadd(v, it->second);
+    smart_set(kv.first, v);
+  }
+  for (auto& kv : rhs.elems)
+    if (!self.elems.count(kv.first)) smart_set(kv.first, subtract ? cneg(kv.second) : kv.second);
+  return out;
+}
 inline Tensor neg(const Tensor& t) {
   Tensor o = t;
   for (auto& x : o.data) x = cneg(x);

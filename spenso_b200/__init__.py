@@ -260,6 +260,18 @@ class _Tensor:
         check(lib().spn_tensor_add(self.ctx.h, self.h, other.h, 1, C.byref(out)))
         return self._wrap(out)
 
+    def add_fallible(self, other: "_Tensor") -> "_Tensor":
+        """FallibleAdd (algebra/fallible_add.rs): like `+`, but Sparse + Sparse does not store exact zeros."""
+        out = C.c_void_p()
+        check(lib().spn_tensor_add(self.ctx.h, self.h, other.h, 2, C.byref(out)))
+        return self._wrap(out)
+
+    def sub_fallible(self, other: "_Tensor") -> "_Tensor":
+        """FallibleSub (algebra/fallible_sub.rs)."""
+        out = C.c_void_p()
+        check(lib().spn_tensor_add(self.ctx.h, self.h, other.h, 3, C.byref(out)))
+        return self._wrap(out)
+
     def __neg__(self):
         out = C.c_void_p()
         check(lib().spn_tensor_neg(self.ctx.h, self.h, C.byref(out)))

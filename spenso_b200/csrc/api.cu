@@ -382,7 +382,8 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
   }
 }
 
-void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out) {
+void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out,
+                        bool drop_zeros) {
   const bool binary = op == EW_ADD || op == EW_SUB;
   if (binary) {
     if (a->st.order() != b->st.order() || a->size() != b->size())
@@ -421,6 +422,8 @@ void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_ten
     for (auto& kv : a->entries) ent[kv.first] = host[kv.first];
     if (binary)
       for (auto& kv : b->entries) ent[kv.first] = host[kv.first];
+    if (drop_zeros)  // smart_set (tensors/data/sparse.rs:712-724): an exactly-zero value is not stored
+      for (auto it = ent.begin(); it != ent.end();) it = (it->second.x == 0.0 && it->second.y == 0.0) ? ent.erase(it) : std::next(it);
     *out = new_shared_sparse(ctx, a->st, ent);
   } else {
     *out = new_shared_dense(ctx, a->st, host.data());
@@ -642,7 +645,8 @@ int spn_tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, 
 }
 int spn_tensor_add(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, int subtract, spn_tensor** out) {
   API_TRY
-  tensor_elementwise(ctx, subtract ? EW_SUB : EW_ADD, a, b, make_double2(0, 0), out);
+  tensor_elementwise(ctx, (subtract & SPN_ADD_SUBTRACT) ? EW_SUB : EW_ADD, a, b, make_double2(0, 0), out,
+                     (subtract & SPN_ADD_FALLIBLE) != 0);
   return SPN_OK;
   API_CATCH
 }

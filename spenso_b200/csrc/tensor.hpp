@@ -132,6 +132,7 @@ void comm_exchange(spn_comm* c, const double2* partial, int n_blocks, double* in
 
 // the Contract trait: result in *out (new tensor)
 void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out);
-void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out);
+void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_tensor* b, double2 s, spn_tensor** out,
+                        bool drop_zeros = false);
 
 }  // namespace spn

@@ -300,9 +300,10 @@ class OTensor:
             raise OracleError(rc, lib().orc_last_error().decode())
         return OTensor(out.value)
 
-    def add(self, other, subtract=False):
+    def add(self, other, subtract=False, fallible=False):
+        """AddAssign / SubAssign (default) or FallibleAdd / FallibleSub (fallible=True: exact zeros not stored)."""
         out = C.c_void_p()
-        rc = lib().orc_add(self.h, other.h, C.byref(out), int(subtract))
+        rc = lib().orc_add(self.h, other.h, C.byref(out), int(subtract) | (2 if fallible else 0))
         if rc:
             raise OracleError(rc, lib().orc_last_error().decode())
         return OTensor(out.value)

@@ -431,3 +431,45 @@ def test_device_reference_seed_sweeps_equal_einsum(ctx, multi):
             assert (by_label(f.slots["aind"], arr, out) == want).all(), (s, ka, kb)
             done += 1
     assert done > 100
+
+
+# ---- tests.rs:1074-1141 sparse_addition / sparse_sub: operands given in different slot orders are added by index
+#      label, and an entry that cancels exactly is not stored ---------------------------------------------------------
+def _sparse_add_sub_cases(mk):
+    a = mk([("euc", 2, 2), ("euc", 2, 1)], {(1, 0): 1.0, (0, 1): 2.0})
+    b = mk([("euc", 2, 1), ("euc", 2, 2)], {(1, 0): 1.0, (0, 1): 2.0})
+    a2 = mk([("euc", 2, 2), ("euc", 2, 1)], {(1, 0): 1.0, (0, 1): 2.0})
+    b2 = mk([("euc", 2, 2), ("euc", 2, 1)], {(1, 0): 1.0, (0, 1): 3.0})
+    return a, b, a2, b2
+
+
+def _labelled_entries(t, shape=(2, 2)):
+    """{(index of aind 2, index of aind 1): value} of the stored entries"""
+    ainds = [int(x) for x in t.slots["aind"]]
+    out = {}
+    for flat, v in t.entries().items():
+        idx = np.unravel_index(flat, shape)
+        out[(int(idx[ainds.index(2)]), int(idx[ainds.index(1)]))] = v
+    return out
+
+
+def test_oracle_sparse_addition_and_sub_kats():
+    a, b, a2, b2 = _sparse_add_sub_cases(lambda sl, e: O.OTensor.sparse(oslots(sl), e))
+    f = a.add(b, fallible=True)
+    assert f.is_sparse and _labelled_entries(f) == {(0, 1): 3.0, (1, 0): 3.0}
+    g = a2.add(b2, subtract=True, fallible=True)                           # sub_fallible
+    assert g.is_sparse and _labelled_entries(g) == {(0, 1): -1.0}          # 1 - 1 cancels: not stored
+    h = a2.add(b2, subtract=True)                                          # `-=` (sub_assign.rs) keeps the explicit zero
+    assert h.is_sparse and _labelled_entries(h) == {(0, 1): -1.0, (1, 0): 0.0}
+
+
+@pytest.mark.gpu
+def test_device_sparse_addition_and_sub_kats(ctx):
+    import spenso_b200 as sp
+    a, b, a2, b2 = _sparse_add_sub_cases(lambda sl, e: sp.SparseTensor.from_entries(ctx, eslots(sl), e))
+    f = a.add_fallible(b)
+    assert f.is_sparse and _labelled_entries(f) == {(0, 1): 3.0, (1, 0): 3.0}
+    g = a2.sub_fallible(b2)
+    assert g.is_sparse and _labelled_entries(g) == {(0, 1): -1.0}
+    h = a2 - b2
+    assert h.is_sparse and _labelled_entries(h) == {(0, 1): -1.0, (1, 0): 0.0}
