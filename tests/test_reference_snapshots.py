@@ -473,3 +473,84 @@ def test_device_sparse_addition_and_sub_kats(ctx):
     assert g.is_sparse and _labelled_entries(g) == {(0, 1): -1.0}
     h = a2 - b2
     assert h.is_sparse and _labelled_entries(h) == {(0, 1): -1.0, (1, 0): 0.0}
+
+
+# ---- tests.rs:903-973 mixed_tensor_contraction, :1471-1510 transpose, :476-500 contract_with_rank_one_in_middle ---------
+IM = complex(1.5, 1.25)
+
+
+def _mixed_cases(sparse, dense):
+    """returns [(result tensor, label order of the reference's result, expected row-major data)]"""
+    sa = [("euc", 2, 2), ("euc", 2, 1)]
+    sb = [("euc", 2, 2), ("euc", 2, 4)]
+    a = sparse(sa, {(0, 0): 1.0, (1, 1): 2.0})                      # real data: f64 upgrades to (x, 0.0)
+    b = dense(sb, np.array([1, 2, 3, 4]) * IM)
+    f1 = b.contract(a)                                              # legacy result order: b's free (4), a's free (1)
+    a2 = sparse(sa, {(0, 0): 1.0 * IM, (1, 1): 2.0 * IM})
+    b2 = dense(sb, np.array([1.0, 2.0, 3.0, 4.0]))
+    f2 = a2.contract(b2)                                            # a's free (1), b's free (4)
+    return [(f1, [4, 1], np.array([1, 6, 2, 8]) * IM), (f2, [1, 4], np.array([1, 2, 6, 8]) * IM)]
+
+
+def _transpose_case(dense):
+    a = dense([("euc", 2, 1)], [1, 2])
+    b = dense([("euc", 2, 2)], [3, 4])
+    m_t = dense([("euc", 2, 1), ("euc", 2, 2)], [0, 1, 0, 0])
+    m_d = dense([("euc", 2, 2), ("euc", 2, 1)], [0, 0, 1, 0])      # the same matrix, data laid out transposed
+    return a.contract(m_t).contract(b), a.contract(m_d).contract(b)
+
+
+def _rank_one_in_middle_case():
+    s = 12
+    common = R.test_structure(3, s)
+    sa = R.test_structure(2, s + 1) + common                        # legacy merge without common slots appends
+    sb = R.test_structure(1, s + 2) + common
+    sha, shb = [d for _, d, _ in sa], [d for _, d, _ in sb]
+    ea = R.test_tensor(int(np.prod(sha)), s + 3, "i32", -1000, 1000)
+    eb = R.test_tensor(int(np.prod(shb)), s + 4, "i32", -1000, 1000)
+    L = {a: chr(ord("a") + k) for k, a in enumerate(sorted({x for _, _, x in sa + sb}))}
+    cl = [y for _, _, y in common]
+    free = [x for _, _, x in sb if x not in cl] + [x for _, _, x in sa if x not in cl]
+    expr = "".join(L[x] for _, _, x in sb) + "," + "".join(L[x] for _, _, x in sa) + "->" + "".join(L[x] for x in free)
+    # mink slots carry the metric sign on contraction: apply it to one operand before the plain einsum
+    B = dense_of(eb, shb).astype(np.int64)
+    for ax, (r, d, _) in enumerate(sb):
+        if r == "mink" and (r, d, sb[ax][2]) in common:
+            sign = np.ones(d, dtype=np.int64)
+            sign[1:] = -1
+            B = B * sign.reshape([-1 if k == ax else 1 for k in range(len(sb))])
+    want = np.einsum(expr, B, dense_of(ea, sha))
+    return sa, sha, ea, sb, shb, eb, free, want
+
+
+def test_oracle_mixed_transpose_rank_one_kats():
+    sparse = lambda sl, e: O.OTensor.sparse(oslots(sl), e)
+    dense = lambda sl, d: O.OTensor.dense(oslots(sl), d)
+    for f, order, want in _mixed_cases(sparse, dense):
+        assert not f.is_sparse                                      # Dense unless both operands are Sparse
+        assert (by_label(f.slots["aind"], f.to_dense(), order).reshape(-1) == want).all()
+    ft, fd = _transpose_case(dense)
+    assert ft.to_dense().reshape(-1)[0] == fd.to_dense().reshape(-1)[0] == 4
+    sa, sha, ea, sb, shb, eb, free, want = _rank_one_in_middle_case()
+    f = sparse(sb, unflatten(eb, shb)).contract(sparse(sa, unflatten(ea, sha)))
+    g = dense(sb, dense_of(eb, shb)).contract(dense(sa, dense_of(ea, sha)))
+    assert (f.to_dense() == g.to_dense()).all()                     # the reference's assertion
+    assert (by_label(g.slots["aind"], g.to_dense(), free) == want).all()
+
+
+@pytest.mark.gpu
+def test_device_mixed_transpose_rank_one_kats(ctx):
+    import spenso_b200 as sp
+    sparse = lambda sl, e: sp.SparseTensor.from_entries(ctx, eslots(sl), e)
+    dense = lambda sl, d: sp.DenseTensor.from_data(ctx, eslots(sl), d)
+    arr = lambda t: t.to_numpy().reshape([int(d) for d in t.slots["dim"]])
+    for f, order, want in _mixed_cases(sparse, dense):
+        assert not f.is_sparse
+        assert (by_label(f.slots["aind"], arr(f), order).reshape(-1) == want).all()
+    ft, fd = _transpose_case(dense)
+    assert ft.to_numpy().reshape(-1)[0] == fd.to_numpy().reshape(-1)[0] == 4
+    sa, sha, ea, sb, shb, eb, free, want = _rank_one_in_middle_case()
+    f = sparse(sb, unflatten(eb, shb)).contract(sparse(sa, unflatten(ea, sha)))
+    g = dense(sb, dense_of(eb, shb)).contract(dense(sa, dense_of(ea, sha)))
+    assert (arr(f) == arr(g)).all()
+    assert (by_label(g.slots["aind"], arr(g), free) == want).all()
