@@ -139,7 +139,7 @@ void jit_load_impl(JitKernel& k, int block) {
   cuda_check(cudaLibraryGetKernel(&k.kernel, k.lib, k.name.c_str()), "cudaLibraryGetKernel");
   cudaFuncAttributes attr{};
   if (cudaFuncGetAttributes(&attr, (const void*)k.kernel) == cudaSuccess) k.num_regs = attr.numRegs;
-  if (k.smem_bytes > 48 * 1024) {
+  if (k.smem_bytes >= 48 * 1024) {
     int dev = 0;
     cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
     cuda_check(cudaKernelSetAttributeForDevice(k.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem_bytes, dev),

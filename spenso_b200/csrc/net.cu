@@ -141,7 +141,10 @@ struct spn_net {
   // stepwise
   std::vector<std::unique_ptr<spn_tensor>> const_tensors;  // per value id (leaf consts), lazily uploaded
 
-  int kBlock = getenv("SPN_BLOCK") ? atoi(getenv("SPN_BLOCK")) : 128;  // threads per CTA of the fused kernels
+  // threads per CTA of the fused kernels.  256: measured never slower than 128 (cfg2, cfg2mr: equal) and faster for the
+  // ring-prefetch kernels (cfg5 +3..7 %, cfg5r +10 %): one 256-thread CTA per SM amortises the ring fill and the
+  // per-CTA fold of the Monte-Carlo partials over twice the points (profiles/r01_knob_sweep_*.txt)
+  int kBlock = getenv("SPN_BLOCK") ? atoi(getenv("SPN_BLOCK")) : 256;
   int kMinBlocks = getenv("SPN_MIN_BLOCKS") ? atoi(getenv("SPN_MIN_BLOCKS")) : 0;
   static constexpr uint64_t kMaxFusedElems = 1u << 16;
 
@@ -665,7 +668,8 @@ struct spn_net {
     if (stats.n_load_bytes == 0 || stats.n_load_bytes > 512 || t_fp <= 0.5 * t_hbm || getenv("SPN_NO_PREFETCH")) return pf;
     pf.n_loads = (uint32_t)ring_units(variant).size();
     pf.smem_bytes = (size_t)kRingDepth * pf.n_loads * (size_t)kBlock * 16;
-    pf.mode = (pf.smem_bytes <= 96 * 1024 && !getenv("SPN_NO_RING")) ? PF_RING : PF_REGS;
+    const size_t ring_max = (size_t)(getenv("SPN_RING_MAX_KB") ? atoi(getenv("SPN_RING_MAX_KB")) : 200) * 1024;
+    pf.mode = (pf.smem_bytes <= ring_max && !getenv("SPN_NO_RING")) ? PF_RING : PF_REGS;
     if (pf.mode != PF_RING) pf.smem_bytes = 0;
     return pf;
   }
