@@ -405,6 +405,25 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = n * KE * world / (e2e_ms * 1e-3)
+    # what the link can do: the same pinned input buffers copied to the device with plain async copies (no kernel, no
+    # D2H), best of 3 — the ceiling of any host-fed number on this box
+    link_gbs = None
+    try:
+        dsts = [torch.empty(p.numel(), dtype=torch.float64, device=dev) for p in host_sets[0]]
+        best = 1e30
+        for _ in range(3):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            c0.record(stream)
+            for d, p in zip(dsts, host_sets[0]):
+                d.copy_(p.view(-1), non_blocking=True)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, c0.elapsed_time(c1))
+        link_gbs = h2d / (best * 1e-3) / 1e9
+        del dsts
+    except Exception:
+        link_gbs = None
 
     # ---- roofline of the dominant kernel (the fused network kernel) ----------------------------------------------------
     peak, peak_src = measured_peaks()
@@ -447,7 +466,8 @@ def run_b200(args):
                                          if (want_sum and world > 1) else "")},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": KE, "ms_per_step": e2e_ms / KE, "api": "spn_net_execute_host (chunked H2D/kernel/D2H pipeline)",
-                    "chunk_points": e2e_chunk},
+                    "chunk_points": e2e_chunk, "h2d_gbs_in_e2e": h2d * KE / (e2e_ms * 1e-3) / 1e9,
+                    "h2d_gbs_plain_copy": link_gbs},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

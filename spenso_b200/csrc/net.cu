@@ -611,7 +611,7 @@ struct spn_net {
   //   REGS  register double buffering of the next point (when the ring would not fit in shared memory)
   //   NONE  bandwidth-bound networks at high occupancy (cfg2): loads are placed lazily next to their first use
   enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2 };
-  static constexpr int kRingDepth = 4;
+  const int kRingDepth = (getenv("SPN_RING_DEPTH") && (atoi(getenv("SPN_RING_DEPTH")) == 2 || atoi(getenv("SPN_RING_DEPTH")) == 8)) ? atoi(getenv("SPN_RING_DEPTH")) : 4;  // power of two
   struct PrefetchPlan {
     int mode = PF_NONE;
     uint32_t n_loads = 0;
