@@ -610,6 +610,9 @@ struct spn_net {
   //         (conflict-free [slot][load][thread] layout; no block barrier: a thread only reads what it wrote)
   //   REGS  register double buffering of the next point (when the ring would not fit in shared memory)
   //   NONE  bandwidth-bound networks at high occupancy (cfg2): loads are placed lazily next to their first use
+  // measured: L1::no_allocate on the once-read streaming loads is +1 % (cfg2 point-major), +3 % (cfg2mr), +7-8 %
+  // (component-major cfg2, cfg3) over plain ld.global.nc; evict_first is equivalent
+  static constexpr const char* kDefaultLoadHint = ".L1::no_allocate";
   enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2 };
   const int kRingDepth = (getenv("SPN_RING_DEPTH") && (atoi(getenv("SPN_RING_DEPTH")) == 2 || atoi(getenv("SPN_RING_DEPTH")) == 8)) ? atoi(getenv("SPN_RING_DEPTH")) : 4;  // power of two
   struct PrefetchPlan {
@@ -684,12 +687,21 @@ struct spn_net {
     o << "// inputs: " << n_inputs << ", result components: " << size_out << ", fp64 instr/point: " << stats.n_fp
       << ", input bytes/point: " << stats.n_load_bytes << "\n";
     o << "typedef unsigned long long ull;\n";
-    o << "__device__ __forceinline__ double2 ld16(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }\n";
-    o << "__device__ __forceinline__ double ld8(const double* p) { return __ldg(p); }\n";
+    // streaming loads: every input byte is read exactly once, so the L1 policy is a free parameter (SPN_LD_HINT:
+    // "" plain, "na" = L1::no_allocate, "ef" = L1::evict_first)
+    const char* hint_env = getenv("SPN_LD_HINT");
+    const std::string hint = !hint_env ? std::string(kDefaultLoadHint)
+                             : std::string(hint_env) == "na" ? ".L1::no_allocate"
+                             : std::string(hint_env) == "ef" ? ".L1::evict_first" : "";
+    const std::string ldnc = "ld.global.nc" + hint;
+    o << "__device__ __forceinline__ double2 ld16(const double* p) {\n  double2 v;\n"
+         "  asm(\"" << ldnc << ".v2.f64 {%0,%1}, [%2];\" : \"=d\"(v.x), \"=d\"(v.y) : \"l\"(p));\n  return v;\n}\n";
+    o << "__device__ __forceinline__ double ld8(const double* p) {\n  double v;\n"
+         "  asm(\"" << ldnc << ".f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p));\n  return v;\n}\n";
     o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
-         "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
+         "  asm(\"" << ldnc << ".v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
     o << "__device__ __forceinline__ void ld32r(const double* p, double& a, double& b, double& c, double& d) {\n"
-         "  asm(\"ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a), \"=d\"(b), \"=d\"(c), \"=d\"(d) : \"l\"(p));\n}\n";
+         "  asm(\"" << ldnc << ".v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a), \"=d\"(b), \"=d\"(c), \"=d\"(d) : \"l\"(p));\n}\n";
     o << "__device__ __forceinline__ void cp_async16(void* s, const double* g) {\n"
          "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 16;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g));\n}\n";
     o << "__device__ __forceinline__ void cp_async8(void* s, const double* g) {\n"
@@ -788,6 +800,17 @@ struct spn_net {
     };
     const PrefetchPlan pf = plan_prefetch(variant);
     const bool prefetch = pf.mode != PF_NONE;
+    // inputs read with warp-coalesced loads (see below): point-major, 32-byte aligned, exactly 4 complex components per
+    // point, all of them live, direct-load kernels only
+    std::vector<int> coal;
+    if (!prefetch && jit_has_256bit_loads() && kBlock % 32 == 0 && !getenv("SPN_NO_COALESCE"))
+      for (uint32_t in = 0; in < n_inputs; ++in) {
+        const Node& n = nodes[input_nodes[(size_t)in]];
+        if (variant[(size_t)in] != 'p' || n.st.size() != 4) continue;
+        bool all = true;
+        for (uint64_t f = 0; f < 4; ++f) all = all && load_dst.count({(int)in, f});
+        if (all) coal.push_back((int)in);
+      }
     for (const Ins& i : prog.ins) {
       if (i.op == I_LOADC) {
         name[(size_t)i.dst] = "l" + std::to_string(i.dst) + ".x";
@@ -869,6 +892,36 @@ struct spn_net {
           if (!t.str().empty()) o << "      " << t.str();
         }
       o << "    }\n";
+    } else if (!coal.empty()) {
+      // Warp-coalesced point-major loads.  A 64-byte tensor per point (4 complex components: spinors, momenta) read
+      // thread = point makes every 256-bit load instruction touch 32 half-used 64-byte segments.  Instead the warp
+      // reads its 32 points' 2 KB slab with two fully contiguous 1 KB instructions; lane t then holds sector (t & 1) of
+      // points t/2 (first instruction) and 16 + t/2 (second).  Even lanes evaluate point t/2, odd lanes point
+      // 16 + t/2: each keeps one sector and swaps the other with its neighbour (one shfl.xor round of 4 doubles).
+      o << "  const unsigned lane = threadIdx.x & 31u;\n";
+      o << "  for (ull p0 = (ull)blockIdx.x * " << kBlock << " + threadIdx.x; p0 - lane < n_points; p0 += (ull)gridDim.x * "
+        << kBlock << ") {\n";
+      o << "    const ull pw = p0 - lane;\n    const bool full = pw + 32 <= n_points;   // warp-uniform\n";
+      o << "    if (!full && p0 >= n_points) continue;\n";
+      o << "    const ull p = full ? pw + (lane >> 1) + ((lane & 1u) << 4) : p0;\n";
+      for (int in : coal) {
+        const int d0 = load_dst[{in, 0}], d1 = load_dst[{in, 1}], d2 = load_dst[{in, 2}], d3 = load_dst[{in, 3}];
+        o << "    double2 l" << d0 << ", l" << d1 << ", l" << d2 << ", l" << d3 << ";\n";
+        o << "    if (full) {\n";
+        o << "      double2 a0, b0, a1, b1;\n";
+        o << "      ld32(in" << in << " + (pw * 4ull + (ull)lane * 2ull) * 2, a0, b0);\n";
+        o << "      ld32(in" << in << " + (pw * 4ull + 64ull + (ull)lane * 2ull) * 2, a1, b1);\n";
+        o << "      const bool odd = lane & 1u;\n";
+        o << "      double2 sa = odd ? a0 : a1, sb = odd ? b0 : b1;   // the sector my neighbour evaluates\n";
+        o << "      sa.x = __shfl_xor_sync(0xffffffffu, sa.x, 1); sa.y = __shfl_xor_sync(0xffffffffu, sa.y, 1);\n";
+        o << "      sb.x = __shfl_xor_sync(0xffffffffu, sb.x, 1); sb.y = __shfl_xor_sync(0xffffffffu, sb.y, 1);\n";
+        o << "      l" << d0 << " = odd ? sa : a0; l" << d1 << " = odd ? sb : b0;\n";
+        o << "      l" << d2 << " = odd ? a1 : sa; l" << d3 << " = odd ? b1 : sb;\n";
+        o << "    } else {\n";
+        o << "      ld32(in" << in << " + (p * 4ull + 0ull) * 2, l" << d0 << ", l" << d1 << ");\n";
+        o << "      ld32(in" << in << " + (p * 4ull + 2ull) * 2, l" << d2 << ", l" << d3 << ");\n";
+        o << "    }\n";
+      }
     } else {
       o << "  for (ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << kBlock
         << ") {\n";
@@ -878,6 +931,7 @@ struct spn_net {
         case I_LOADC:
         case I_LOADR: {
           if (prefetch) break;
+          if (std::find(coal.begin(), coal.end(), i.in) != coal.end()) break;  // loaded at the top of the iteration
           std::ostringstream t;
           emit_load(t, i, "p", "l", true);
           if (!t.str().empty()) o << "    " << t.str();
@@ -973,6 +1027,8 @@ struct spn_net {
     k->name = nm;
     k->source = gen_source(variant, k->name);
     k->smem_bytes = plan_prefetch(variant).smem_bytes;
+    // occupancy experiments: SPN_PAD_SMEM_KB adds unused dynamic shared memory (fewer CTAs per SM, grid follows)
+    if (const char* e = getenv("SPN_PAD_SMEM_KB")) k->smem_bytes += (size_t)atoi(e) * 1024;
     jit_compile(*k);
     JitKernel& ref = *k;
     variants[variant].k = std::move(k);

@@ -149,7 +149,7 @@ def test_network_compile_plan_only():
     # cfg2: reads exactly the four spinors, 256-bit loads, no constant survives as a multiply
     net = workloads.build_engine(workloads.eemumu(), None)
     assert net.input_bytes_per_point == 256
-    assert "ld.global.nc.v4.f64" in net.cuda_source
+    assert "ld.global.nc.L1::no_allocate.v4.f64" in net.cuda_source   # 256-bit streaming loads
     assert net.fp64_instr_per_point <= 160
     # cfg3: the gather touches only the components facing non-zeros of T (17) and f (54)
     net = workloads.build_engine(workloads.su3_colour(), None)
