@@ -1,6 +1,8 @@
 """Multi-GPU plumbing: phase-space points are independent, so the batch is cut into contiguous blocks,
 one per rank; nothing is exchanged while the network is evaluated.  The only collective
-of the path is the final all-reduce of the Monte-Carlo partial sums (2*|out| doubles)."""
+of the path is the all-reduce of the Monte-Carlo partial sums (2*|out| doubles): connect_peers() gives the
+library's own exchange over NVLink peer memory (csrc/comm.cu), allreduce_partial_sums() the torch.distributed
+one (NCCL on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
 from typing import Tuple
