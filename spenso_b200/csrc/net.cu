@@ -697,7 +697,9 @@ struct spn_net {
     o << "__device__ __forceinline__ double2 ld16(const double* p) {\n  double2 v;\n"
          "  asm(\"" << ldnc << ".v2.f64 {%0,%1}, [%2];\" : \"=d\"(v.x), \"=d\"(v.y) : \"l\"(p));\n  return v;\n}\n";
     o << "__device__ __forceinline__ double ld8(const double* p) {\n  double v;\n"
-         "  asm(\"" << ldnc << ".f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p));\n  return v;\n}\n";
+         "  asm(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p));\n  return v;\n}\n";   // 8-byte loads share their sector with later loads of the same thread: keep it in L1 (measured: no_allocate here costs 19 %)
+    o << "__device__ __forceinline__ double ld8s(const double* p) {\n  double v;\n"
+         "  asm(\"" << ldnc << ".f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p));\n  return v;\n}\n";   // component-major: the warp consumes whole sectors
     o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
          "  asm(\"" << ldnc << ".v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
     o << "__device__ __forceinline__ void ld32r(const double* p, double& a, double& b, double& c, double& d) {\n"
@@ -772,7 +774,7 @@ struct spn_net {
         }
       }
       if (i.op == I_LOADR) {
-        os << (decl ? "const double " : "") << pre << i.dst << " = ld8(in" << i.in;
+        os << (decl ? "const double " : "") << pre << i.dst << " = " << (lay == 'c' ? "ld8s" : "ld8") << "(in" << i.in;
         if (lay != 'c')
           os << " + " << pv << " * " << sz << "ull + " << i.flat << "ull);\n";
         else
