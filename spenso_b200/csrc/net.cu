@@ -698,6 +698,8 @@ struct spn_net {
          "  asm(\"" << ldnc << ".v2.f64 {%0,%1}, [%2];\" : \"=d\"(v.x), \"=d\"(v.y) : \"l\"(p));\n  return v;\n}\n";
     o << "__device__ __forceinline__ double ld8(const double* p) {\n  double v;\n"
          "  asm(\"ld.global.nc.f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p));\n  return v;\n}\n";   // 8-byte loads share their sector with later loads of the same thread: keep it in L1 (measured: no_allocate here costs 19 %)
+    o << "__device__ __forceinline__ double2 ld16c(const double* p) {\n  double2 v;\n"
+         "  asm(\"ld.global.nc.v2.f64 {%0,%1}, [%2];\" : \"=d\"(v.x), \"=d\"(v.y) : \"l\"(p));\n  return v;\n}\n";   // half-sector loads of a thread that reads the other half next: L1-cached
     o << "__device__ __forceinline__ double ld8s(const double* p) {\n  double v;\n"
          "  asm(\"" << ldnc << ".f64 %0, [%1];\" : \"=d\"(v) : \"l\"(p));\n  return v;\n}\n";   // component-major: the warp consumes whole sectors
     o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
@@ -796,8 +798,10 @@ struct spn_net {
         if (decl) os << "double2 " << a << ", " << b << "; ";
         os << "ld32(in" << i.in << " + (" << pv << " * " << sz << "ull + " << base << "ull) * 2, " << a << ", " << b << ");\n";
       } else {
-        os << (decl ? "const double2 " : "") << ln << " = ld16(in" << i.in << " + (" << pv << " * " << sz << "ull + " << i.flat
-           << "ull) * 2);\n";
+        // unpaired 16-byte load: streaming when its sector partner is dead, L1-cached when the partner is loaded separately
+        const bool partner_live = load_dst.count({i.in, i.flat ^ 1ull}) != 0;
+        os << (decl ? "const double2 " : "") << ln << " = " << (partner_live ? "ld16c" : "ld16") << "(in" << i.in << " + (" << pv
+           << " * " << sz << "ull + " << i.flat << "ull) * 2);\n";
       }
     };
     const PrefetchPlan pf = plan_prefetch(variant);
