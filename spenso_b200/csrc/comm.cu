@@ -145,6 +145,13 @@ struct spn_comm {
   int* status_dev = nullptr;
   bool connected = false;
   double timeout_s = 10.0;
+  // frees what this rank owns (the caller has unmapped the peers first); also the cleanup of a failed create
+  ~spn_comm() {
+    if (peer_dev) cudaFree(peer_dev);
+    if (local) cudaFree(local);
+    if (status_host) cudaFreeHost(status_host);
+    cudaGetLastError();
+  }
 };
 
 namespace spn {
@@ -278,10 +285,6 @@ int spn_comm_disconnect(spn_comm* c) {
 void spn_comm_destroy(spn_comm* c) {
   if (!c) return;
   spn_comm_disconnect(c);
-  if (c->peer_dev) cudaFree(c->peer_dev);
-  if (c->local) cudaFree(c->local);
-  if (c->status_host) cudaFreeHost(c->status_host);
-  cudaGetLastError();
   delete c;
 }
 
