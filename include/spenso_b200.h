@@ -286,7 +286,10 @@ int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t 
  *   host channel (torch.distributed / MPI / a file); 3. spn_comm_connect with the world's handles in rank order.
  * Calls are collective: every rank must issue the same sequence.  They are enqueued on the context's stream
  * and are CUDA-graph capturable.  A peer that never arrives trips a device-side timeout (default 10 s,
- * SPN_COMM_TIMEOUT_S) instead of hanging the GPU: spn_comm_status returns 1 + its rank. */
+ * SPN_COMM_TIMEOUT_S) instead of hanging the GPU: the sums of that exchange are poisoned with NaN, spn_comm_status
+ * returns 1 + the rank that was missing, spn_ctx_synchronize and every later exchange on the communicator fail with
+ * SPN_ERR_OTHER.  The status is sticky (the ranks' epochs are out of step): destroy and re-create the communicator
+ * on every rank. */
 typedef struct spn_comm spn_comm;
 #define SPN_COMM_HANDLE_BYTES 64
 int spn_comm_create(spn_ctx* ctx, int rank, int world, uint32_t max_f64, spn_comm** out);

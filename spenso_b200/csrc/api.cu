@@ -53,8 +53,8 @@ KTables build_k_tables(const spn_contract_plan& p, bool emulate_reference_pairin
       ob += (long long)ib[d] * (long long)p.k_stride_b[ord_b[d]];
       if (p.k_metric[ord_a[d]] && ia[d] > 0) neg = !neg;  // the sign comes from self's (a's) metric iterator
     }
-    t.off_a[k] = (int)oa;
-    t.off_b[k] = (int)ob;
+    t.off_a[k] = oa;
+    t.off_b[k] = ob;
     t.sign[k] = neg ? 1 : 0;
     for (uint32_t d = nd; d-- > 0;) {
       if (++ia[d] < p.k_dim[ord_a[d]]) break;
@@ -221,7 +221,7 @@ static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KT
   };
   enumerate(true, row_a, out_row);
   enumerate(false, col_b, out_col);
-  std::vector<long long> k_a(kt.off_a.begin(), kt.off_a.end()), k_b(kt.off_b.begin(), kt.off_b.end());
+  const std::vector<long long>&k_a = kt.off_a, &k_b = kt.off_b;
   std::vector<double> ks;
   bool any_sign = false;
   for (auto s : kt.sign) any_sign |= s != 0;
@@ -297,7 +297,8 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
     const auto& d_out = a_sp ? plan.out_stride_b : plan.out_stride_a;
     const auto& ks = a_sp ? kt.off_a : kt.off_b;
     const auto& kd = a_sp ? kt.off_b : kt.off_a;
-    std::vector<int> row_ptr(plan.size_out + 1, 0), col;
+    std::vector<int> row_ptr(plan.size_out + 1, 0);
+    std::vector<long long> col;  // offsets into the dense operand: 64-bit (tensors beyond 2^31 elements)
     std::vector<double2> val;
     std::vector<unsigned char> sgn;
     std::vector<uint32_t> idx(plan.order_out, 0);
@@ -310,17 +311,19 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
       for (size_t k = 0; k < ks.size(); ++k) {
         auto it = sp->entries.find(offs + (uint64_t)ks[k]);
         if (it == sp->entries.end()) continue;
-        col.push_back((int)(offd + (uint64_t)kd[k]));
+        col.push_back((long long)(offd + (uint64_t)kd[k]));
         val.push_back(it->second);
         sgn.push_back(kt.sign[k]);
       }
+      if (col.size() > (size_t)0x7fffffff) throw Error(SPN_ERR_INVALID, "sparse operand: more than 2^31 stored products");
       row_ptr[o + 1] = (int)col.size();
       for (uint32_t r = plan.order_out; r-- > 0;) {
         if (++idx[r] < plan.out_dim[r]) break;
         idx[r] = 0;
       }
     }
-    DevArray<int> d_row(row_ptr, ctx->stream), d_col(col, ctx->stream);
+    DevArray<int> d_row(row_ptr, ctx->stream);
+    DevArray<long long> d_col(col, ctx->stream);
     DevArray<double2> d_val(val, ctx->stream);
     DevArray<unsigned char> d_sgn(sgn, ctx->stream);
     cuda_check(launch_contract_csr(dn->operand(), res->output(), d_row.p, d_col.p, d_val.p, d_sgn.p,
@@ -334,7 +337,7 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
   } else {
     // K1/K5/K7 (and sparse x sparse over the densified shared copies; the structural/zero
     // filter of the sparse result is applied below)
-    DevArray<int> d_ka(kt.off_a, ctx->stream), d_kb(kt.off_b, ctx->stream);
+    DevArray<long long> d_ka(kt.off_a, ctx->stream), d_kb(kt.off_b, ctx->stream);
     DevArray<unsigned char> d_ks(kt.sign, ctx->stream);
     cuda_check(launch_contract_dense(map, a->operand(), b->operand(), res->output(), d_ka.p, d_kb.p, d_ks.p,
                                      kt.off_a.size(), n_points, point_fastest, ctx->stream),
@@ -508,6 +511,10 @@ int spn_ctx_set_reference_quirks(spn_ctx* ctx, int emulate_interleaved_pairing) 
 int spn_ctx_synchronize(spn_ctx* ctx) {
   API_TRY
   cuda_check(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
+  for (const int* st : ctx->comm_status)
+    if (const int v = *reinterpret_cast<const volatile int*>(st))
+      throw Error(SPN_ERR_OTHER, "Monte-Carlo sum exchange timed out waiting for rank " + std::to_string(v - 1) +
+                                     " (the sum was poisoned with NaN; re-create the communicator)");
   return SPN_OK;
   API_CATCH
 }
@@ -673,7 +680,12 @@ int spn_tensor_trace(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const spn_
   API_TRY
   // `slots` is the index list of `a` as the caller sees it, with one repeated (slot, dual) pair:
   // traces(), structure.rs:462-485.  The data of `a` is row major over `slots`.
-  if (n != a->st.order() && !(n > 0)) throw Error(SPN_ERR_INVALID, "trace: slot count mismatch");
+  if (n == 0 || n != a->st.order()) throw Error(SPN_ERR_INVALID, "trace: slot count differs from the tensor's order");
+  {
+    uint64_t vol = 1;
+    for (uint32_t i = 0; i < n; ++i) vol *= slots[i].dim;
+    if (vol != a->size()) throw Error(SPN_ERR_DIMENSION, "trace: the slot dimensions do not multiply to the tensor's size");
+  }
   int p0 = -1, p1 = -1;
   for (uint32_t i = 0; i < n && p0 < 0; ++i)
     for (uint32_t j = i + 1; j < n; ++j)

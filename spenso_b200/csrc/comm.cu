@@ -18,6 +18,7 @@
 // overwritten its previous content (epoch e-1) is no longer needed anywhere.  The epoch counter lives in
 // device memory and is advanced by the kernel itself, so launches are CUDA-graph capturable.
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "tensor.hpp"
@@ -116,9 +117,10 @@ mc_sum_exchange_kernel(const double2* __restrict__ partial, int n_blocks, double
         }
         if (pending && (++spins & 255u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
           atomicExch_system(status, 1 + (int)(r0 + (unsigned)__ffs((int)pending) - 1));  // a peer that never arrived
+          // poison the sum: a missing contribution must not look like a plausible Monte-Carlo estimate
 #pragma unroll
           for (unsigned k = 0; k < kRanksPerPass; ++k)
-            if (pending >> k & 1u) v[k] = 0.0;
+            if (pending >> k & 1u) v[k] = __longlong_as_double(0x7ff8000000000000LL);
           pending = 0;
         }
       }
@@ -147,6 +149,12 @@ struct spn_comm {
   double timeout_s = 10.0;
   // frees what this rank owns (the caller has unmapped the peers first); also the cleanup of a failed create
   ~spn_comm() {
+    if (ctx && status_host)
+      for (auto it = ctx->comm_status.begin(); it != ctx->comm_status.end(); ++it)
+        if (*it == status_host) {
+          ctx->comm_status.erase(it);
+          break;
+        }
     if (peer_dev) cudaFree(peer_dev);
     if (local) cudaFree(local);
     if (status_host) cudaFreeHost(status_host);
@@ -158,6 +166,10 @@ namespace spn {
 // used by net.cu: fold the per-CTA partials and exchange in one launch
 void comm_exchange(spn_comm* c, const double2* partial, int n_blocks, double* inout_device, uint32_t n_f64) {
   if (!c->connected) throw Error(SPN_ERR_INVALID, "spn_comm: not connected (call spn_comm_connect on every rank)");
+  if (const int st = *reinterpret_cast<volatile int*>(c->status_host))
+    throw Error(SPN_ERR_OTHER, "spn_comm: an earlier exchange timed out waiting for rank " + std::to_string(st - 1) +
+                                   "; its result was poisoned with NaN and the epochs are out of step — destroy and re-create "
+                                   "the communicator on every rank");
   if (n_f64 == 0) return;
   if (n_f64 > c->cap) throw Error(SPN_ERR_INVALID, "spn_comm: message larger than the mailbox capacity");
   if (partial && (n_f64 & 1)) throw Error(SPN_ERR_INVALID, "spn_comm: partials are complex (even number of doubles)");
@@ -209,6 +221,7 @@ int spn_comm_create(spn_ctx* ctx, int rank, int world, uint32_t max_f64, spn_com
   cuda_check(cudaMemset(c->local, 0, bytes), "cudaMemset (mailbox)");
   cuda_check(cudaHostAlloc((void**)&c->status_host, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc (comm status)");
   *c->status_host = 0;
+  ctx->comm_status.push_back(c->status_host);   // spn_ctx_synchronize reports a timed-out exchange
   cuda_check(cudaHostGetDevicePointer((void**)&c->status_dev, c->status_host, 0), "cudaHostGetDevicePointer");
   cuda_check(cudaMalloc((void**)&c->peer_dev, sizeof(char*) * (size_t)world), "cudaMalloc (peer table)");
   cuda_check(cudaDeviceSynchronize(), "mailbox initialisation");

@@ -131,6 +131,12 @@ class JParser {
       p_ += 4;
       return v;
     }
+    if (!std::string(p_, 3).compare("NaN")) {   // written by jlit() for a NaN constant
+      p_ += 3;
+      v.kind = JVal::Num;
+      v.s = "nan";
+      return v;
+    }
     const char* q = p_;
     while (*q == '-' || *q == '+' || *q == '.' || *q == 'e' || *q == 'E' || (*q >= '0' && *q <= '9')) ++q;
     if (q == p_) fail("value expected");

@@ -64,7 +64,7 @@ __device__ __forceinline__ void split_index(ull t, ull size_out, ull n_points, b
 template <bool AC, bool BC>
 __global__ void __launch_bounds__(256)
 contract_dense_kernel(const __grid_constant__ DevOutMap map, DevOperand a, DevOperand b, DevOut out,
-                      const int* __restrict__ koff_a, const int* __restrict__ koff_b,
+                      const long long* __restrict__ koff_a, const long long* __restrict__ koff_b,
                       const unsigned char* __restrict__ ksign, ull n_k, ull n_points, int point_fastest) {
   const ull total = map.size_out * n_points;
   for (ull t = (ull)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (ull)gridDim.x * blockDim.x) {
@@ -80,8 +80,8 @@ contract_dense_kernel(const __grid_constant__ DevOutMap map, DevOperand a, DevOp
     }
     double2 acc = make_double2(0.0, 0.0);
     for (ull k = 0; k < n_k; ++k) {
-      double2 x = load_elem<AC>(a.ptr, offa + (ll)__ldg(koff_a + k) * a.fs);
-      double2 y = load_elem<BC>(b.ptr, offb + (ll)__ldg(koff_b + k) * b.fs);
+      double2 x = load_elem<AC>(a.ptr, offa + __ldg(koff_a + k) * a.fs);
+      double2 y = load_elem<BC>(b.ptr, offb + __ldg(koff_b + k) * b.fs);
       cacc_rn(acc, cmul_rn(x, y), __ldg(ksign + k) != 0);
     }
     store_elem(out.ptr, (ll)p * out.ps + (ll)o * out.fs, acc, out.is_complex);
@@ -91,19 +91,19 @@ contract_dense_kernel(const __grid_constant__ DevOutMap map, DevOperand a, DevOp
 // ---- K2: dense (per point) x sparse (shared, CSR staged in shared memory) ---------------------
 template <bool DC, bool STAGE>
 __global__ void __launch_bounds__(256)
-contract_csr_kernel(DevOperand dense, DevOut out, const int* __restrict__ row_ptr, const int* __restrict__ col_off,
+contract_csr_kernel(DevOperand dense, DevOut out, const int* __restrict__ row_ptr, const long long* __restrict__ col_off,
                     const double2* __restrict__ val, const unsigned char* __restrict__ sign, int dense_is_first,
                     ull size_out, ull nnz, ull n_points, int point_fastest) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int* s_row = row_ptr;
-  const int* s_col = col_off;
+  const ll* s_col = col_off;
   const double2* s_val = val;
   const unsigned char* s_sign = sign;
   if (STAGE) {
     double2* sv = reinterpret_cast<double2*>(smem);
-    int* sr = reinterpret_cast<int*>(sv + nnz);
-    int* sc = sr + (size_out + 1);
-    unsigned char* ss = reinterpret_cast<unsigned char*>(sc + nnz);
+    ll* sc = reinterpret_cast<ll*>(sv + nnz);
+    int* sr = reinterpret_cast<int*>(sc + nnz);
+    unsigned char* ss = reinterpret_cast<unsigned char*>(sr + (size_out + 1));
     for (ull i = threadIdx.x; i < nnz; i += blockDim.x) {
       sv[i] = __ldg(val + i);
       sc[i] = __ldg(col_off + i);
@@ -124,7 +124,7 @@ contract_csr_kernel(DevOperand dense, DevOut out, const int* __restrict__ row_pt
     double2 acc = make_double2(0.0, 0.0);
     const int e1 = s_row[o + 1];
     for (int e = s_row[o]; e < e1; ++e) {
-      double2 x = load_elem<DC>(dense.ptr, base + (ll)s_col[e] * dense.fs);
+      double2 x = load_elem<DC>(dense.ptr, base + s_col[e] * dense.fs);
       double2 v = s_val[e];
       double2 pr = dense_is_first ? cmul_rn(x, v) : cmul_rn(v, x);
       cacc_rn(acc, pr, s_sign[e] != 0);
@@ -276,8 +276,8 @@ unsigned grid_for(ull total, int block, int blocks_per_sm) {
 
 }  // namespace
 
-cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand b, DevOut out, const int* koff_a,
-                                  const int* koff_b, const unsigned char* ksign, ull n_k, ull n_points,
+cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand b, DevOut out, const long long* koff_a,
+                                  const long long* koff_b, const unsigned char* ksign, ull n_k, ull n_points,
                                   bool point_fastest, cudaStream_t stream) {
   const ull total = map.size_out * n_points;
   if (total == 0) return cudaSuccess;
@@ -297,13 +297,13 @@ cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand
   return cudaGetLastError();
 }
 
-cudaError_t launch_contract_csr(DevOperand dense, DevOut out, const int* row_ptr, const int* col_off,
+cudaError_t launch_contract_csr(DevOperand dense, DevOut out, const int* row_ptr, const long long* col_off,
                                 const double2* val, const unsigned char* sign, int dense_is_first, ull size_out,
                                 ull nnz, ull n_points, bool point_fastest, cudaStream_t stream) {
   const ull total = size_out * n_points;
   if (total == 0) return cudaSuccess;
   unsigned grid = grid_for(total, 256, 8);
-  size_t smem = nnz * (sizeof(double2) + sizeof(int) + 1) + (size_out + 1) * sizeof(int) + 16;
+  size_t smem = nnz * (sizeof(double2) + sizeof(ll) + 1) + (size_out + 1) * sizeof(int) + 16;
   const bool stage = smem <= 40 * 1024;
 #define SPN_LAUNCH_CSR(DC, ST)                                                                              \
   contract_csr_kernel<DC, ST><<<grid, 256, (ST) ? smem : 0, stream>>>(dense, out, row_ptr, col_off, val, sign, \

@@ -35,14 +35,14 @@ struct DevOutMap {
 // multicontract.rs:25-78, exteriorproduct.rs.  koff_a/koff_b/ksign: device tables of the
 // contracted loop in the reference's enumeration order (n_k entries).
 cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand b, DevOut out,
-                                  const int* koff_a, const int* koff_b, const unsigned char* ksign,
+                                  const long long* koff_a, const long long* koff_b, const unsigned char* ksign,
                                   unsigned long long n_k, unsigned long long n_points, bool point_fastest,
                                   cudaStream_t stream);
 
 // K2 (dense(per point) x sparse(shared)): singlecontract.rs:78-196, multicontract.rs:80-200.
 // CSR over result elements: row o holds (offset into the dense operand, value, sign) for every
 // stored entry of the sparse fibre, in ascending fibre position.
-cudaError_t launch_contract_csr(DevOperand dense, DevOut out, const int* row_ptr, const int* col_off,
+cudaError_t launch_contract_csr(DevOperand dense, DevOut out, const int* row_ptr, const long long* col_off,
                                 const double2* val, const unsigned char* sign, int dense_is_first,
                                 unsigned long long size_out, unsigned long long nnz, unsigned long long n_points,
                                 bool point_fastest, cudaStream_t stream);

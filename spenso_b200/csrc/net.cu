@@ -707,9 +707,9 @@ struct spn_net {
     o << "__device__ __forceinline__ void ld32r(const double* p, double& a, double& b, double& c, double& d) {\n"
          "  asm(\"" << ldnc << ".v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a), \"=d\"(b), \"=d\"(c), \"=d\"(d) : \"l\"(p));\n}\n";
     o << "__device__ __forceinline__ void cp_async16(void* s, const double* g) {\n"
-         "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 16;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g));\n}\n";
+         "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 16;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g) : \"memory\");\n}\n";
     o << "__device__ __forceinline__ void cp_async8(void* s, const double* g) {\n"
-         "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 8;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g));\n}\n";
+         "  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 8;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g) : \"memory\");\n}\n";
     o << "extern \"C\" __global__ void __launch_bounds__(" << kBlock << (kMinBlocks ? ", " + std::to_string(kMinBlocks) : std::string()) << ") " << kname << "(";
     for (uint32_t k = 0; k < n_inputs; ++k) o << "const double* __restrict__ in" << k << ", ull cs" << k << ", ";
     o << "double* __restrict__ out, ull ocs, double2* __restrict__ block_sums, ull n_points) {\n";
@@ -858,7 +858,7 @@ struct spn_net {
           << " + threadIdx.x], " << unit_addr(units[e], "pp") << ");\n";
       o << "  };\n";
       o << "  for (int d = 0; d < " << kRingDepth << "; ++d) {\n    if (p + d * stride < n_points) issue(p + d * stride, d);\n"
-           "    asm volatile(\"cp.async.commit_group;\" ::);\n  }\n";
+           "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n  }\n";
       o << "  for (int it = 0; p < n_points; p += stride, ++it) {\n    const int slot = it & " << (kRingDepth - 1) << ";\n";
       o << "    asm volatile(\"cp.async.wait_group " << (kRingDepth - 1) << ";\" ::: \"memory\");\n";
       for (size_t e = 0; e < units.size(); ++e) {
@@ -1003,7 +1003,7 @@ struct spn_net {
         if (i.op == I_LOADC || i.op == I_LOADR) o << "    l" << i.dst << " = n" << i.dst << ";\n";
     if (pf.mode == PF_RING)  // refill the slot just consumed with the point kRingDepth iterations ahead
       o << "    if (p + " << kRingDepth << " * stride < n_points) issue(p + " << kRingDepth << " * stride, slot);\n"
-           "    asm volatile(\"cp.async.commit_group;\" ::);\n";
+           "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
     o << "  }\n";
     if (want_sum) {
       // per-block partial of the Monte-Carlo sum: fixed shuffle tree + fixed order over warps
@@ -1186,6 +1186,8 @@ void run_stepwise(spn_net* net, const spn_tensor* const* inputs, spn_tensor* out
                "reduce_points_kernel");
     ctx->launches += 2;
     cudaFreeAsync(partial, ctx->stream);
+    // with a communicator attached sum_out is the sum over ALL ranks, whatever the execution mode
+    if (net->comm) comm_exchange(net->comm, nullptr, 0, sum_out, (uint32_t)(2 * res->size()));
   }
   // intermediates are freed when `owned` goes out of scope; the stream is ordered, cudaFree syncs
 }
@@ -1422,19 +1424,19 @@ const char* spn_net_to_json(spn_net* net) {
       o << ",\"params\":[";
       for (size_t k = 0; k < n.fn_params.size(); ++k) o << (k ? "," : "") << "[" << n.fn_params[k].first << "," << n.fn_params[k].second << "]";
       o << "],\"consts\":[";
-      for (size_t k = 0; k < n.fn_consts.size(); ++k) o << (k ? "," : "") << "[" << lit(n.fn_consts[k].x) << "," << lit(n.fn_consts[k].y) << "]";
+      for (size_t k = 0; k < n.fn_consts.size(); ++k) o << (k ? "," : "") << "[" << jlit(n.fn_consts[k].x) << "," << jlit(n.fn_consts[k].y) << "]";
       o << "],\"code\":[";
       for (size_t k = 0; k < n.fn_raw_code.size(); ++k) o << (k ? "," : "") << n.fn_raw_code[k];
       o << "]}";
     } else if (n.kind == LEAF_CONST && n.is_scalar_leaf) {
-      o << "{\"kind\":\"scalar\",\"re\":" << lit(n.dense[0].x) << ",\"im\":" << lit(n.dense[0].y) << "}";
+      o << "{\"kind\":\"scalar\",\"re\":" << jlit(n.dense[0].x) << ",\"im\":" << jlit(n.dense[0].y) << "}";
     } else if (n.kind == LEAF_CONST) {
       o << "{\"kind\":\"tensor\",\"sparse\":" << (n.sparse ? "true" : "false") << ",\"slots\":";
       json_slots(o, n.st.slots);
       o << ",\"entries\":[";
       bool first = true;
       auto put = [&](uint64_t f, double2 v) {
-        o << (first ? "" : ",") << "[" << f << "," << lit(v.x) << "," << lit(v.y) << "]";
+        o << (first ? "" : ",") << "[" << f << "," << jlit(v.x) << "," << jlit(v.y) << "]";
         first = false;
       };
       if (n.sparse)
@@ -1843,7 +1845,12 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   jit_load(k, net->kBlock);
 
   if (n_points == 0) {
-    if (sum_out_device) cuda_check(cudaMemsetAsync(sum_out_device, 0, size_out * 16, ctx->stream), "memset");
+    // an empty shard (world > n_points) still takes part in the exchange: its contribution is zero, and a rank that
+    // skipped the collective would stall its peers and fall one epoch behind for good
+    if (sum_out_device) {
+      cuda_check(cudaMemsetAsync(sum_out_device, 0, size_out * 16, ctx->stream), "memset");
+      if (net->comm) comm_exchange(net->comm, nullptr, 0, sum_out_device, (uint32_t)(2 * size_out));
+    }
     return SPN_OK;
   }
   const uint64_t need = (n_points + net->kBlock - 1) / net->kBlock;

@@ -21,6 +21,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -329,12 +330,27 @@ struct Program {
   }
 };
 
+// a double as a CUDA C literal that round-trips exactly; non-finite values have no literal form and are spelled
+// through their bit pattern
 inline std::string lit(double v) {
   char buf[64];
+  if (!std::isfinite(v)) {
+    unsigned long long bits;
+    static_assert(sizeof bits == sizeof v, "double is 64 bits");
+    std::memcpy(&bits, &v, sizeof bits);
+    std::snprintf(buf, sizeof buf, "__longlong_as_double(0x%016llxLL)", bits);
+    return buf;
+  }
   std::snprintf(buf, sizeof buf, "%.17g", v);
   std::string s = buf;
-  if (s.find_first_of(".en") == std::string::npos) s += ".0";  // "inf"/"nan" contain 'n'
+  if (s.find_first_of(".e") == std::string::npos) s += ".0";
   return s;
+}
+// the same for the JSON plan format: +-1e999 reads back as +-infinity with any strtod, NaN as the bare word
+inline std::string jlit(double v) {
+  if (std::isnan(v)) return "NaN";
+  if (std::isinf(v)) return v > 0 ? "1e999" : "-1e999";
+  return lit(v);
 }
 
 }  // namespace spn

@@ -26,6 +26,9 @@ struct spn_ctx {
   bool emulate_reference_pairing = false;  // SURVEY K-note 3, see build_k_tables
   // specialised pairwise kernels (pairwise_jit.cu), keyed by a hash of (plan, storage, dtype, layout)
   std::map<uint64_t, std::shared_ptr<spn::JitKernel>> pair_kernels;
+  // sticky status words (pinned host memory) of the communicators created on this context (comm.cu): non-zero after
+  // an exchange timed out; checked by spn_ctx_synchronize
+  std::vector<const int*> comm_status;
 };
 
 struct spn_tensor {
@@ -112,7 +115,7 @@ inline bool trace_enabled() {
 
 // host-side helpers shared by the pairwise API and the network compiler
 struct KTables {
-  std::vector<int> off_a, off_b;
+  std::vector<long long> off_a, off_b;  // element offsets: 64-bit, a tensor may hold more than 2^31 elements
   std::vector<unsigned char> sign;
 };
 KTables build_k_tables(const spn_contract_plan& p, bool emulate_reference_pairing = false);

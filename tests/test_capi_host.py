@@ -282,3 +282,22 @@ def test_merge_missed_match_is_restated_literally():
         om, p = O.merge(x, y), sp.plan_contract(x, y)
         assert om["common_a"].sum() == 1 and p.n_common == 1 and p.order_out == 1     # match found
         assert _plan_fields(p, len(x), len(y))["slots"].tobytes() == om["slots"].tobytes()
+
+
+def test_non_finite_constants_compile_and_round_trip():
+    """A non-finite constant has no C literal: the generated kernel spells it through its bit pattern (NVRTC
+    compiles it), and the JSON plan format carries it as 1e999 / NaN."""
+    net = sp.Network(None)
+    x = net.batched([sp.Bispinor.new_slot(4, 1)])
+    net.set_root(net.product(net.scalar(complex(float("inf"), 0.0)), x))
+    text = net.to_json()
+    assert "1e999" in text and "inf" not in text
+    back = sp.Network.from_json(None, text)
+    assert back.to_json() == text
+    net.compile(sp.FUSED)                      # NVRTC runs here: "inf" in the source would fail to compile
+    assert "__longlong_as_double(0x7ff0000000000000LL)" in net.cuda_source
+    nan = sp.Network(None)
+    y = nan.batched([sp.Bispinor.new_slot(4, 1)])
+    nan.set_root(nan.sum(nan.product(nan.scalar(complex(0.0, float("nan"))), y), y))
+    assert "NaN" in nan.to_json()
+    assert sp.Network.from_json(None, nan.to_json()).to_json() == nan.to_json()

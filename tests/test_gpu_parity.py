@@ -1006,3 +1006,18 @@ def test_special_values_follow_ieee_like_the_reference(ctx):
                     assert (np.isnan(g) == np.isnan(w)).all()
                     ok = ~np.isnan(w)
                     assert (g[ok].view(np.uint64) == w[ok].view(np.uint64)).all()      # incl. the sign of zeros and infinities
+
+
+def test_trace_rejects_a_slot_list_that_is_not_the_tensors(ctx):
+    """spn_tensor_trace computes strides from the caller's slot list: a list of another order or volume would make
+    the kernel read out of bounds, so it is refused (Invalid / DimensionError)."""
+    m = lambda a: sp.Minkowski.new_slot(4, a)
+    t = sp.BatchTensor.from_numpy(ctx, [m(1), m(2), sp.Bispinor.new_slot(4, 3)], np.ones((3, 4, 4, 4)))
+    with pytest.raises(sp.SpensoError) as e:
+        t.trace([m(1), m(1)])                                   # order 2 for an order-3 tensor
+    assert e.value.code == 7
+    with pytest.raises(sp.SpensoError) as e:
+        t.trace([m(1), m(1), sp.Bispinor.new_slot(8, 3)])       # right order, wrong volume
+    assert e.value.code == 3
+    with pytest.raises(sp.SpensoError):
+        t.trace([])

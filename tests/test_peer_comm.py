@@ -66,6 +66,7 @@ def test_world_of_one_fold_and_exchange_matches_plain_sum():
     g = torch.cuda.CUDAGraph()
     st = torch.cuda.Stream()
     ctx.set_stream(st.cuda_stream)
+    st.wait_stream(torch.cuda.current_stream())
     s2 = torch.zeros_like(s1)
     with torch.cuda.graph(g, stream=st):
         for _ in range(3):
@@ -74,6 +75,27 @@ def test_world_of_one_fold_and_exchange_matches_plain_sum():
         g.replay()
     torch.cuda.synchronize()
     assert torch.equal(s0, s2) and comm.status == 0
+    # an empty point range still runs the exchange (a rank whose shard is empty must not skip the collective)
+    net.set_comm(comm)
+    s3 = torch.full((2 * size,), 3.0, dtype=torch.float64, device="cuda:0")
+    launches = ctx.launch_count
+    net.execute(ins, None, sum_out_ptr=s3.data_ptr(), first_point=n)
+    assert ctx.launch_count - launches == 1          # the exchange kernel alone
+    ctx.synchronize()
+    assert float(s3.abs().max()) == 0.0 and comm.status == 0
+    # stepwise execution honours the communicator too
+    step = workloads.build_engine(spec, ctx, sp.STEPWISE)
+    s4 = torch.zeros_like(s0)
+    step.set_comm(comm)
+    launches = ctx.launch_count
+    step.execute(ins, None, sum_out_ptr=s4.data_ptr())
+    ctx.synchronize()
+    assert float((s4 - s0).abs().max()) <= 1e-12 * float(s0.abs().max()) and comm.status == 0
+    step.set_comm(None)
+    s5 = torch.zeros_like(s0)
+    l1 = ctx.launch_count
+    step.execute(ins, None, sum_out_ptr=s5.data_ptr())
+    assert (ctx.launch_count - l1) + 1 == l1 - launches      # the attached communicator added exactly one launch
     net.set_comm(None)
     comm.close()
 
@@ -150,6 +172,38 @@ def _worker(rank, world, port, q):
         scale = float(ref.abs().max())
         ok &= float((total - ref).abs().max()) <= 1e-12 * scale
         ok &= comm.status == 0
+        # (3) more ranks than points: the ranks with an EMPTY shard still go through spn_net_execute (an empty point
+        # range) and must take part in the exchange — fused and stepwise
+        for mode in (sp.FUSED, sp.STEPWISE):
+            netm = workloads.build_engine(spec, ctx, mode)
+            netm.set_comm(comm)
+            n_few = world - 1                       # the last rank owns nothing
+            lo, m = shard_range(n_few, rank, world)
+            ins = []
+            for sl, a in zip([nd[1] for nd in spec.nodes if nd[0] == "batched"], arrs):
+                t = sp.BatchTensor.empty(ctx, sl, max(m, 1))
+                if m:
+                    t.upload(a[lo:lo + m])
+                ins.append(t)
+            out = torch.full((2 * size,), 7.0, dtype=torch.float64, device=dev)
+            if mode == sp.FUSED or m:
+                netm.execute(ins, None, sum_out_ptr=out.data_ptr(), first_point=0 if m else 1)
+            else:       # stepwise runs whole tensors: an empty shard contributes zeros through the plain exchange
+                out.zero_()
+                comm.allreduce_sum(out.data_ptr(), 2 * size)
+            torch.cuda.synchronize()
+            netm.set_comm(None)
+            one = workloads.build_engine(spec, ctx, sp.FUSED)
+            ins1 = []
+            for sl, a in zip([nd[1] for nd in spec.nodes if nd[0] == "batched"], arrs):
+                t = sp.BatchTensor.empty(ctx, sl, n_few)
+                t.upload(a[:n_few])
+                ins1.append(t)
+            want = torch.zeros(2 * size, dtype=torch.float64, device=dev)
+            one.execute(ins1, None, sum_out_ptr=want.data_ptr())
+            torch.cuda.synchronize()
+            ok &= float((out - want).abs().max()) <= 1e-12 * max(float(want.abs().max()), 1e-300)
+            ok &= comm.status == 0
         net.set_comm(None)
         comm.close(dist.barrier)
         dist.destroy_process_group()
