@@ -67,8 +67,14 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    build_oracle()
-    L = C.CDLL(LIB_PATH)
+    # SPN_ORACLE_LIB: another build of the same sources (bench.py's cpu_baseline legs build one with -march=native
+    # on the box they run on; the committed recipe is portable because the .so travels to a box with another CPU)
+    override = os.environ.get("SPN_ORACLE_LIB")
+    if override and os.path.exists(override):
+        L = C.CDLL(override)
+    else:
+        build_oracle()
+        L = C.CDLL(LIB_PATH)
     vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double
     L.orc_last_error.restype = C.c_char_p
     L.orc_tensor_dense.restype = vp
