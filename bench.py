@@ -396,7 +396,7 @@ def device_inputs(job, spec, wl, n, layout, seed):
 
 def kernel_name_of(net, key):
     try:
-        m = re.search(r"__global__ void[^(]*?(spn_fused_net_[0-9a-f]+_[a-z]+)\s*\(", net.prepare_variant(key))
+        m = re.search(r"\b(spn_fused_net_[0-9a-f]{8}_[a-z]+)\s*\(", net.prepare_variant(key))
         return m.group(1) if m else None
     except Exception:
         return None
@@ -604,7 +604,7 @@ def measure_network(job, args, wl, n, layout_name="point", K=20, W=3, exec_mode=
             nthr = os.cpu_count() or 1
             fn = lambda m: make_inputs(spec, wl, m, 1234)
             rate, sample, secs = oracle_rate(spec, fn, nthr, args.cpu_seconds)
-            rate1, sample1, secs1 = oracle_rate(spec, fn, 1, min(args.cpu_seconds / 2, 6.0))
+            rate1, sample1, secs1 = oracle_rate(spec, fn, 1, min(args.cpu_seconds / 3, 4.0))
             entry["cpu_baseline"] = {
                 "value": rate, "unit": UNIT, "cores": nthr, "kind": "port", "cpu_model": cpu_model(), "build": build,
                 "value_1core": rate1,

@@ -96,6 +96,13 @@ int spn_structure_canonicalize(const spn_slot* in, uint32_t n, spn_slot* out, in
  * a and b must be canonically ordered. */
 int spn_plan_contract(const spn_slot* a, uint32_t na, const spn_slot* b, uint32_t nb, spn_contract_plan* out);
 
+/* Inspection (host only, no device): the CUDA source of the kernel specialised for a.contract(b) of two BATCHED
+ * tensors with these canonical structures (physics-sized tensors; compiled with NVRTC on the way, so code-generation
+ * errors surface here).  Empty string: the contraction takes a generic kernel.  NULL: error.  The string is owned by
+ * the library and valid until the next call on this thread. */
+const char* spn_plan_contract_cuda_source(const spn_slot* a, uint32_t na, int dtype_a, int layout_a, const spn_slot* b,
+                                          uint32_t nb, int dtype_b, int layout_b);
+
 /* ---- context --------------------------------------------------------------------- */
 typedef struct spn_ctx spn_ctx;
 int spn_ctx_create(int device, spn_ctx** out);
@@ -115,6 +122,10 @@ int spn_ctx_set_reference_quirks(spn_ctx* ctx, int emulate_interleaved_pairing);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t spn_ctx_launch_count(const spn_ctx* ctx);
 int spn_ctx_sm_count(const spn_ctx* ctx);
+/* spn_tensor_contract keeps everything it derives from a pair of structures (merge plan, enumeration tables, device
+ * tables, kernel choice) in a per-context cache — the reference re-derives it on every call (contraction.rs:126-207).
+ * Counters of that cache (any pointer may be NULL). */
+int spn_ctx_plan_cache_stats(const spn_ctx* ctx, uint64_t* hits, uint64_t* misses, uint64_t* entries);
 
 /* ---- tensors (S1) ---------------------------------------------------------------- */
 enum { SPN_F64 = 0, SPN_C64 = 1 };

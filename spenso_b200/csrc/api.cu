@@ -1,6 +1,7 @@
 // C ABI (include/spenso_b200.h): context, device tensors and the pairwise ops
 // (Contract / add / sub / neg / scalar_mul / conj / trace / reduce).  Every compute entry point
 // launches the sm_100a kernels of kernels.cu; there is no host execution path.
+#include <atomic>
 #include <cstring>
 #include <memory>
 
@@ -113,7 +114,9 @@ spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, in
   return t.release();
 }
 
+static std::atomic<uint64_t> g_next_uid{1};
 static void upload_shared(spn_tensor* t) {
+  t->uid = g_next_uid.fetch_add(1);
   t->dptr = dev_alloc(t->host_dense.size() * sizeof(double2));
   t->owns = true;
   cuda_check(cudaMemcpyAsync(t->dptr, t->host_dense.data(), t->host_dense.size() * sizeof(double2),
@@ -146,17 +149,21 @@ spn_tensor* new_shared_sparse(spn_ctx* ctx, const Structure& st, const std::map<
   return t.release();
 }
 
+// a device table that lives as long as the plan-cache entry that owns it
 template <class T>
-struct DevArray {
+struct DevTable {
   T* p = nullptr;
-  cudaStream_t s;
-  DevArray(const std::vector<T>& h, cudaStream_t stream) : s(stream) {
-    cuda_check(cudaMallocAsync((void**)&p, (h.size() ? h.size() : 1) * sizeof(T), s), "cudaMallocAsync");
-    if (!h.empty())
-      cuda_check(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s), "table upload");
+  size_t n = 0;
+  DevTable() = default;
+  DevTable(const DevTable&) = delete;
+  DevTable& operator=(const DevTable&) = delete;
+  void upload(const std::vector<T>& h) {
+    n = h.size();
+    cuda_check(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T)), "cudaMalloc (plan table)");
+    if (n) cuda_check(cudaMemcpy(p, h.data(), n * sizeof(T), cudaMemcpyHostToDevice), "plan table upload");
   }
-  ~DevArray() {
-    if (p) cudaFreeAsync(p, s);
+  ~DevTable() {
+    if (p) cudaFree(p);
   }
 };
 
@@ -178,22 +185,51 @@ static GemmShape gemm_shape(const spn_contract_plan& p) {
   for (uint32_t r = 0; r < p.order_out; ++r) (p.partition[r] ? g.M : g.N) *= p.out_dim[r];
   return g;
 }
-static bool zgemm_applicable(const spn_contract_plan& p, const spn_tensor* a, const spn_tensor* b, const spn_tensor* res,
-                             uint64_t n_points, const KTables& kt) {
+static bool zgemm_applicable(const spn_contract_plan& p, const spn_tensor* a, const spn_tensor* b, int res_dtype,
+                             long long res_fs, uint64_t n_points, const KTables& kt) {
   if (getenv("SPN_NO_ZGEMM")) return false;
   if (a->sparse() || b->sparse()) return false;
   // complex x complex -> ZGEMM, real x real -> DGEMM; mixed operands take the streaming kernel
-  if (a->dtype != b->dtype || a->dtype != res->dtype) return false;
+  if (a->dtype != b->dtype || a->dtype != res_dtype) return false;
   if (p.n_partition != p.order_out || p.n_common == 0) return false;
   // element stride 1 within a point (point-major batched, or shared)
-  if (a->operand().fs != 1 || b->operand().fs != 1 || res->operand().fs != 1) return false;
+  if (a->operand().fs != 1 || b->operand().fs != 1 || res_fs != 1) return false;
   if (n_points > 65535) return false;
   GemmShape g = gemm_shape(p);
   return g.M >= 32 && g.N >= 32 && kt.off_a.size() >= 8 && (double)g.M * (double)g.N * (double)kt.off_a.size() >= 65536.0;
 }
-static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KTables& kt, const spn_tensor* a,
-                              const spn_tensor* b, spn_tensor* res, uint64_t n_points) {
-  GemmShape g = gemm_shape(p);
+
+enum ContractPath { PATH_JIT = 0, PATH_CSR = 1, PATH_GEMM = 2, PATH_DENSE = 3 };
+
+// Everything tensor_contract derives from (structure of a, structure of b, what the operands are): computed once per
+// distinct pair and kept in spn_ctx::contract_cache.
+struct ContractEntry {
+  spn_contract_plan plan{};
+  Structure rs;
+  KTables kt;
+  DevOutMap map{};
+  int path = PATH_DENSE;
+  PairJit jit;
+  // PATH_DENSE: contracted-loop tables, and (size_out <= 2^22) the operand base offsets of every result element
+  DevTable<long long> d_ka, d_kb, d_toa, d_tob;
+  DevTable<unsigned char> d_ks;
+  bool has_out_tables = false;
+  // PATH_CSR: CSR over result elements of the shared sparse operand
+  DevTable<int> d_row;
+  DevTable<long long> d_col;
+  DevTable<double2> d_val;
+  DevTable<unsigned char> d_sgn;
+  size_t nnz = 0;
+  // PATH_GEMM: row / column / k gather tables
+  GemmShape g;
+  DevTable<long long> d_row_a, d_out_row, d_col_b, d_out_col;
+  DevTable<double> d_ksign;
+  bool any_sign = false, vec_tables = false;
+};
+
+static void build_gemm_tables(ContractEntry& e) {
+  const spn_contract_plan& p = e.plan;
+  e.g = gemm_shape(p);
   std::vector<uint64_t> ostride(p.order_out, 1);
   for (uint32_t r = p.order_out; r-- > 1;) ostride[r - 1] = ostride[r] * p.out_dim[r];
   std::vector<long long> row_a, out_row, col_b, out_col;
@@ -201,7 +237,7 @@ static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KT
     std::vector<uint32_t> dims;
     for (uint32_t r = 0; r < p.order_out; ++r)
       if ((p.partition[r] != 0) == from_a) dims.push_back(r);
-    const long long n = from_a ? g.M : g.N;
+    const long long n = from_a ? e.g.M : e.g.N;
     src.resize((size_t)n);
     dst.resize((size_t)n);
     std::vector<uint32_t> idx(dims.size(), 0);
@@ -221,133 +257,233 @@ static void launch_zgemm_path(spn_ctx* ctx, const spn_contract_plan& p, const KT
   };
   enumerate(true, row_a, out_row);
   enumerate(false, col_b, out_col);
-  const std::vector<long long>&k_a = kt.off_a, &k_b = kt.off_b;
+  const std::vector<long long>&k_a = e.kt.off_a, &k_b = e.kt.off_b;
   std::vector<double> ks;
-  bool any_sign = false;
-  for (auto s : kt.sign) any_sign |= s != 0;
-  if (any_sign)
-    for (auto s : kt.sign) ks.push_back(s ? -1.0 : 1.0);
-  DevArray<long long> d_row_a(row_a, ctx->stream), d_out_row(out_row, ctx->stream), d_col_b(col_b, ctx->stream),
-      d_out_col(out_col, ctx->stream), d_k_a(k_a, ctx->stream), d_k_b(k_b, ctx->stream);
-  DevArray<double> d_ks(ks, ctx->stream);
-  if (a->dtype == SPN_C64)
-    cuda_check(launch_contract_zgemm(static_cast<const double2*>(a->dptr), static_cast<const double2*>(b->dptr),
-                                     static_cast<double2*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
-                                     d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
-                                     a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
-               "contract_zgemm_kernel");
-  else {
-    // 16-byte gathers when both tables are pairwise contiguous, every base offset is even and everything is aligned
-    bool vec = g.N % 2 == 0 && k_a.size() % 2 == 0 && a->operand().ps % 2 == 0 && b->operand().ps % 2 == 0 &&
-               (uintptr_t)a->dptr % 16 == 0 && (uintptr_t)b->dptr % 16 == 0;
-    for (size_t k = 0; vec && k + 1 < k_a.size(); k += 2) vec = k_a[k] % 2 == 0 && k_a[k + 1] == k_a[k] + 1;
-    for (size_t c = 0; vec && c + 1 < col_b.size(); c += 2) vec = col_b[c] % 2 == 0 && col_b[c + 1] == col_b[c] + 1;
-    for (size_t r = 0; vec && r < row_a.size(); ++r) vec = row_a[r] % 2 == 0;
-    for (size_t k = 0; vec && k < k_b.size(); ++k) vec = k_b[k] % 2 == 0;
-    cuda_check(launch_contract_dgemm(static_cast<const double*>(a->dptr), static_cast<const double*>(b->dptr),
-                                     static_cast<double*>(res->dptr), d_row_a.p, d_k_a.p, d_col_b.p, d_k_b.p, d_out_row.p,
-                                     d_out_col.p, any_sign ? d_ks.p : nullptr, g.M, g.N, (long long)k_a.size(),
-                                     a->operand().ps, b->operand().ps, res->operand().ps, n_points, vec, ctx->stream),
-               "contract_dgemm_kernel");
+  for (auto s : e.kt.sign) e.any_sign |= s != 0;
+  if (e.any_sign)
+    for (auto s : e.kt.sign) ks.push_back(s ? -1.0 : 1.0);
+  // DGEMM: 16-byte gathers when both tables are pairwise contiguous and every base offset is even
+  bool vec = e.g.N % 2 == 0 && k_a.size() % 2 == 0;
+  for (size_t k = 0; vec && k + 1 < k_a.size(); k += 2) vec = k_a[k] % 2 == 0 && k_a[k + 1] == k_a[k] + 1;
+  for (size_t c = 0; vec && c + 1 < col_b.size(); c += 2) vec = col_b[c] % 2 == 0 && col_b[c + 1] == col_b[c] + 1;
+  for (size_t r = 0; vec && r < row_a.size(); ++r) vec = row_a[r] % 2 == 0;
+  for (size_t k = 0; vec && k < k_b.size(); ++k) vec = k_b[k] % 2 == 0;
+  e.vec_tables = vec;
+  e.d_row_a.upload(row_a);
+  e.d_out_row.upload(out_row);
+  e.d_col_b.upload(col_b);
+  e.d_out_col.upload(out_col);
+  e.d_ka.upload(k_a);
+  e.d_kb.upload(k_b);
+  e.d_ksign.upload(ks);
+}
+
+static void build_csr_tables(ContractEntry& e, const spn_tensor* a, const spn_tensor* b) {
+  const spn_contract_plan& plan = e.plan;
+  const bool a_sp = a->sparse();
+  const spn_tensor* sp = a_sp ? a : b;
+  const auto& s_out = a_sp ? plan.out_stride_a : plan.out_stride_b;
+  const auto& d_out = a_sp ? plan.out_stride_b : plan.out_stride_a;
+  const auto& ks = a_sp ? e.kt.off_a : e.kt.off_b;
+  const auto& kd = a_sp ? e.kt.off_b : e.kt.off_a;
+  std::vector<int> row_ptr(plan.size_out + 1, 0);
+  std::vector<long long> col;  // offsets into the dense operand: 64-bit (tensors beyond 2^31 elements)
+  std::vector<double2> val;
+  std::vector<unsigned char> sgn;
+  std::vector<uint32_t> idx(plan.order_out, 0);
+  for (uint64_t o = 0; o < plan.size_out; ++o) {
+    uint64_t offs = 0, offd = 0;
+    for (uint32_t r = 0; r < plan.order_out; ++r) {
+      offs += (uint64_t)idx[r] * s_out[r];
+      offd += (uint64_t)idx[r] * d_out[r];
+    }
+    for (size_t k = 0; k < ks.size(); ++k) {
+      auto it = sp->entries.find(offs + (uint64_t)ks[k]);
+      if (it == sp->entries.end()) continue;
+      col.push_back((long long)(offd + (uint64_t)kd[k]));
+      val.push_back(it->second);
+      sgn.push_back(e.kt.sign[k]);
+    }
+    if (col.size() > (size_t)0x7fffffff) throw Error(SPN_ERR_INVALID, "sparse operand: more than 2^31 stored products");
+    row_ptr[o + 1] = (int)col.size();
+    for (uint32_t r = plan.order_out; r-- > 0;) {
+      if (++idx[r] < plan.out_dim[r]) break;
+      idx[r] = 0;
+    }
   }
-  ctx->launches++;
+  e.nnz = col.size();
+  e.d_row.upload(row_ptr);
+  e.d_col.upload(col);
+  e.d_val.upload(val);
+  e.d_sgn.upload(sgn);
+}
+
+static uint64_t batch_points(const spn_tensor* a, const spn_tensor* b) {
+  if (a->batched() && b->batched()) {
+    if (a->n_points != b->n_points) throw Error(SPN_ERR_INVALID, "batched operands have different point counts");
+    return a->n_points;
+  }
+  return a->batched() ? a->n_points : (b->batched() ? b->n_points : 1);
+}
+
+// cache key: the two structures as plain bytes + what the operands are.  Point counts enter only through the two
+// thresholds the dispatch uses.
+static void contract_key(std::string& key, const spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, uint64_t n_points) {
+  key.clear();
+  key.reserve(2 * (SPN_MAX_ORDER * sizeof(spn_slot) + 16) + 4);
+  for (const spn_tensor* t : {a, b}) {
+    key.append(reinterpret_cast<const char*>(t->st.slots.data()), t->st.slots.size() * sizeof(spn_slot));
+    const char tag[6] = {(char)t->storage, (char)t->dtype, (char)t->layout, (char)(((uintptr_t)t->dptr % 32) == 0),
+                         (char)(((uintptr_t)t->dptr % 16) == 0), (char)t->st.slots.size()};
+    key.append(tag, sizeof tag);
+    key.append(reinterpret_cast<const char*>(&t->uid), sizeof t->uid);
+  }
+  key.push_back((char)(n_points >= 2048));
+  key.push_back((char)(n_points <= 65535));
+  key.push_back((char)ctx->emulate_reference_pairing);
+}
+
+static std::shared_ptr<ContractEntry> build_entry(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b,
+                                                  const spn_tensor* res_probe, uint64_t n_points) {
+  auto e = std::make_shared<ContractEntry>();
+  e->plan = plan_contract(a->st, b->st);
+  e->rs = structure_of_plan_result(e->plan);
+  e->kt = build_k_tables(e->plan, ctx->emulate_reference_pairing);
+  e->map = out_map_of(e->plan);
+  if (e->kt.off_a.size() > (size_t)1 << 24) throw Error(SPN_ERR_INVALID, "contracted volume too large for the table path");
+  (void)res_probe;
+  (void)n_points;
+  return e;
 }
 
 void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn_tensor** out) {
-  spn_contract_plan plan = plan_contract(a->st, b->st);
-  check_empty_sparse(a, b, (int)plan.merge_kind);
-  Structure rs = structure_of_plan_result(plan);
-  uint64_t n_points = 1;
-  if (a->batched() && b->batched()) {
-    if (a->n_points != b->n_points) throw Error(SPN_ERR_INVALID, "batched operands have different point counts");
-    n_points = a->n_points;
-  } else if (a->batched()) {
-    n_points = a->n_points;
-  } else if (b->batched()) {
-    n_points = b->n_points;
-  }
+  const uint64_t n_points = batch_points(a, b);
   const bool any_batched = a->batched() || b->batched();
   const int out_dtype = (a->dtype == SPN_F64 && b->dtype == SPN_F64) ? SPN_F64 : SPN_C64;
   const int out_layout = a->batched() ? a->layout : (b->batched() ? b->layout : SPN_POINT_MAJOR);
-  std::unique_ptr<spn_tensor> res(new_batched(ctx, rs, n_points, out_dtype, out_layout, nullptr));
   const bool point_fastest = out_layout == SPN_COMPONENT_MAJOR;
-  KTables kt = build_k_tables(plan, ctx->emulate_reference_pairing);
-  DevOutMap map = out_map_of(plan);
-  if (kt.off_a.size() > (size_t)1 << 24) throw Error(SPN_ERR_INVALID, "contracted volume too large for the table path");
 
-  const bool a_sp = a->sparse(), b_sp = b->sparse();
-  static const char* kind_name[] = {"FirstBeforeSecond", "SecondBeforeFirst", "Interleaved"};
-  const char* how = plan.n_common == 0 ? "exterior" : (plan.n_common == 1 ? "single" : "multi");
-  if (any_batched && contract_small_jit(ctx, plan, kt, a, b, res.get(), n_points)) {
-    // physics-sized per-point tensors: a kernel specialised for this stride plan (same rounding as below)
-    SPN_TRACE_LOG("contract %s %s: size_out=%llu n_k=%zu points=%llu -> specialised kernel", how, kind_name[plan.merge_kind],
-                  (unsigned long long)plan.size_out, kt.off_a.size(), (unsigned long long)n_points);
-    *out = res.release();
-    return;
+  thread_local std::string key;
+  contract_key(key, ctx, a, b, n_points);
+  std::shared_ptr<ContractEntry> entry;
+  auto hit = ctx->contract_cache.find(key);
+  if (hit != ctx->contract_cache.end()) {
+    entry = hit->second;
+    ctx->contract_cache_hits++;
+  } else {
+    ctx->contract_cache_misses++;
+    entry = build_entry(ctx, a, b, nullptr, n_points);
   }
-  SPN_TRACE_LOG("contract %s %s: size_out=%llu n_k=%zu points=%llu -> %s", how, kind_name[plan.merge_kind],
-                (unsigned long long)plan.size_out, kt.off_a.size(), (unsigned long long)n_points,
-                a_sp != b_sp ? "CSR gather kernel"
-                             : (zgemm_applicable(plan, a, b, res.get(), n_points, kt) ? "DMMA ZGEMM kernel" : "generic dense kernel"));
-  if (a_sp != b_sp) {
-    // K2: one shared sparse operand -> CSR gather over the stored entries only
-    const spn_tensor* sp = a_sp ? a : b;
-    const spn_tensor* dn = a_sp ? b : a;
-    const auto& s_out = a_sp ? plan.out_stride_a : plan.out_stride_b;
-    const auto& d_out = a_sp ? plan.out_stride_b : plan.out_stride_a;
-    const auto& ks = a_sp ? kt.off_a : kt.off_b;
-    const auto& kd = a_sp ? kt.off_b : kt.off_a;
-    std::vector<int> row_ptr(plan.size_out + 1, 0);
-    std::vector<long long> col;  // offsets into the dense operand: 64-bit (tensors beyond 2^31 elements)
-    std::vector<double2> val;
-    std::vector<unsigned char> sgn;
-    std::vector<uint32_t> idx(plan.order_out, 0);
-    for (uint64_t o = 0; o < plan.size_out; ++o) {
-      uint64_t offs = 0, offd = 0;
-      for (uint32_t r = 0; r < plan.order_out; ++r) {
-        offs += (uint64_t)idx[r] * s_out[r];
-        offd += (uint64_t)idx[r] * d_out[r];
-      }
-      for (size_t k = 0; k < ks.size(); ++k) {
-        auto it = sp->entries.find(offs + (uint64_t)ks[k]);
-        if (it == sp->entries.end()) continue;
-        col.push_back((long long)(offd + (uint64_t)kd[k]));
-        val.push_back(it->second);
-        sgn.push_back(kt.sign[k]);
-      }
-      if (col.size() > (size_t)0x7fffffff) throw Error(SPN_ERR_INVALID, "sparse operand: more than 2^31 stored products");
-      row_ptr[o + 1] = (int)col.size();
-      for (uint32_t r = plan.order_out; r-- > 0;) {
-        if (++idx[r] < plan.out_dim[r]) break;
-        idx[r] = 0;
+  ContractEntry& e = *entry;
+  const spn_contract_plan& plan = e.plan;
+  // not cached: it depends on what the operands hold (an empty sparse receiver facing an empty dense operand)
+  check_empty_sparse(a, b, (int)plan.merge_kind);
+  std::unique_ptr<spn_tensor> res(new_batched(ctx, e.rs, n_points, out_dtype, out_layout, nullptr));
+  const bool a_sp = a->sparse(), b_sp = b->sparse();
+
+  if (hit == ctx->contract_cache.end()) {
+    // ---- first time for this pair of structures: choose the kernel and build its tables ----
+    static const char* kind_name[] = {"FirstBeforeSecond", "SecondBeforeFirst", "Interleaved"};
+    const char* how = plan.n_common == 0 ? "exterior" : (plan.n_common == 1 ? "single" : "multi");
+    if (any_batched && ((uintptr_t)res->dptr % 32) == 0 && pair_jit_applicable(plan, e.kt, a, b, res->batched(), n_points)) {
+      // physics-sized per-point tensors: a kernel specialised for this stride plan (same rounding as the generic ones)
+      e.path = PATH_JIT;
+      e.jit = pair_jit_build(ctx, plan, e.kt, a, b, res.get());
+    } else if (a_sp != b_sp) {
+      e.path = PATH_CSR;  // K2: one shared sparse operand -> CSR gather over the stored entries only
+      build_csr_tables(e, a, b);
+    } else if (zgemm_applicable(plan, a, b, out_dtype, res->operand().fs, n_points, e.kt)) {
+      e.path = PATH_GEMM;  // K6: the contraction reshapes to a GEMM large enough for the FP64 tensor pipe
+      build_gemm_tables(e);
+    } else {
+      // K1/K5/K7 (and sparse x sparse over the densified shared copies; the structural/zero filter of the sparse
+      // result is applied below)
+      e.path = PATH_DENSE;
+      e.d_ka.upload(e.kt.off_a);
+      e.d_kb.upload(e.kt.off_b);
+      e.d_ks.upload(e.kt.sign);
+      if (plan.size_out <= (1ull << 22) && !getenv("SPN_NO_DENSE_TABLES")) {
+        std::vector<long long> toa(plan.size_out), tob(plan.size_out);
+        std::vector<uint32_t> idx(plan.order_out, 0);
+        for (uint64_t o = 0; o < plan.size_out; ++o) {
+          long long oa = 0, ob = 0;
+          for (uint32_t r = 0; r < plan.order_out; ++r) {
+            oa += (long long)idx[r] * (long long)plan.out_stride_a[r];
+            ob += (long long)idx[r] * (long long)plan.out_stride_b[r];
+          }
+          toa[o] = oa;
+          tob[o] = ob;
+          for (uint32_t r = plan.order_out; r-- > 0;) {
+            if (++idx[r] < plan.out_dim[r]) break;
+            idx[r] = 0;
+          }
+        }
+        e.d_toa.upload(toa);
+        e.d_tob.upload(tob);
+        e.has_out_tables = true;
       }
     }
-    DevArray<int> d_row(row_ptr, ctx->stream);
-    DevArray<long long> d_col(col, ctx->stream);
-    DevArray<double2> d_val(val, ctx->stream);
-    DevArray<unsigned char> d_sgn(sgn, ctx->stream);
-    cuda_check(launch_contract_csr(dn->operand(), res->output(), d_row.p, d_col.p, d_val.p, d_sgn.p,
-                                   /*dense_is_first=*/a_sp ? 0 : 1, plan.size_out, col.size(), n_points,
-                                   point_fastest, ctx->stream),
-               "contract_csr_kernel");
-    ctx->launches++;
-  } else if (zgemm_applicable(plan, a, b, res.get(), n_points, kt)) {
-    // K6: the contraction reshapes to a complex GEMM large enough for the FP64 tensor pipe
-    launch_zgemm_path(ctx, plan, kt, a, b, res.get(), n_points);
-  } else {
-    // K1/K5/K7 (and sparse x sparse over the densified shared copies; the structural/zero
-    // filter of the sparse result is applied below)
-    DevArray<long long> d_ka(kt.off_a, ctx->stream), d_kb(kt.off_b, ctx->stream);
-    DevArray<unsigned char> d_ks(kt.sign, ctx->stream);
-    cuda_check(launch_contract_dense(map, a->operand(), b->operand(), res->output(), d_ka.p, d_kb.p, d_ks.p,
-                                     kt.off_a.size(), n_points, point_fastest, ctx->stream),
-               "contract_dense_kernel");
-    ctx->launches++;
+    static const char* path_name[] = {"specialised kernel", "CSR gather kernel", "DMMA GEMM kernel", "generic dense kernel"};
+    SPN_TRACE_LOG("contract %s %s: size_out=%llu n_k=%zu points=%llu -> %s%s", how, kind_name[plan.merge_kind],
+                  (unsigned long long)plan.size_out, e.kt.off_a.size(), (unsigned long long)n_points, path_name[e.path],
+                  e.path == PATH_JIT && e.jit.slab ? " (slab-staged)" : "");
+    if (ctx->contract_cache.size() >= 4096) ctx->contract_cache.clear();  // bounded: entries hold device tables
+    ctx->contract_cache.emplace(key, entry);
+  }
+
+  switch (e.path) {
+    case PATH_JIT:
+      if (((uintptr_t)res->dptr % 32) != 0) throw Error(SPN_ERR_OTHER, "pooled result allocation is not 32-byte aligned");
+      pair_jit_launch(ctx, e.jit, a, b, res.get(), n_points);
+      break;
+    case PATH_CSR: {
+      const spn_tensor* dn = a_sp ? b : a;
+      cuda_check(launch_contract_csr(dn->operand(), res->output(), e.d_row.p, e.d_col.p, e.d_val.p, e.d_sgn.p,
+                                     /*dense_is_first=*/a_sp ? 0 : 1, plan.size_out, e.nnz, n_points, point_fastest,
+                                     ctx->stream),
+                 "contract_csr_kernel");
+      ctx->launches++;
+      break;
+    }
+    case PATH_GEMM: {
+      const long long K = (long long)e.kt.off_a.size();
+      if (a->dtype == SPN_C64)
+        cuda_check(launch_contract_zgemm(static_cast<const double2*>(a->dptr), static_cast<const double2*>(b->dptr),
+                                         static_cast<double2*>(res->dptr), e.d_row_a.p, e.d_ka.p, e.d_col_b.p, e.d_kb.p,
+                                         e.d_out_row.p, e.d_out_col.p, e.any_sign ? e.d_ksign.p : nullptr, e.g.M, e.g.N, K,
+                                         a->operand().ps, b->operand().ps, res->operand().ps, n_points, ctx->stream),
+                   "contract_zgemm_kernel");
+      else {
+        const bool vec = e.vec_tables && a->operand().ps % 2 == 0 && b->operand().ps % 2 == 0 &&
+                         (uintptr_t)a->dptr % 16 == 0 && (uintptr_t)b->dptr % 16 == 0;
+        cuda_check(launch_contract_dgemm(static_cast<const double*>(a->dptr), static_cast<const double*>(b->dptr),
+                                         static_cast<double*>(res->dptr), e.d_row_a.p, e.d_ka.p, e.d_col_b.p, e.d_kb.p,
+                                         e.d_out_row.p, e.d_out_col.p, e.any_sign ? e.d_ksign.p : nullptr, e.g.M, e.g.N, K,
+                                         a->operand().ps, b->operand().ps, res->operand().ps, n_points, vec, ctx->stream),
+                   "contract_dgemm_kernel");
+      }
+      ctx->launches++;
+      break;
+    }
+    default: {
+      cudaError_t rc = cudaErrorInvalidConfiguration;
+      if (e.has_out_tables)
+        rc = launch_contract_dense_tab(a->operand(), b->operand(), res->output(), e.d_toa.p, e.d_tob.p, e.d_ka.p, e.d_kb.p,
+                                       e.d_ks.p, e.kt.off_a.size(), plan.size_out, n_points, point_fastest, ctx->stream);
+      if (rc == cudaErrorInvalidConfiguration)  // result too large for tables / 32-bit tiles: run-time index arithmetic
+        rc = launch_contract_dense(e.map, a->operand(), b->operand(), res->output(), e.d_ka.p, e.d_kb.p, e.d_ks.p,
+                                   e.kt.off_a.size(), n_points, point_fastest, ctx->stream);
+      cuda_check(rc, "contract_dense_kernel");
+      ctx->launches++;
+      break;
+    }
   }
   if (any_batched) {
     *out = res.release();
     return;
   }
+  const KTables& kt = e.kt;
+  const Structure& rs = e.rs;
   // shared x shared: the result is itself a shared tensor (computed on the device with one point)
   std::vector<double2> host(plan.size_out);
   cuda_check(cudaMemcpyAsync(host.data(), res->dptr, host.size() * sizeof(double2), cudaMemcpyDeviceToHost,
@@ -465,6 +601,18 @@ int spn_plan_contract(const spn_slot* a, uint32_t na, const spn_slot* b, uint32_
   API_CATCH
 }
 
+const char* spn_plan_contract_cuda_source(const spn_slot* a, uint32_t na, int dtype_a, int layout_a, const spn_slot* b,
+                                          uint32_t nb, int dtype_b, int layout_b) {
+  static thread_local std::string src;
+  try {
+    src = pair_jit_source(structure_of_canonical(a, na), dtype_a, layout_a, structure_of_canonical(b, nb), dtype_b, layout_b);
+    return src.c_str();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
 int spn_ctx_create(int device, spn_ctx** out) {
   API_TRY
   int count = 0;
@@ -519,6 +667,12 @@ int spn_ctx_synchronize(spn_ctx* ctx) {
   API_CATCH
 }
 uint64_t spn_ctx_launch_count(const spn_ctx* ctx) { return ctx->launches; }
+int spn_ctx_plan_cache_stats(const spn_ctx* ctx, uint64_t* hits, uint64_t* misses, uint64_t* entries) {
+  if (hits) *hits = ctx->contract_cache_hits;
+  if (misses) *misses = ctx->contract_cache_misses;
+  if (entries) *entries = ctx->contract_cache.size();
+  return SPN_OK;
+}
 int spn_ctx_sm_count(const spn_ctx* ctx) { return ctx->sm_count; }
 
 int spn_tensor_batched(spn_ctx* ctx, const spn_slot* slots, uint32_t n, uint64_t n_points, int dtype, int layout,

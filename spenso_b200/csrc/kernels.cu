@@ -14,6 +14,8 @@
 // (CSR of a sparse library tensor) is staged in shared memory.
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace spn {
 
 namespace {
@@ -83,6 +85,60 @@ contract_dense_kernel(const __grid_constant__ DevOutMap map, DevOperand a, DevOp
       double2 x = load_elem<AC>(a.ptr, offa + __ldg(koff_a + k) * a.fs);
       double2 y = load_elem<BC>(b.ptr, offb + __ldg(koff_b + k) * b.fs);
       cacc_rn(acc, cmul_rn(x, y), __ldg(ksign + k) != 0);
+    }
+    store_elem(out.ptr, (ll)p * out.ps + (ll)o * out.fs, acc, out.is_complex);
+  }
+}
+
+// The same contraction without run-time index arithmetic: the base offsets of every result element come from two
+// host-built tables (toa[o], tob[o]: the plan-cache entry owns them), the contracted-loop tables sit in shared
+// memory, and a CTA works on tiles of 256 consecutive elements of the fastest axis — results of one point (point
+// major: consecutive threads = consecutive result elements, coalesced stores) or one result element over 256
+// points (component major).  One 32-bit division per tile instead of 2 x order 64-bit divisions per element.
+template <bool AC, bool BC, bool PF>
+__global__ void __launch_bounds__(256)
+contract_dense_tab_kernel(DevOperand a, DevOperand b, DevOut out, const ll* __restrict__ toa, const ll* __restrict__ tob,
+                          const ll* __restrict__ koff_a, const ll* __restrict__ koff_b,
+                          const unsigned char* __restrict__ ksign, unsigned n_k, unsigned size_out, ull n_points,
+                          unsigned inner_tiles, unsigned n_tiles, int stage_k) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ll* ka = koff_a;
+  const ll* kb = koff_b;
+  const unsigned char* ks = ksign;
+  if (stage_k) {
+    ll* sa = reinterpret_cast<ll*>(smem);
+    ll* sb = sa + n_k;
+    unsigned char* ss = reinterpret_cast<unsigned char*>(sb + n_k);
+    for (unsigned k = threadIdx.x; k < n_k; k += blockDim.x) {
+      sa[k] = __ldg(koff_a + k) * a.fs;
+      sb[k] = __ldg(koff_b + k) * b.fs;
+      ss[k] = __ldg(ksign + k);
+    }
+    __syncthreads();
+    ka = sa;
+    kb = sb;
+    ks = ss;
+  }
+  const ll fsa = stage_k ? 1 : a.fs, fsb = stage_k ? 1 : b.fs;
+  for (unsigned T = blockIdx.x; T < n_tiles; T += gridDim.x) {
+    const unsigned outer = T / inner_tiles;
+    const ull inner = (ull)(T - outer * inner_tiles) * 256ull + threadIdx.x;
+    ull p, o;
+    if (PF) {
+      o = outer;
+      p = inner;
+      if (p >= n_points) continue;
+    } else {
+      p = outer;
+      o = inner;
+      if (o >= size_out) continue;
+    }
+    const ll offa = (ll)p * a.ps + __ldg(toa + o) * a.fs, offb = (ll)p * b.ps + __ldg(tob + o) * b.fs;
+    double2 acc = make_double2(0.0, 0.0);
+    for (unsigned k = 0; k < n_k; ++k) {
+      double2 x = load_elem<AC>(a.ptr, offa + ka[k] * fsa);
+      double2 y = load_elem<BC>(b.ptr, offb + kb[k] * fsb);
+      cacc_rn(acc, cmul_rn(x, y), ks[k] != 0);
     }
     store_elem(out.ptr, (ll)p * out.ps + (ll)o * out.fs, acc, out.is_complex);
   }
@@ -294,6 +350,39 @@ cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand
   else
     SPN_LAUNCH_DD(false, false);
 #undef SPN_LAUNCH_DD
+  return cudaGetLastError();
+}
+
+cudaError_t launch_contract_dense_tab(DevOperand a, DevOperand b, DevOut out, const ll* toa, const ll* tob, const ll* koff_a,
+                                      const ll* koff_b, const unsigned char* ksign, ull n_k, ull size_out, ull n_points,
+                                      bool point_fastest, cudaStream_t stream) {
+  if (size_out * n_points == 0) return cudaSuccess;
+  const ull inner = point_fastest ? n_points : size_out, outer = point_fastest ? size_out : n_points;
+  const ull inner_tiles = (inner + 255) / 256, n_tiles = inner_tiles * outer;
+  if (n_tiles >= 0xffffffffull || n_k >= 0xffffffffull || size_out >= 0xffffffffull) return cudaErrorInvalidConfiguration;
+  const int stage_k = n_k <= 2048;
+  const size_t smem = stage_k ? (size_t)n_k * 17 + 16 : 0;
+  const unsigned grid = (unsigned)std::min<ull>(n_tiles, (ull)sm_count() * 8);
+#define SPN_LAUNCH_DT(AC, BC, PF)                                                                                       \
+  contract_dense_tab_kernel<AC, BC, PF><<<grid, 256, smem, stream>>>(a, b, out, toa, tob, koff_a, koff_b, ksign,         \
+                                                                     (unsigned)n_k, (unsigned)size_out, n_points,      \
+                                                                     (unsigned)inner_tiles, (unsigned)n_tiles, stage_k)
+#define SPN_LAUNCH_DT2(AC, BC) \
+  if (point_fastest)           \
+    SPN_LAUNCH_DT(AC, BC, true); \
+  else                         \
+    SPN_LAUNCH_DT(AC, BC, false)
+  if (a.is_complex && b.is_complex) {
+    SPN_LAUNCH_DT2(true, true);
+  } else if (a.is_complex) {
+    SPN_LAUNCH_DT2(true, false);
+  } else if (b.is_complex) {
+    SPN_LAUNCH_DT2(false, true);
+  } else {
+    SPN_LAUNCH_DT2(false, false);
+  }
+#undef SPN_LAUNCH_DT2
+#undef SPN_LAUNCH_DT
   return cudaGetLastError();
 }
 

@@ -39,6 +39,13 @@ cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand
                                   unsigned long long n_k, unsigned long long n_points, bool point_fastest,
                                   cudaStream_t stream);
 
+// the same with host-built per-result-element base offsets toa/tob (size_out entries each): no index arithmetic on
+// the device.  Needs size_out, n_k and the tile count below 2^32 (cudaErrorInvalidConfiguration otherwise).
+cudaError_t launch_contract_dense_tab(DevOperand a, DevOperand b, DevOut out, const long long* toa, const long long* tob,
+                                      const long long* koff_a, const long long* koff_b, const unsigned char* ksign,
+                                      unsigned long long n_k, unsigned long long size_out, unsigned long long n_points,
+                                      bool point_fastest, cudaStream_t stream);
+
 // K2 (dense(per point) x sparse(shared)): singlecontract.rs:78-196, multicontract.rs:80-200.
 // CSR over result elements: row o holds (offset into the dense operand, value, sign) for every
 // stored entry of the sparse fibre, in ascending fibre position.

@@ -1,9 +1,18 @@
 // Specialised kernels for the pairwise Contract trait on small per-point tensors (the physics sizes: Bispinor 4,
 // Minkowski 4, colour 3/8).  The generic kernels of kernels.cu spend their time on index arithmetic (one thread
 // per output component, run-time strides, table lookups per multiply); here the stride plan of ONE contraction is
-// burnt into a straight-line kernel — thread = phase-space point, every operand component loaded once with a
-// 128-bit load, every product at a literal offset, results written with 256-bit stores — compiled with NVRTC for
-// sm_100a and cached per (plan, storage, dtype, layout).
+// burnt into a straight-line kernel — thread = phase-space point, every operand component read once, every product at
+// a literal offset — compiled with NVRTC for sm_100a and cached per (plan, storage, dtype, layout).
+//
+// Memory side.  A point-major operand of S bytes per point read thread = point makes every warp-wide load touch 32
+// cache lines (one sector each); beyond S = 64 B that runs into the L1 tag rate and the kernels of round 1 stalled at
+// 0.75-0.87 of the HBM roofline.  So point-major operands and results are STAGED: every warp owns slabs of 32
+// consecutive points; it copies the slab — a contiguous 32*S byte range — global -> shared with 16-byte cp.async
+// (LDGSTS; consecutive lanes = consecutive addresses, i.e. full lines), two slabs deep, into a padded [point][unit]
+// layout (row stride odd in 16-byte units => the thread-=-point reads that follow are bank-conflict free); results go
+// registers -> padded shared slab -> contiguous 16-byte global stores.  No block barrier: a warp only touches its
+// own slabs (__syncwarp).  Component-major operands are already coalesced thread = point and are read directly; a
+// shared dense operand is read with uniform (broadcast) loads; a shared sparse operand is literals in the code.
 //
 // The arithmetic is the reference's, operation for operation (singlecontract.rs:25-196, multicontract.rs:25-200,
 // exteriorproduct.rs:19-153; complex product algebra/complex/mul.rs:16-21; f64 upgraded to (x, 0.0),
@@ -23,14 +32,39 @@ namespace spn {
 
 namespace {
 
-const int kPairBlock = getenv("SPN_PAIR_BLOCK") ? atoi(getenv("SPN_PAIR_BLOCK")) : 256;  // threads per CTA (measured: 256 >= 128 >= 64 by 0-4 %)
+const int kPairBlock = getenv("SPN_PAIR_BLOCK") ? atoi(getenv("SPN_PAIR_BLOCK")) : 256;  // direct kernels: threads per CTA
+const int kSlabWarps = getenv("SPN_PAIR_SLAB_WARPS") ? atoi(getenv("SPN_PAIR_SLAB_WARPS")) : 4;  // staged kernels: warps per CTA
 
 struct Operand {
   const spn_tensor* t;
   char name;  // 'A' / 'B'
 };
 
-// address expression (in doubles) of component f of an operand at point p
+// how one tensor (operand or result) reaches the registers of the thread that owns its point
+struct Staging {
+  bool staged = false;
+  uint64_t units = 0;   // 16-byte units per point
+  uint64_t row = 0;     // padded row stride in units (odd)
+  uint64_t offset = 0;  // first unit inside a stage (operands) / inside the warp's region (result)
+};
+
+bool stageable(const spn_tensor* t) {
+  if (getenv("SPN_PAIR_NO_SLAB")) return false;
+  if (!t->batched() || t->layout != SPN_POINT_MAJOR) return false;
+  const uint64_t bytes = t->size() * t->elem_bytes();
+  return bytes % 16 == 0 && bytes >= 32 && ((uintptr_t)t->dptr % 16) == 0;
+}
+Staging staging_of(const spn_tensor* t) {
+  Staging s;
+  s.staged = stageable(t);
+  if (s.staged) {
+    s.units = t->size() * t->elem_bytes() / 16;
+    s.row = s.units | 1ull;  // odd: 8 consecutive rows start in 8 different 16-byte bank groups
+  }
+  return s;
+}
+
+// address expression (in doubles) of component f of an operand at point p — direct (unstaged) access
 std::string addr(const Operand& o, uint64_t f) {
   std::ostringstream s;
   const int w = o.t->dtype == SPN_C64 ? 2 : 1;
@@ -43,11 +77,49 @@ std::string addr(const Operand& o, uint64_t f) {
   return s.str();
 }
 
-std::string generate(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b,
-                     const spn_tensor* res, const std::string& kname, bool wide_stores) {
+struct Generated {
+  std::string source;
+  bool slab = false;
+  size_t smem_bytes = 0;
+  int block = 0;
+};
+
+Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b,
+                   const spn_tensor* res, const std::string& kname, bool wide_stores) {
   const bool wide_loads = !getenv("SPN_NO_WIDE_LOADS");
+  Generated gen;
+  Staging sa = a->sparse() ? Staging() : staging_of(a), sb = b->sparse() ? Staging() : staging_of(b), sc = staging_of(res);
+  gen.slab = sa.staged || sb.staged || sc.staged;
+  // shared memory of one warp: [2 stages][A slab | B slab] then the result slab
+  uint64_t stage_units = 0;
+  if (sa.staged) { sa.offset = stage_units; stage_units += 32 * sa.row; }
+  if (sb.staged) { sb.offset = stage_units; stage_units += 32 * sb.row; }
+  int n_stages = (getenv("SPN_PAIR_STAGES") && atoi(getenv("SPN_PAIR_STAGES")) == 1) ? 1 : 2;
+  const bool force_stages = getenv("SPN_PAIR_STAGES") != nullptr;
+  uint64_t warp_units = n_stages * stage_units + (sc.staged ? 32 * sc.row : 0);
+  int warps = kSlabWarps;
+  if (gen.slab) {
+    // keep at least ~4 warps resident per SM: fall back to one stage, then to fewer warps per CTA
+    const uint64_t budget = 220 * 1024 / 16;
+    if (warp_units * 4 > budget && !force_stages) {
+      n_stages = 1;
+      warp_units = stage_units + (sc.staged ? 32 * sc.row : 0);
+    }
+    while (warps > 1 && warp_units * (uint64_t)warps > budget) warps /= 2;
+    if (warp_units > budget) {  // does not fit at all: direct kernel
+      gen.slab = false;
+      sa = sb = sc = Staging();
+    }
+  }
+  sc.offset = (uint64_t)n_stages * stage_units;
+  gen.block = gen.slab ? 32 * warps : kPairBlock;
+  gen.smem_bytes = gen.slab ? (size_t)(warp_units * (uint64_t)warps * 16) : 0;
+
   std::ostringstream o;
   o << "// generated by spenso_b200 (pairwise_jit.cu): one pairwise contraction, thread = point, reference rounding\n";
+  if (gen.slab)
+    o << "// point-major tensors staged through shared memory in warp-owned slabs of 32 points (" << n_stages << " stage(s), "
+      << warp_units * 16 << " B per warp, " << warps << " warps per CTA)\n";
   o << "typedef unsigned long long ull;\n";
   o << "__device__ __forceinline__ double2 ld16(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }\n";
   o << "__device__ __forceinline__ double2 ld8(const double* p) { return make_double2(__ldg(p), 0.0); }\n";
@@ -56,12 +128,59 @@ std::string generate(const spn_contract_plan& plan, const KTables& kt, const spn
     << ".v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";   // whole sector, read once
   o << "__device__ __forceinline__ void st32(double* p, double2 a, double2 b) {\n"
        "  asm volatile(\"st.global.v4.f64 [%0], {%1,%2,%3,%4};\" :: \"l\"(p), \"d\"(a.x), \"d\"(a.y), \"d\"(b.x), \"d\"(b.y) : \"memory\");\n}\n";
+  o << "__device__ __forceinline__ void cp16(double2* s, const double2* g) {\n"
+       "  asm volatile(\"cp.async.cg.shared.global [%0], [%1], 16;\" :: \"r\"((unsigned)__cvta_generic_to_shared(s)), \"l\"(g) : \"memory\");\n}\n";
   o << "__device__ __forceinline__ double2 cmul_rn(double2 a, double2 b) {\n"
        "  return make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));\n}\n";
-  o << "extern \"C\" __global__ void __launch_bounds__(" << kPairBlock << ") " << kname
+  o << "extern \"C\" __global__ void __launch_bounds__(" << gen.block << ") " << kname
     << "(const double* __restrict__ A, ull csA, const double* __restrict__ B, ull csB, double* __restrict__ C, ull csC, ull n_points) {\n";
-  o << "  for (ull p = (ull)blockIdx.x * " << kPairBlock << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << kPairBlock
-    << ") {\n";
+  if (gen.slab) {
+    o << "  extern __shared__ __align__(16) double2 smem[];\n";
+    o << "  const unsigned lane = threadIdx.x & 31u;\n";
+    o << "  double2* const ws = smem + (threadIdx.x >> 5) * " << warp_units << "u;   // this warp's slabs\n";
+    o << "  const ull n_slabs = (n_points + 31ull) >> 5;\n";
+    o << "  const ull n_warps = (ull)gridDim.x * " << warps << "ull;\n";
+    o << "  ull slab = (ull)blockIdx.x * " << warps << "ull + (threadIdx.x >> 5);\n";
+    // issue(slab, stage): cp.async the operand slabs of `slab` into stage `stage`
+    o << "  auto issue = [&](ull sl, unsigned stage) {\n";
+    o << "    const ull p0 = sl << 5;\n";
+    o << "    const unsigned np = (unsigned)(n_points - p0 < 32ull ? n_points - p0 : 32ull);\n";
+    for (auto pr : {std::make_pair(&sa, 'A'), std::make_pair(&sb, 'B')}) {
+      const Staging& s = *pr.first;
+      if (!s.staged) continue;
+      o << "    {\n      const double2* src = reinterpret_cast<const double2*>(" << pr.second << ") + p0 * " << s.units << "ull;\n";
+      o << "      double2* dst = ws + stage * " << stage_units << "u + " << s.offset << "u;\n";
+      o << "      const unsigned lim = np * " << s.units << "u;\n";
+      o << "#pragma unroll\n      for (unsigned j = 0; j < " << s.units << "u; ++j) {\n";
+      o << "        const unsigned g = lane + 32u * j;\n";
+      if (s.row == s.units)
+        o << "        if (g < lim) cp16(dst + g, src + g);\n";
+      else
+        o << "        if (g < lim) cp16(dst + g + g / " << s.units << "u, src + g);\n";  // row stride = units + 1
+      o << "      }\n    }\n";
+    }
+    o << "  };\n";
+    o << "  if (slab < n_slabs) issue(slab, 0u);\n";
+    o << "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
+    o << "  for (unsigned stage = 0; slab < n_slabs; slab += n_warps" << (n_stages == 2 ? ", stage ^= 1u" : "") << ") {\n";
+    if (n_stages == 2) {
+      o << "    if (slab + n_warps < n_slabs) issue(slab + n_warps, stage ^ 1u);\n";
+      o << "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
+      o << "    asm volatile(\"cp.async.wait_group 1;\" ::: \"memory\");\n";
+    } else {
+      o << "    asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\");\n";
+    }
+    o << "    __syncwarp();\n";
+    o << "    const ull p0 = slab << 5;\n    const ull p = p0 + lane;\n";
+    o << "    const unsigned np = (unsigned)(n_points - p0 < 32ull ? n_points - p0 : 32ull);\n";
+    if (sa.staged) o << "    const double2* const sA = ws + stage * " << stage_units << "u + " << sa.offset << "u + lane * " << sa.row << "u;\n";
+    if (sb.staged) o << "    const double2* const sB = ws + stage * " << stage_units << "u + " << sb.offset << "u + lane * " << sb.row << "u;\n";
+    if (sc.staged) o << "    double2* const sC = ws + " << sc.offset << "u + lane * " << sc.row << "u;\n";
+    o << "    if (lane < np) {\n";
+  } else {
+    o << "  for (ull p = (ull)blockIdx.x * " << gen.block << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << gen.block
+      << ") {\n";
+  }
   Operand oa{a, 'A'}, ob{b, 'B'};
   // which components are needed, in first-use order
   std::vector<char> seen_a(a->size(), 0), seen_b(b->size(), 0);
@@ -88,22 +207,30 @@ std::string generate(const spn_contract_plan& plan, const KTables& kt, const spn
       }
     }
   }
-  auto use = [&](const Operand& op, std::vector<char>& seen, const std::vector<char>& used, uint64_t f) -> std::string {
+  const std::string ind = gen.slab ? "      " : "    ";
+  auto use = [&](const Operand& op, const Staging& st, std::vector<char>& seen, const std::vector<char>& used, uint64_t f) -> std::string {
     const std::string pre(1, (char)(op.name + 32));  // a12 / b3
     const std::string nm = pre + std::to_string(f);
-    if (!seen[f]) {
-      const bool pairable = wide_loads && jit_has_256bit_loads() && op.t->batched() && op.t->dtype == SPN_C64 &&
-                            op.t->layout == SPN_POINT_MAJOR && op.t->size() % 2 == 0 && ((uintptr_t)op.t->dptr % 32) == 0 &&
-                            used[f ^ 1ull];
-      if (pairable) {
-        const uint64_t base = f & ~1ull;
-        seen[base] = seen[base + 1] = 1;
-        o << "    double2 " << pre << base << ", " << pre << base + 1 << "; ld32(" << addr(op, base) << ", " << pre << base << ", "
-          << pre << base + 1 << ");\n";
-      } else {
-        seen[f] = 1;
-        o << "    const double2 " << nm << " = " << (op.t->dtype == SPN_C64 ? "ld16(" : "ld8(") << addr(op, f) << ");\n";
-      }
+    if (seen[f]) return nm;
+    if (st.staged) {
+      seen[f] = 1;
+      if (op.t->dtype == SPN_C64)
+        o << ind << "const double2 " << nm << " = s" << op.name << "[" << f << "];\n";
+      else
+        o << ind << "const double2 " << nm << " = make_double2(reinterpret_cast<const double*>(s" << op.name << ")[" << f << "], 0.0);\n";
+      return nm;
+    }
+    const bool pairable = wide_loads && jit_has_256bit_loads() && op.t->batched() && op.t->dtype == SPN_C64 &&
+                          op.t->layout == SPN_POINT_MAJOR && op.t->size() % 2 == 0 && ((uintptr_t)op.t->dptr % 32) == 0 &&
+                          used[f ^ 1ull];
+    if (pairable) {
+      const uint64_t base = f & ~1ull;
+      seen[base] = seen[base + 1] = 1;
+      o << ind << "double2 " << pre << base << ", " << pre << base + 1 << "; ld32(" << addr(op, base) << ", " << pre << base << ", "
+        << pre << base + 1 << ");\n";
+    } else {
+      seen[f] = 1;
+      o << ind << "const double2 " << nm << " = " << (op.t->dtype == SPN_C64 ? "ld16(" : "ld8(") << addr(op, f) << ");\n";
     }
     return nm;
   };
@@ -121,65 +248,97 @@ std::string generate(const spn_contract_plan& plan, const KTables& kt, const spn
       offb += (uint64_t)idx[r] * plan.out_stride_b[r];
     }
     std::ostringstream body;
-    body << "    double2 r" << e << " = make_double2(0.0, 0.0);\n";
+    body << ind << "double2 r" << e << " = make_double2(0.0, 0.0);\n";
     for (size_t k = 0; k < kt.off_a.size(); ++k) {
       const uint64_t fa = offa + (uint64_t)kt.off_a[k], fb = offb + (uint64_t)kt.off_b[k];
       if (a->sparse() && !a->entries.count(fa)) continue;  // the sparse fibre holds no entry here
       if (b->sparse() && !b->entries.count(fb)) continue;
-      std::string xa = a->sparse() ? literal(a, fa) : use(oa, seen_a, used_a, fa);
-      std::string xb = b->sparse() ? literal(b, fb) : use(ob, seen_b, used_b, fb);
-      body << "    { const double2 t = cmul_rn(" << xa << ", " << xb << "); r" << e << ".x = "
+      std::string xa = a->sparse() ? literal(a, fa) : use(oa, sa, seen_a, used_a, fa);
+      std::string xb = b->sparse() ? literal(b, fb) : use(ob, sb, seen_b, used_b, fb);
+      body << ind << "{ const double2 t = cmul_rn(" << xa << ", " << xb << "); r" << e << ".x = "
            << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(r" << e << ".x, t.x); r" << e << ".y = "
            << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(r" << e << ".y, t.y); }\n";
     }
     o << body.str();
     // store
     const bool point_major = res->layout == SPN_POINT_MAJOR;
-    if (!out_c) {
-      if (point_major)
-        o << "    C[p * " << plan.size_out << "ull + " << e << "ull] = r" << e << ".x;\n";
+    if (sc.staged) {
+      if (out_c)
+        o << ind << "sC[" << e << "] = r" << e << ";\n";
       else
-        o << "    C[" << e << "ull * csC + p] = r" << e << ".x;\n";
+        o << ind << "reinterpret_cast<double*>(sC)[" << e << "] = r" << e << ".x;\n";
+    } else if (!out_c) {
+      if (point_major)
+        o << ind << "C[p * " << plan.size_out << "ull + " << e << "ull] = r" << e << ".x;\n";
+      else
+        o << ind << "C[" << e << "ull * csC + p] = r" << e << ".x;\n";
     } else if (point_major && wide_stores && plan.size_out % 2 == 0) {
       if (e % 2 == 0) {
         pending = "r" + std::to_string(e);
       } else {
-        o << "    st32(C + (p * " << plan.size_out << "ull + " << (e - 1) << "ull) * 2, " << pending << ", r" << e << ");\n";
+        o << ind << "st32(C + (p * " << plan.size_out << "ull + " << (e - 1) << "ull) * 2, " << pending << ", r" << e << ");\n";
       }
     } else if (point_major) {
-      o << "    reinterpret_cast<double2*>(C)[p * " << plan.size_out << "ull + " << e << "ull] = r" << e << ";\n";
+      o << ind << "reinterpret_cast<double2*>(C)[p * " << plan.size_out << "ull + " << e << "ull] = r" << e << ";\n";
     } else {
-      o << "    reinterpret_cast<double2*>(C)[" << e << "ull * csC + p] = r" << e << ";\n";
+      o << ind << "reinterpret_cast<double2*>(C)[" << e << "ull * csC + p] = r" << e << ";\n";
     }
     for (uint32_t r = plan.order_out; r-- > 0;) {
       if (++idx[r] < plan.out_dim[r]) break;
       idx[r] = 0;
     }
   }
+  if (gen.slab) {
+    o << "    }\n";
+    if (sc.staged) {
+      // the warp's result slab is a contiguous range of the output: 16-byte stores, consecutive lanes = consecutive units
+      o << "    __syncwarp();\n";
+      o << "    {\n      double2* dst = reinterpret_cast<double2*>(C) + p0 * " << sc.units << "ull;\n";
+      o << "      const double2* src = ws + " << sc.offset << "u;\n";
+      o << "      const unsigned lim = np * " << sc.units << "u;\n";
+      o << "#pragma unroll\n      for (unsigned j = 0; j < " << sc.units << "u; ++j) {\n";
+      o << "        const unsigned g = lane + 32u * j;\n";
+      if (sc.row == sc.units)
+        o << "        if (g < lim) dst[g] = src[g];\n";
+      else
+        o << "        if (g < lim) dst[g] = src[g + g / " << sc.units << "u];\n";
+      o << "      }\n    }\n";
+    }
+    o << "    __syncwarp();   // every lane is done with this stage before it is refilled\n";
+    if (n_stages == 1) {
+      o << "    if (slab + n_warps < n_slabs) issue(slab + n_warps, 0u);\n";
+      o << "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
+    }
+  }
   o << "  }\n}\n";
-  return o.str();
+  gen.source = o.str();
+  return gen;
 }
 
 }  // namespace
 
-// true when the contraction was launched through a specialised kernel
-bool contract_small_jit(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
-                        const spn_tensor* b, spn_tensor* res, uint64_t n_points) {
+bool pair_jit_applicable(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b,
+                         bool res_batched, uint64_t n_points) {
   if (getenv("SPN_NO_PAIR_JIT")) return false;
   // specialising costs one NVRTC compile (~0.3 s, cached on disk): only worth it for batches that amortise it
-  if (!res->batched() || n_points < 2048) return false;
+  if (!res_batched || n_points < 2048) return false;
   if (a->sparse() && b->sparse()) return false;
   const uint64_t loaded = (a->sparse() ? 0 : a->size()) + (b->sparse() ? 0 : b->size());
   const uint64_t products = plan.size_out * (uint64_t)kt.off_a.size();
   // everything lives in registers: at most ~80 complex operand components and a few thousand products
-  if (loaded > 80 || plan.size_out > 256 || products > 4096 || products == 0) return false;
+  return !(loaded > 80 || plan.size_out > 256 || products > 4096 || products == 0);
+}
+
+PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
+                       const spn_tensor* b, const spn_tensor* res) {
   const bool wide = ((uintptr_t)res->dptr % 32) == 0;
-  // cache key: the plan (plain data), what the operands are, and the entries of a sparse operand
+  // kernel identity: the plan (plain data), what the operands are, and the entries of a sparse operand
   std::string key(reinterpret_cast<const char*>(&plan), sizeof plan);
   for (const spn_tensor* t : {a, b, (const spn_tensor*)res}) {
     key.push_back((char)t->storage);
     key.push_back((char)t->dtype);
     key.push_back((char)t->layout);
+    key.push_back(stageable(t) ? 'S' : 'd');
   }
   key.push_back(wide ? 'w' : 'n');
   key.append(reinterpret_cast<const char*>(kt.off_a.data()), kt.off_a.size() * sizeof(long long));
@@ -193,29 +352,67 @@ bool contract_small_jit(spn_ctx* ctx, const spn_contract_plan& plan, const KTabl
         key.append(reinterpret_cast<const char*>(&kv.second), sizeof kv.second);
       }
   const uint64_t h = fnv1a(key);
+  PairJit pj;
   auto it = ctx->pair_kernels.find(h);
-  if (it == ctx->pair_kernels.end()) {
-    auto k = std::make_shared<JitKernel>();
-    char nm[64];
-    std::snprintf(nm, sizeof nm, "spn_pair_contract_%016llx", (unsigned long long)h);
-    k->name = nm;
-    k->source = generate(plan, kt, a, b, res, k->name, wide);
-    jit_compile(*k);
-    jit_load(*k, kPairBlock);
-    it = ctx->pair_kernels.emplace(h, std::move(k)).first;
-  }
-  JitKernel& k = *it->second;
-  const uint64_t need = (n_points + kPairBlock - 1) / kPairBlock;
-  const unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm);
+  if (it != ctx->pair_kernels.end()) return it->second;
+  auto k = std::make_shared<JitKernel>();
+  char nm[64];
+  std::snprintf(nm, sizeof nm, "spn_pair_contract_%016llx", (unsigned long long)h);
+  k->name = nm;
+  Generated g = generate(plan, kt, a, b, res, k->name, wide);
+  k->source = g.source;
+  k->smem_bytes = g.smem_bytes;
+  jit_compile(*k);
+  jit_load(*k, g.block);
+  pj.k = k;
+  pj.block = g.block;
+  pj.slab = g.slab;
+  ctx->pair_kernels.emplace(h, pj);
+  return pj;
+}
+
+// Inspection without a device: the source of the kernel a batched x batched contraction of these structures would
+// run (compiled with NVRTC so that a code-generation error shows up where no GPU exists).  Empty = generic kernel.
+std::string pair_jit_source(const Structure& sa, int dtype_a, int layout_a, const Structure& sb, int dtype_b, int layout_b) {
+  spn_tensor a, b, r;
+  auto fake = [](spn_tensor& t, const Structure& st, int dtype, int layout) {
+    t.st = st;
+    t.storage = SPN_STORAGE_BATCHED;
+    t.dtype = dtype;
+    t.layout = layout;
+    t.n_points = 4096;
+    t.dptr = reinterpret_cast<void*>(uintptr_t(1) << 20);  // never dereferenced: alignment only
+    t.owns = false;
+  };
+  fake(a, sa, dtype_a, layout_a);
+  fake(b, sb, dtype_b, layout_b);
+  spn_contract_plan plan = plan_contract(sa, sb);
+  KTables kt = build_k_tables(plan, false);
+  if (!pair_jit_applicable(plan, kt, &a, &b, true, 4096)) return std::string();
+  fake(r, structure_of_plan_result(plan), (dtype_a == SPN_F64 && dtype_b == SPN_F64) ? SPN_F64 : SPN_C64, layout_a);
+  JitKernel k;
+  k.name = "spn_pair_contract_inspect";
+  Generated g = generate(plan, kt, &a, &b, &r, k.name, true);
+  k.source = g.source;
+  jit_compile(k);
+  return g.source;
+}
+
+void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const spn_tensor* b, spn_tensor* res,
+                     uint64_t n_points) {
+  JitKernel& k = *pj.k;
+  // direct kernels: one thread per point; staged kernels: one warp per slab of 32 points
+  const uint64_t need = pj.slab ? ((n_points + 31) / 32 + (uint64_t)(pj.block / 32) - 1) / (uint64_t)(pj.block / 32)
+                                : (n_points + (uint64_t)pj.block - 1) / (uint64_t)pj.block;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm));
   const double* pa = static_cast<const double*>(a->dptr);
   const double* pb = static_cast<const double*>(b->dptr);
   double* pc = static_cast<double*>(res->dptr);
   unsigned long long csa = a->n_points, csb = b->n_points, csc = res->n_points, np = n_points;
   void* args[] = {&pa, &csa, &pb, &csb, &pc, &csc, &np};
-  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(kPairBlock), args, 0, ctx->stream),
+  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3((unsigned)pj.block), args, k.smem_bytes, ctx->stream),
              "launch specialised pairwise kernel");
   ctx->launches++;
-  return true;
 }
 
 }  // namespace spn

@@ -9,6 +9,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -16,6 +17,13 @@
 
 namespace spn {
 struct JitKernel;
+struct ContractEntry;  // api.cu: everything spn_tensor_contract derives from a pair of structures, built once
+// a specialised pairwise kernel (pairwise_jit.cu) with its launch shape
+struct PairJit {
+  std::shared_ptr<JitKernel> k;
+  int block = 0;      // threads per CTA
+  bool slab = false;  // staged: one warp per slab of 32 points (else one thread per point)
+};
 }
 
 struct spn_ctx {
@@ -25,7 +33,13 @@ struct spn_ctx {
   int sm_count = 148;
   bool emulate_reference_pairing = false;  // SURVEY K-note 3, see build_k_tables
   // specialised pairwise kernels (pairwise_jit.cu), keyed by a hash of (plan, storage, dtype, layout)
-  std::map<uint64_t, std::shared_ptr<spn::JitKernel>> pair_kernels;
+  std::map<uint64_t, spn::PairJit> pair_kernels;
+  // plan cache of the pairwise Contract path, keyed by the two operand structures (+ storage, dtype, layout,
+  // alignment, identity of a shared operand): merge plan, enumeration tables, device tables, kernel choice.
+  // The reference re-derives all of it on every a.contract(&b) (contraction.rs:126-207); here a repeated contraction
+  // costs one hash lookup, one stream-ordered allocation and one launch.
+  std::unordered_map<std::string, std::shared_ptr<spn::ContractEntry>> contract_cache;
+  uint64_t contract_cache_hits = 0, contract_cache_misses = 0;
   // sticky status words (pinned host memory) of the communicators created on this context (comm.cu): non-zero after
   // an exchange timed out; checked by spn_ctx_synchronize
   std::vector<const int*> comm_status;
@@ -45,6 +59,7 @@ struct spn_tensor {
   // shared tensors: host copies (canonical row major)
   std::vector<double2> host_dense;
   std::map<uint64_t, double2> entries;  // sparse only, keyed (and therefore sorted) by flat index
+  uint64_t uid = 0;  // shared tensors: process-unique identity (they are immutable), part of the plan-cache key
 
   uint64_t size() const { return st.size(); }
   size_t elem_bytes() const { return dtype == SPN_C64 ? 16 : 8; }
@@ -125,9 +140,14 @@ spn_tensor* new_shared_dense(spn_ctx* ctx, const Structure& st, const double2* d
 spn_tensor* new_shared_sparse(spn_ctx* ctx, const Structure& st, const std::map<uint64_t, double2>& entries);
 spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, int dtype, int layout, void* wrap);
 
-// pairwise_jit.cu: launch a kernel specialised for this contraction (small per-point tensors); false = not applicable
-bool contract_small_jit(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
-                        const spn_tensor* b, spn_tensor* res, uint64_t n_points);
+// pairwise_jit.cu: kernels specialised for one contraction of small per-point tensors
+bool pair_jit_applicable(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b,
+                         bool res_batched, uint64_t n_points);
+PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
+                       const spn_tensor* b, const spn_tensor* res);
+void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const spn_tensor* b, spn_tensor* res,
+                     uint64_t n_points);
+std::string pair_jit_source(const Structure& sa, int dtype_a, int layout_a, const Structure& sb, int dtype_b, int layout_b);
 
 // comm.cu: fold the per-CTA partials (or take inout as the local sum when partial == nullptr) and exchange with
 // the peers in one launch on the context's stream

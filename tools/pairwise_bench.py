@@ -57,6 +57,46 @@ cases.append(("dense[bis,bis] x dense[bis] -> [bis]              (K1)", lambda: 
 cases.append(("dense[bis,bis] + dense[bis,bis]              (add)", lambda: M1 + M1, 3 * 16 * 16))
 W, sw = rand_batch([b(1), b(2)])
 cases.append(("dense[bis,bis] x dense[bis,bis] -> scalar (multi, K5)", lambda: M1.contract(W), (s1 + sw + 1) * 16))
+# shapes outside the specialised-kernel thresholds: table-driven generic kernel / CSR gather
+co = lambda a: sp.ColorAdjoint.new_slot(8, a)
+D3, sd3 = rand_batch([co(1), co(2), co(3)])
+D2, sd2 = rand_batch([co(3), co(4)])
+cases.append(("dense[coad^3] x dense[coad^2] -> [coad^3]  (generic dense)", lambda: D3.contract(D2), (sd3 + sd2 + 512) * 16))
+from spenso_b200 import workloads  # noqa: E402
+F = sp.SparseTensor.from_entries(ctx, [co(1), co(2), co(4)], workloads.su3_f())
+cases.append(("dense[coad^3] x sparse f (shared) -> [coad^2]  (CSR gather)", lambda: D3.contract(F), (sd3 + 64) * 16))
 for name, fn, bytes_pp in cases:
     ms, r = timeit(fn)
     print(f"{name:62s} {ms*1e3:8.1f} us  {bytes_pp*n/ms/1e6:7.0f} GB/s  ({bytes_pp} B/point)", flush=True)
+del cases, r
+
+# host cost of one a.contract(b) call (Python + ctypes + plan-cache lookup + allocation + launch): small batches, so
+# that the device is never the bottleneck and the launch queue never fills
+n_small = 4096
+n_keep, n = n, n_small
+a_s, _ = rand_batch([b(1), b(2)])
+b_s, _ = rand_batch([b(2), b(3)])
+for _ in range(200):
+    r = a_s.contract(b_s)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+N = 5000
+for _ in range(N):
+    r = a_s.contract(b_s)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+import ctypes as C  # noqa: E402
+from spenso_b200._capi import lib  # noqa: E402
+h, m_, e_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
+lib().spn_ctx_plan_cache_stats(ctx.h, C.byref(h), C.byref(m_), C.byref(e_))
+# the C call alone (no Python object construction around it)
+out = C.c_void_p()
+t2 = time.perf_counter()
+for _ in range(N):
+    lib().spn_tensor_contract(ctx.h, a_s.h, b_s.h, C.byref(out))
+    lib().spn_tensor_free(out)
+t3 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"host cost per a.contract(b) call at {n_small} points: {(t1 - t0) / N * 1e6:.1f} us through the Python mirror, "
+      f"{(t3 - t2) / N * 1e6:.1f} us for spn_tensor_contract + spn_tensor_free through ctypes; "
+      f"plan cache: {h.value} hits, {m_.value} misses, {e_.value} entries", flush=True)
