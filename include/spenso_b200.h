@@ -240,6 +240,17 @@ int spn_net_leaf_library_custom(spn_net* net, const spn_slot* slots, uint32_t n,
 int spn_net_leaf_scalar(spn_net* net, double re, double im);
 int spn_net_op(spn_net* net, int op, const int32_t* children, uint32_t n_children, int32_t power);
 int spn_net_set_root(spn_net* net, int node);
+/* The HOST's contraction order (north_star: "the Rust host resolves ... contraction order ... on the CPU exactly as
+ * today").  pairs[2k], pairs[2k+1] = (n1, n2) of the k-th pairwise contraction in the reference's own naming: a factor
+ * of a Product is known by its node id, and the result of n1.contract(n2) takes the place and the id of n1 — the graph
+ * surgery of SingleSmallestDegree::contract (spenso/src/network/contract.rs:346-497: replace n1 by the result leaf,
+ * delete n2).  A (LibraryKey, LocalTensor) pair runs as local.contract(lib), like contract.rs:428-443.  Entries are
+ * global and ordered; each must name two current factors of one Product when its turn comes (compile fails with
+ * SPN_ERR_INVALID otherwise).  Factors a schedule leaves over (scalars, which ContractScalars folds without a log
+ * entry) are multiplied in by the default rule.  With a schedule set the fused compiler does not search for a cheaper
+ * order.  n_pairs = 0 removes the schedule.  spn_net_schedule returns the order of a compiled network in the same
+ * naming, so that one network's schedule can be replayed on another. */
+int spn_net_set_schedule(spn_net* net, const int32_t* pairs, uint32_t n_pairs);
 /* Plan interchange: the expression graph as JSON text (format: csrc/net.cu).  A host that owns
  * the real spenso Network (graph + store derive serde, spenso/src/network.rs:33-51, network/graph.rs:39-58) can
  * emit this text instead of making one call per node.  to_json returns a string owned by net (valid until the
@@ -256,7 +267,8 @@ uint32_t spn_net_result_order(const spn_net* net);
 int spn_net_result_slots(const spn_net* net, spn_slot* out);
 uint64_t spn_net_result_size(const spn_net* net);
 uint32_t spn_net_n_inputs(const spn_net* net);
-/* number of pairwise contractions in the schedule and (a,b) node pairs in execution order */
+/* number of pairwise contractions in the schedule and the (n1, n2) node-id pairs in execution order, in the naming of
+ * spn_net_set_schedule (the result of a contraction is known by the id of n1) */
 int spn_net_schedule(const spn_net* net, int32_t* pairs, uint32_t cap);
 /* generated CUDA source of the fused kernel (NUL terminated; owned by net) */
 const char* spn_net_cuda_source(const spn_net* net);

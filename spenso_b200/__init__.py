@@ -579,6 +579,12 @@ class Network:
     def set_root(self, node):
         check(lib().spn_net_set_root(self.h, int(node)))
 
+    def set_schedule(self, pairs):
+        """The host's contraction order: [(n1, n2), ...] in the reference's naming — the result of n1.contract(n2) is
+        known by the id of n1 afterwards (spn_net_set_schedule; SingleSmallestDegree::contract, contract.rs:346-497)."""
+        buf = np.ascontiguousarray([int(x) for p in pairs for x in p], dtype=np.int32)
+        check(lib().spn_net_set_schedule(self.h, ptr(buf) if len(buf) else None, len(buf) // 2))
+
     # expression style of the reference: Network::from_tensor(a) * Network::from_tensor(b) + ... (network.rs:335-351, 585-607)
     def from_tensor(self, t, sl=None, dtype: int = C64) -> "NetExpr":
         """A leaf as an expression node: a shared tensor (DenseTensor / SparseTensor), or — given slots — a per-point

@@ -96,6 +96,7 @@ SYMBOLS = {
     "spn_net_leaf_scalar": (_I, [_P, _D, _D]),
     "spn_net_op": (_I, [_P, _I, _P, _U32, C.c_int32]),
     "spn_net_set_root": (_I, [_P, _I]),
+    "spn_net_set_schedule": (_I, [_P, _P, _U32]),
     "spn_net_to_json": (C.c_char_p, [_P]),
     "spn_net_from_json": (_I, [_P, C.c_char_p, C.POINTER(_P)]),
     "spn_net_compile": (_I, [_P, _I]),

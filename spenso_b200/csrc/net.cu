@@ -56,6 +56,7 @@ struct Node {
   std::vector<uint64_t> flat_map;
   int alias_of = -1;  // node id of the batched leaf this one re-indexes
   bool is_scalar_leaf = false;  // created by spn_net_leaf_scalar (NetworkLeaf::Scalar)
+  bool from_library = false;    // NetworkLeaf::LibraryKey (spn_net_leaf_library / _custom); else a LocalTensor
   // LEAF_FUNCTION: per-point tensor computed on the device from components of other batched leaves
   std::vector<std::pair<int, uint64_t>> fn_params;  // (leaf node id, canonical flat component)
   std::vector<double2> fn_consts;
@@ -90,7 +91,14 @@ struct spn_net {
   int exec_mode = SPN_EXEC_FUSED;
   std::vector<Value> values;
   std::vector<Step> steps;
-  std::vector<std::pair<int, int>> schedule;  // (node a, node b) of every pairwise contraction, -1 = intermediate
+  // (n1, n2) of every pairwise contraction in execution order, in the reference's naming: a factor of a product is
+  // known by its node id, and the result of n1.contract(n2) takes the place — and the id — of n1 (the graph surgery of
+  // SingleSmallestDegree::contract, network/contract.rs:346-497, which the oracle's contraction log records too)
+  std::vector<std::pair<int, int>> schedule;
+  // the HOST's contraction order (spn_net_set_schedule): the same naming; consumed by schedule_product
+  std::vector<std::pair<int, int>> host_schedule;
+  std::vector<char> host_used;
+  bool has_host_schedule = false;
   int result_value = -1;
   std::map<int, int> node_value;  // node id -> value id of the compiled schedule
   std::vector<int> input_nodes_all;  // ids of every LEAF_BATCHED node, including re-indexed views
@@ -163,10 +171,9 @@ struct spn_net {
     steps.push_back({op, dst, a, b});
     return dst;
   }
-  int emit_contract(int a, int b) {
+  int emit_contract(int a, int b, int name_a = -1, int name_b = -1) {
     spn_contract_plan p = plan_contract(values[a].st, values[b].st);
-    int la = values[a].leaf, lb = values[b].leaf;
-    schedule.emplace_back(la, lb);
+    schedule.emplace_back(name_a, name_b);
     return emit(ST_CONTRACT, a, b, structure_of_plan_result(p));
   }
   static bool same_structure(const Structure& a, const Structure& b) {
@@ -201,12 +208,40 @@ struct spn_net {
     rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
     return (double)(rng_state >> 11) / 9007199254740992.0;
   }
-  int schedule_product(std::vector<int> vals) {
+  // `names[i]`: the node id factor i is known by (see `schedule`)
+  int schedule_product(std::vector<int> vals, std::vector<int> names) {
     if (vals.empty()) throw Error(SPN_ERR_INVALID, "empty product");
     struct Cand {
       size_t i, j;
       std::array<double, 3> cost;
     };
+    auto contract_pair = [&](size_t bi, size_t bj) {
+      // n1.contract(n2), except (LibraryKey, LocalTensor), which the reference runs as local.contract(lib)
+      // (contract.rs:428-443) — the operand order decides the rounding of the pairwise kernels
+      int a = vals[bi], b = vals[bj];
+      auto is_lib = [&](int v) { return values[(size_t)v].leaf >= 0 && nodes[(size_t)values[(size_t)v].leaf].from_library; };
+      auto is_local = [&](int v) { return values[(size_t)v].leaf < 0 || !nodes[(size_t)values[(size_t)v].leaf].from_library; };
+      if (has_host_schedule && is_lib(a) && is_local(b) && !values[(size_t)b].scalar_kind) std::swap(a, b);
+      int r = emit_contract(a, b, names[bi], names[bj]);
+      vals[bi] = r;
+      vals.erase(vals.begin() + (long)bj);
+      names.erase(names.begin() + (long)bj);
+    };
+    if (has_host_schedule) {
+      // replay the host's order: entries are global; the ones naming two current factors of THIS product are taken in
+      // sequence (a result keeps the id of its first operand)
+      for (size_t h = 0; h < host_schedule.size(); ++h) {
+        if (host_used[h]) continue;
+        size_t bi = names.size(), bj = names.size();
+        for (size_t i = 0; i < names.size(); ++i) {
+          if (names[i] == host_schedule[h].first && bi == names.size()) bi = i;
+          if (names[i] == host_schedule[h].second && bj == names.size()) bj = i;
+        }
+        if (bi == names.size() || bj == names.size() || bi == bj) continue;  // belongs to another product
+        host_used[h] = 1;
+        contract_pair(bi, bj);
+      }
+    }
     while (vals.size() > 1) {
       size_t bi = 0, bj = 1;
       std::vector<Cand> cands;
@@ -248,9 +283,7 @@ struct spn_net {
         bi = std::min(idx[0], idx[1]);
         bj = std::max(idx[0], idx[1]);
       }
-      int r = emit_contract(vals[bi], vals[bj]);
-      vals[bi] = r;
-      vals.erase(vals.begin() + (long)bj);
+      contract_pair(bi, bj);
     }
     return vals[0];
   }
@@ -293,7 +326,7 @@ struct spn_net {
             vals.push_back(build(c, memo));
             all_scalars = all_scalars && values[(size_t)vals.back()].scalar_kind;
           }
-          v = schedule_product(vals);
+          v = schedule_product(vals, kids);
           if (all_scalars && kids.size() > 1) values[(size_t)v].scalar_kind = true;
           break;
         }
@@ -342,7 +375,7 @@ struct spn_net {
               break;
             }
             v = c;
-            for (int k = 1; k < np; ++k) v = emit_contract(v, c);
+            for (int k = 1; k < np; ++k) v = emit_contract(v, c, n.children[0], n.children[0]);
             if (pw < 0) v = emit(ST_RECIP, v, -1, values[(size_t)v].st);
             values[(size_t)v].scalar_kind = true;
             break;
@@ -355,12 +388,13 @@ struct spn_net {
             v = c;
             break;
           }
-          int square = emit_contract(c, c);
+          const int nm = n.children[0];
+          int square = emit_contract(c, c, nm, nm);
           if (np % 2 == 1) {
             v = c;
             if (np != 1) {
-              for (int k = 0; k < np / 2; ++k) square = emit_contract(square, square);
-              v = emit_contract(square, c);
+              for (int k = 0; k < np / 2; ++k) square = emit_contract(square, square, nm, nm);
+              v = emit_contract(square, c, nm, nm);
             }
             if (pw < 0) {
               if (values[(size_t)v].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "negative exponent on a non-scalar");
@@ -370,7 +404,7 @@ struct spn_net {
           } else {
             if (values[(size_t)square].st.order() != 0) throw Error(SPN_ERR_STRUCTURE, "even power of a tensor is not a scalar");
             v = square;
-            for (int k = 1; k < np / 2; ++k) v = emit_contract(v, square);
+            for (int k = 1; k < np / 2; ++k) v = emit_contract(v, square, nm, nm);
             if (pw < 0) v = emit(ST_RECIP, v, -1, values[(size_t)v].st);
             values[(size_t)v].scalar_kind = true;
           }
@@ -1328,7 +1362,9 @@ int spn_net_leaf_library(spn_net* net, int which, const spn_slot* slots, uint32_
   LibraryData d = builtin_library(which, args);
   Structure st;
   auto ent = instantiate_library(d, args, &st);
-  return add_const_leaf(net, st, ent, true, nullptr);
+  const int id = add_const_leaf(net, st, ent, true, nullptr);
+  net->nodes.back().from_library = true;
+  return id;
   NET_CATCH(true)
 }
 int spn_net_leaf_library_custom(spn_net* net, const spn_slot* slots, uint32_t n, const uint64_t* flat,
@@ -1345,7 +1381,9 @@ int spn_net_leaf_library_custom(spn_net* net, const spn_slot* slots, uint32_t n,
   }
   Structure st;
   auto ent = instantiate_library(d, args, &st);
-  return add_const_leaf(net, st, ent, true, nullptr);
+  const int id = add_const_leaf(net, st, ent, true, nullptr);
+  net->nodes.back().from_library = true;
+  return id;
   NET_CATCH(true)
 }
 int spn_net_leaf_scalar(spn_net* net, double re, double im) {
@@ -1372,6 +1410,21 @@ int spn_net_op(spn_net* net, int op, const int32_t* children, uint32_t n_childre
   net->nodes.push_back(std::move(nd));
   return (int)net->nodes.size() - 1;
   NET_CATCH(true)
+}
+int spn_net_set_schedule(spn_net* net, const int32_t* pairs, uint32_t n_pairs) {
+  NET_TRY
+  check_uncompiled(net);
+  if (n_pairs && !pairs) throw Error(SPN_ERR_INVALID, "set_schedule: null pair list");
+  net->host_schedule.clear();
+  for (uint32_t k = 0; k < n_pairs; ++k) {
+    const int a = pairs[2 * k], b = pairs[2 * k + 1];
+    if (a < 0 || b < 0 || a >= (int)net->nodes.size() || b >= (int)net->nodes.size() || a == b)
+      throw Error(SPN_ERR_INVALID, "set_schedule: a pair must name two different existing nodes");
+    net->host_schedule.emplace_back(a, b);
+  }
+  net->has_host_schedule = n_pairs > 0;
+  return SPN_OK;
+  NET_CATCH(false)
 }
 int spn_net_set_root(spn_net* net, int node) {
   NET_TRY
@@ -1431,7 +1484,8 @@ const char* spn_net_to_json(spn_net* net) {
     } else if (n.kind == LEAF_CONST && n.is_scalar_leaf) {
       o << "{\"kind\":\"scalar\",\"re\":" << jlit(n.dense[0].x) << ",\"im\":" << jlit(n.dense[0].y) << "}";
     } else if (n.kind == LEAF_CONST) {
-      o << "{\"kind\":\"tensor\",\"sparse\":" << (n.sparse ? "true" : "false") << ",\"slots\":";
+      o << "{\"kind\":\"tensor\",\"sparse\":" << (n.sparse ? "true" : "false") << (n.from_library ? ",\"library\":true" : "")
+        << ",\"slots\":";
       json_slots(o, n.st.slots);
       o << ",\"entries\":[";
       bool first = true;
@@ -1450,7 +1504,14 @@ const char* spn_net_to_json(spn_net* net) {
       o << "]}";
     }
   }
-  o << "\n],\"root\":" << net->root << "}\n";
+  o << "\n],\"root\":" << net->root;
+  if (net->has_host_schedule) {   // the host's contraction order (spn_net_set_schedule)
+    o << ",\"schedule\":[";
+    for (size_t k = 0; k < net->host_schedule.size(); ++k)
+      o << (k ? "," : "") << "[" << net->host_schedule[k].first << "," << net->host_schedule[k].second << "]";
+    o << "]";
+  }
+  o << "}\n";
   net->json = o.str();
   return net->json.c_str();
 }
@@ -1494,6 +1555,8 @@ int spn_net_from_json(spn_ctx* ctx, const char* text, spn_net** out) {
         if (!sparse && ent.size() != st.size()) throw Error(SPN_ERR_DIMENSION, "plan json: dense tensor needs every entry");
         id = add_const_leaf(net.get(), st, ent, sparse, nullptr);
         if (!sparse) net->nodes.back().entries.clear();
+        const JVal* lj = jn.find("library");
+        net->nodes.back().from_library = lj && lj->kind == JVal::Bool && lj->b;
       } else if (kind == "function") {
         auto sl = slots_of_json(jn.at("slots"));
         std::vector<int32_t> params, code;
@@ -1528,6 +1591,16 @@ int spn_net_from_json(spn_ctx* ctx, const char* text, spn_net** out) {
     check_uncompiled(net.get());
     int rc = spn_net_set_root(net.get(), (int)doc.at("root").i64());
     if (rc) throw Error(rc, spn_last_error());
+    if (const JVal* sj = doc.find("schedule")) {
+      std::vector<int32_t> pairs;
+      for (auto& e : sj->arr()) {
+        if (e.arr().size() != 2) throw Error(SPN_ERR_INVALID, "plan json: a schedule entry is [n1, n2]");
+        pairs.push_back((int32_t)e.arr()[0].i64());
+        pairs.push_back((int32_t)e.arr()[1].i64());
+      }
+      rc = spn_net_set_schedule(net.get(), pairs.data(), (uint32_t)pairs.size() / 2);
+      if (rc) throw Error(rc, spn_last_error());
+    }
     *out = net.release();
   } catch (const Error&) {
     throw;
@@ -1560,6 +1633,7 @@ int spn_net_compile(spn_net* net, int exec_mode) {
         net->schedule.clear();
         net->prog = Program();
         net->trial = 0;
+        net->host_used.assign(net->host_schedule.size(), 0);
         std::map<int, int> memo;
         net->result_value = net->build(net->root, memo);
         net->node_value = memo;
@@ -1583,13 +1657,19 @@ int spn_net_compile(spn_net* net, int exec_mode) {
     net->result_el.clear();
     net->trial = trial;
     net->rng_state = 0x9e3779b97f4a7c15ull * (uint64_t)(trial + 1);
+    net->host_used.assign(net->host_schedule.size(), 0);
     std::map<int, int> memo;
     net->result_value = net->build(net->root, memo);
     net->node_value = memo;
     if (exec_mode == SPN_EXEC_FUSED) net->compile_fused();
   };
   build_with(0);
-  if (exec_mode == SPN_EXEC_FUSED) {
+  for (size_t h = 0; h < net->host_schedule.size(); ++h)
+    if (!net->host_used[h])
+      throw Error(SPN_ERR_INVALID, "set_schedule: pair " + std::to_string(h) + " (" + std::to_string(net->host_schedule[h].first) +
+                                       ", " + std::to_string(net->host_schedule[h].second) +
+                                       ") does not name two factors of one product at that point of the order");
+  if (exec_mode == SPN_EXEC_FUSED && !net->has_host_schedule) {   // the host's order is law: no search
     // schedule search: the objective is the instruction count of the kernel that would be generated
     int trials = 256;
     if (const char* e = getenv("SPN_SCHEDULE_TRIALS")) trials = atoi(e);

@@ -74,8 +74,9 @@ class NetSpec:
         return self.add("op", OP_POWER, [c], n)
 
 
-def build_engine(spec: NetSpec, ctx, mode: int = FUSED) -> Network:
-    """NetSpec -> compiled spenso_b200.Network (ctx may be None for a plan-only network)."""
+def build_engine(spec: NetSpec, ctx, mode: int = FUSED, schedule=None) -> Network:
+    """NetSpec -> compiled spenso_b200.Network (ctx may be None for a plan-only network).  `schedule`: the host's
+    contraction order as (n1, n2) pairs of SPEC node indices (Network.set_schedule naming)."""
     net = Network(ctx)
     ids: Dict[int, int] = {}
     for k, node in enumerate(spec.nodes):
@@ -97,6 +98,9 @@ def build_engine(spec: NetSpec, ctx, mode: int = FUSED) -> Network:
         else:
             ids[k] = net.op(node[1], [ids[c] for c in node[2]], node[3])
     net.set_root(ids[spec.root])
+    net.spec_ids = ids
+    if schedule is not None:
+        net.set_schedule([(ids[a], ids[b]) for a, b in schedule])
     net.compile(mode)
     return net
 

@@ -503,7 +503,21 @@ def net_from_spec(spec, arrays, point: int = 0):
         else:
             ids[k] = net.op(node[1], [ids[c] for c in node[2]], node[3])
     net.set_root(ids[spec.root])
+    net.spec_ids = ids
     return net, b_nodes, b_arrays
+
+
+def oracle_schedule(spec, arrays=None):
+    """The contraction order the oracle's restatement of SmallestDegree / SingleSmallestDegree (contract.rs:239-497)
+    chooses for a NetSpec, as (n1, n2) pairs of SPEC node indices in execution order — the naming of the reference's
+    graph surgery: the result of n1.contract(n2) is known by n1 afterwards.  This is what a Rust host would hand to
+    spn_net_set_schedule."""
+    if arrays is None:
+        arrays = [np.ones((1, size), dtype=np.complex128) for _, size in spec.inputs]
+    net, _, _ = net_from_spec(spec, arrays, 0)
+    net.execute()
+    back = {v: k for k, v in net.spec_ids.items()}
+    return [(back[a], back[b]) for a, b in net.log()]
 
 
 def eval_spec(spec, arrays, n_threads: int = 1, want_out: bool = True):

@@ -301,3 +301,58 @@ def test_non_finite_constants_compile_and_round_trip():
     nan.set_root(nan.sum(nan.product(nan.scalar(complex(0.0, float("nan"))), y), y))
     assert "NaN" in nan.to_json()
     assert sp.Network.from_json(None, nan.to_json()).to_json() == nan.to_json()
+
+
+# ---- host-driven contraction order (spn_net_set_schedule) ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg5", "gl03"])
+def test_host_schedule_is_replayed_literally(name):
+    """The order the oracle's SmallestDegree restatement picks (its contraction log = what a Rust host would send) is
+    replayed pair by pair, in both execution modes, and the engine reports it back in the same naming."""
+    spec = workloads.WORKLOADS[name]()
+    want = O.oracle_schedule(spec)
+    assert len(want) >= 1
+    for mode in (sp.STEPWISE, sp.FUSED):
+        net = workloads.build_engine(spec, None, mode, schedule=want)
+        got = net.schedule
+        mapped = [(net.spec_ids[a], net.spec_ids[b]) for a, b in want]
+        # the host's pairs come first and in order; what it leaves over (scalar factors, which ContractScalars folds
+        # without a log entry) is multiplied in afterwards
+        hosted = [p for p in got if p in mapped]
+        assert hosted == mapped, (got, mapped)
+        assert net.result_size == workloads.build_engine(spec, None, mode).result_size
+
+
+def test_schedule_round_trips_between_networks_and_through_json():
+    spec = workloads.one_loop_massive()
+    a = workloads.build_engine(spec, None, sp.FUSED)
+    sched = a.schedule                                   # the engine's own (searched) order, engine node ids
+    b = sp.Network.from_json(None, a.to_json())
+    b.set_schedule(sched)
+    text = b.to_json()
+    assert '"schedule":[[' in text
+    b.compile(sp.FUSED)
+    assert b.schedule == sched
+    assert b.fp64_instr_per_point == a.fp64_instr_per_point and b.cuda_source == a.cuda_source
+    c = sp.Network.from_json(None, text).compile(sp.STEPWISE)          # the schedule travels inside the plan text
+    assert c.schedule == sched
+
+
+def test_schedule_errors():
+    # two factors without a common index are a legal step (an exterior product), so that compiles ...
+    outer = workloads.build_engine(workloads.eemumu(), None, sp.STEPWISE, schedule=[(0, 1)])
+    assert outer.schedule[0] == (outer.spec_ids[0], outer.spec_ids[1])
+    # ... a pair that names something that is not a factor of one product does not
+    net = sp.Network(None)
+    x = net.batched([sp.Bispinor.new_slot(4, 1)])
+    y = net.batched([sp.Bispinor.new_slot(4, 1)])
+    z = net.batched([sp.Bispinor.new_slot(4, 2)])
+    s = net.sum(net.product(x, y), net.scalar(1.0))
+    net.set_root(net.product(s, z, z))
+    net.set_schedule([(x, z)])                           # x belongs to the inner product, z to the outer one
+    with pytest.raises(sp.SpensoError) as e:
+        net.compile(sp.STEPWISE)
+    assert e.value.code == 7 and "does not name two factors" in str(e.value)
+    with pytest.raises(sp.SpensoError):
+        net.set_schedule([(x, x)])
+    with pytest.raises(sp.SpensoError):
+        net.set_schedule([(x, 999)])

@@ -1021,3 +1021,79 @@ def test_trace_rejects_a_slot_list_that_is_not_the_tensors(ctx):
     assert e.value.code == 3
     with pytest.raises(sp.SpensoError):
         t.trace([])
+
+
+# ---- host-driven contraction order and plan interchange on the device ------------------------------------------------
+@pytest.mark.parametrize("name,scale,real", [("cfg1", 1.0, True), ("cfg2", 1.0, False), ("cfg3", 1.0, False),
+                                             ("cfg5", 100.0, True)])
+def test_host_schedule_executes_like_the_oracle(ctx, name, scale, real):
+    """The contraction order comes from the host (here: the oracle's restatement of SmallestDegree, i.e. what the Rust
+    side would send through spn_net_set_schedule).  Stepwise execution then runs the SAME pairwise contractions in the
+    SAME order with the reference's rounding, so where no scalar factor is folded in between the results are
+    bit-identical to the oracle's per-point evaluation; the fused kernel agrees to 1e-12."""
+    spec = workloads.WORKLOADS[name]()
+    n = 257
+    arrays = workloads.synthetic_inputs(spec, n, 77, scale=scale, real=real)
+    sched = O.oracle_schedule(spec, arrays)
+    ref, _, _ = O.eval_spec(spec, arrays)
+    for mode in (sp.STEPWISE, sp.FUSED):
+        net = workloads.build_engine(spec, ctx, mode, schedule=sched)
+        inputs = []
+        for node, a in zip([x for x in spec.nodes if x[0] == "batched"], arrays):
+            t = sp.BatchTensor.empty(ctx, node[1], n)
+            t.upload(a)
+            inputs.append(t)
+        got = net.evaluate(inputs).to_numpy().reshape(n, -1)
+        assert rel_err(got, ref) <= TOL
+        if mode == sp.STEPWISE and name in ("cfg1", "cfg2"):
+            assert np.array_equal(got, ref), np.abs(got - ref).max()
+
+
+@pytest.mark.parametrize("mode", [sp.FUSED, sp.STEPWISE])
+def test_network_from_json_executes(ctx, mode):
+    """Plan interchange: a network rebuilt from its JSON text — graph, library tensors, host schedule —
+    gives the same bits as the network it was written from."""
+    spec = workloads.one_loop_massive()
+    n = 500
+    arrays = workloads.synthetic_inputs(spec, n, 5, scale=100.0, real=True)
+    sched = O.oracle_schedule(spec, arrays)
+    a = workloads.build_engine(spec, ctx, mode, schedule=sched)
+    text = a.to_json()                                  # what a host would emit: graph + its contraction order
+    b = sp.Network.from_json(ctx, text).compile(mode)
+    assert b.schedule == a.schedule and b.result_size == a.result_size
+    inputs = []
+    for node, arr in zip([x for x in spec.nodes if x[0] == "batched"], arrays):
+        t = sp.BatchTensor.empty(ctx, node[1], n)
+        t.upload(arr)
+        inputs.append(t)
+    ra = a.evaluate(inputs).to_numpy()
+    rb = b.evaluate(inputs).to_numpy()
+    assert np.array_equal(ra, rb)
+    ref, _, _ = O.eval_spec(spec, arrays)
+    assert rel_err(rb.reshape(n, -1), ref) <= TOL
+
+
+def test_plan_cache_serves_repeated_contractions(ctx):
+    """spn_tensor_contract derives merge plan, tables and kernel once per pair of structures: a repeated a.contract(b)
+    is a cache hit and returns the same bits; another structure is a miss."""
+    import ctypes as C
+    from spenso_b200._capi import lib
+
+    def stats():
+        h, m, e = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().spn_ctx_plan_cache_stats(ctx.h, C.byref(h), C.byref(m), C.byref(e))
+        return h.value, m.value, e.value
+
+    rng = np.random.default_rng(3)
+    for n_points in (100, 5000):                      # generic kernel / specialised kernel
+        a, _, da = dense_pair(ctx, rng, O.slots(("bis", 4, 1), ("bis", 4, 2)), n_points)
+        b, _, db = dense_pair(ctx, rng, O.slots(("bis", 4, 2), ("bis", 4, 3)), n_points)
+        h0, m0, _ = stats()
+        r1 = a.contract(b).to_numpy()
+        h1, m1, _ = stats()
+        r2 = a.contract(b).to_numpy()
+        h2, m2, _ = stats()
+        assert m1 == m0 + 1 and h2 == h1 + 1 and m2 == m1
+        assert np.array_equal(r1, r2)
+        want = np.einsum("pij,pjk->pik", da, db)
+        assert rel_err(r1, want) <= TOL

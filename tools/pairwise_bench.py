@@ -57,8 +57,23 @@ cases.append(("dense[bis,bis] x dense[bis] -> [bis]              (K1)", lambda: 
 cases.append(("dense[bis,bis] + dense[bis,bis]              (add)", lambda: M1 + M1, 3 * 16 * 16))
 W, sw = rand_batch([b(1), b(2)])
 cases.append(("dense[bis,bis] x dense[bis,bis] -> scalar (multi, K5)", lambda: M1.contract(W), (s1 + sw + 1) * 16))
+# control: what this box's HBM gives a plain torch kernel of the same shape as the element-wise add (2 reads + 1 write)
+xa = torch.rand(n * 32, dtype=torch.float64, device="cuda")
+xb = torch.rand(n * 32, dtype=torch.float64, device="cuda")
+xc = torch.empty_like(xa)
+ms_ctl, _ = timeit(lambda: torch.add(xa, xb, out=xc))
+print(f"{'control: torch.add of the same 768 B/point':62s} {ms_ctl*1e3:8.1f} us  {768*n/ms_ctl/1e6:7.0f} GB/s", flush=True)
+ms_ctl, _ = timeit(lambda: xc.copy_(xa))
+print(f"{'control: torch copy, 512 B/point':62s} {ms_ctl*1e3:8.1f} us  {512*n/ms_ctl/1e6:7.0f} GB/s", flush=True)
+del xa, xb, xc
+for name, fn, bytes_pp in cases:
+    ms, r = timeit(fn)
+    print(f"{name:62s} {ms*1e3:8.1f} us  {bytes_pp*n/ms/1e6:7.0f} GB/s  ({bytes_pp} B/point)", flush=True)
+del r
 # shapes outside the specialised-kernel thresholds: table-driven generic kernel / CSR gather
+cases = []
 co = lambda a: sp.ColorAdjoint.new_slot(8, a)
+n_keep0, n = n, min(n, 1 << 18)
 D3, sd3 = rand_batch([co(1), co(2), co(3)])
 D2, sd2 = rand_batch([co(3), co(4)])
 cases.append(("dense[coad^3] x dense[coad^2] -> [coad^3]  (generic dense)", lambda: D3.contract(D2), (sd3 + sd2 + 512) * 16))
