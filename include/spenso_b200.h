@@ -148,6 +148,10 @@ int spn_tensor_batched_wrap(spn_ctx* ctx, const spn_slot* slots, uint32_t n, uin
 int spn_tensor_shared_dense(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const double* reim, spn_tensor** out);
 int spn_tensor_shared_sparse(spn_ctx* ctx, const spn_slot* slots, uint32_t n, const uint64_t* flat,
                              const double* reim, uint64_t nnz, spn_tensor** out);
+/* A built-in library tensor with concrete indices in argument order (SPN_LIB_*, see below), as a shared sparse tensor
+ * in canonical slot order: get_lib_data + permute_inds (spenso/src/network/graph.rs:291-322, tensors/data/dense.rs:93-109)
+ * — what `T::from(lib_tensor_with_indices)` is in the blanket ExecuteOp impl (network.rs:1311-1318, 1437-1462). */
+int spn_tensor_library(spn_ctx* ctx, int which, const spn_slot* slots, uint32_t n, spn_tensor** out);
 void spn_tensor_free(spn_tensor* t);
 
 uint32_t spn_tensor_order(const spn_tensor* t);
@@ -182,6 +186,18 @@ int spn_tensor_add(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, int s
 int spn_tensor_neg(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
 int spn_tensor_scalar_mul(spn_ctx* ctx, const spn_tensor* a, double re, double im, spn_tensor** out);
 int spn_tensor_conj(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+/* element-wise 1/x: `Sc::ref_one() / s` of the Power op on scalars (network.rs:1526-1703) */
+int spn_tensor_recip(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+/* deep copy (trait Clone of the reference's tensors) */
+int spn_tensor_clone(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+/* DataTensor::to_dense / to_sparse (tensors/data/sparse.rs:688-708, dense.rs:523-535): to_sparse stores the values
+ * that differ from zero; batched tensors are dense (to_dense copies, to_sparse is SPN_ERR_INVALID). */
+int spn_tensor_to_dense(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+int spn_tensor_to_sparse(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+/* element access by canonical flat index (get_ref_linear / set_flat).  get on an absent sparse entry is
+ * SPN_ERR_EMPTY_SPARSE; set on a sparse tensor stores the value (zeros too).  Synchronous; reim = {re, im}. */
+int spn_tensor_get(const spn_tensor* t, uint64_t point, uint64_t flat, double* reim);
+int spn_tensor_set(spn_tensor* t, uint64_t point, uint64_t flat, double re, double im);
 /* Trace::internal_contract — contraction/trace.rs:12-83; slots may contain one repeated pair per call */
 int spn_tensor_trace(spn_ctx* ctx, const spn_slot* slots_with_repeats, uint32_t n, const spn_tensor* a,
                      spn_tensor** out);

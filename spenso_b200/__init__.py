@@ -25,7 +25,7 @@ from ._capi import SLOT_DTYPE, ContractPlan, SpensoError, build_library, check, 
 __all__ = [
     "Representation", "Euclidean", "Minkowski", "Lorentz", "Bispinor", "SpinFundamental", "ColorAdjoint",
     "ColorFundamental", "ColorSextet", "Slot", "slots", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
-    "Network", "NetExpr", "PeerComm", "SpensoError", "canonicalize", "plan_contract", "build_library",
+    "Network", "NetExpr", "PeerComm", "SpensoError", "canonicalize", "plan_contract", "build_library", "library_tensor",
     "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE", "AUTO",
 ]
 
@@ -287,6 +287,37 @@ class _Tensor:
         check(lib().spn_tensor_conj(self.ctx.h, self.h, C.byref(out)))
         return self._wrap(out)
 
+    def recip(self):
+        """element-wise 1/x (`ref_one() / s` of the Power op on scalars)"""
+        out = C.c_void_p()
+        check(lib().spn_tensor_recip(self.ctx.h, self.h, C.byref(out)))
+        return self._wrap(out)
+
+    def clone(self):
+        out = C.c_void_p()
+        check(lib().spn_tensor_clone(self.ctx.h, self.h, C.byref(out)))
+        return self._wrap(out)
+
+    def to_dense(self):
+        """DataTensor::to_dense (tensors/data/sparse.rs:688-708)."""
+        out = C.c_void_p()
+        check(lib().spn_tensor_to_dense(self.ctx.h, self.h, C.byref(out)))
+        return self._wrap(out)
+
+    def to_sparse(self):
+        """DenseTensor::to_sparse (tensors/data/dense.rs:523-535): values equal to zero are not stored."""
+        out = C.c_void_p()
+        check(lib().spn_tensor_to_sparse(self.ctx.h, self.h, C.byref(out)))
+        return self._wrap(out)
+
+    def get(self, flat: int, point: int = 0) -> complex:
+        v = np.zeros(2)
+        check(lib().spn_tensor_get(self.h, point, flat, ptr(v)))
+        return complex(v[0], v[1])
+
+    def set(self, flat: int, value: complex, point: int = 0):
+        check(lib().spn_tensor_set(self.h, point, flat, float(np.real(value)), float(np.imag(value))))
+
     def trace(self, slots_with_repeats) -> "_Tensor":
         """Trace::internal_contract over one repeated (slot, dual) pair; `slots_with_repeats` is this
         tensor's index list as the caller wrote it (data row major over it)."""
@@ -309,6 +340,14 @@ def _canonical_dense(sl, data, batch: bool):
         arr = arr.reshape(shape)
         arr = np.transpose(arr, axes=[int(p) for p in perm])
     return canon, np.ascontiguousarray(arr)
+
+
+def library_tensor(ctx: Context, which: int, sl) -> "_Tensor":
+    """A built-in hep_lib tensor with concrete indices (spn_tensor_library): shared sparse, canonical order."""
+    s = slots(sl)
+    out = C.c_void_p()
+    check(lib().spn_tensor_library(ctx.h, which, ptr(s), len(s), C.byref(out)))
+    return _Tensor(ctx, None)._wrap(out)
 
 
 class DenseTensor(_Tensor):

@@ -83,6 +83,13 @@ SYMBOLS = {
     "spn_tensor_neg": (_I, [_P, _P, C.POINTER(_P)]),
     "spn_tensor_scalar_mul": (_I, [_P, _P, _D, _D, C.POINTER(_P)]),
     "spn_tensor_conj": (_I, [_P, _P, C.POINTER(_P)]),
+    "spn_tensor_recip": (_I, [_P, _P, C.POINTER(_P)]),
+    "spn_tensor_clone": (_I, [_P, _P, C.POINTER(_P)]),
+    "spn_tensor_to_dense": (_I, [_P, _P, C.POINTER(_P)]),
+    "spn_tensor_to_sparse": (_I, [_P, _P, C.POINTER(_P)]),
+    "spn_tensor_get": (_I, [_P, _U64, _U64, _P]),
+    "spn_tensor_set": (_I, [_P, _U64, _U64, _D, _D]),
+    "spn_tensor_library": (_I, [_P, _I, _P, _U32, C.POINTER(_P)]),
     "spn_tensor_trace": (_I, [_P, _P, _U32, _P, C.POINTER(_P)]),
     "spn_tensor_reduce_points": (_I, [_P, _P, _P]),
     "spn_net_create": (_I, [_P, C.POINTER(_P)]),

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <memory>
 
+#include "library.hpp"
 #include "tensor.hpp"
 
 using namespace spn;
@@ -705,6 +706,18 @@ int spn_tensor_shared_sparse(spn_ctx* ctx, const spn_slot* slots, uint32_t n, co
   return SPN_OK;
   API_CATCH
 }
+// NetworkLeaf::LibraryKey -> tensor with concrete indices: get_lib_data + permute_inds (network/graph.rs:291-322,
+// tensors/data/dense.rs:93-109) for the built-in hep_lib tensors; index bookkeeping once, on the host
+int spn_tensor_library(spn_ctx* ctx, int which, const spn_slot* slots, uint32_t n, spn_tensor** out) {
+  API_TRY
+  std::vector<spn_slot> args(slots, slots + n);
+  LibraryData d = builtin_library(which, args);
+  Structure st;
+  auto ent = instantiate_library(d, args, &st);
+  *out = new_shared_sparse(ctx, st, ent);
+  return SPN_OK;
+  API_CATCH
+}
 void spn_tensor_free(spn_tensor* t) { delete t; }
 
 uint32_t spn_tensor_order(const spn_tensor* t) { return t->st.order(); }
@@ -826,6 +839,93 @@ int spn_tensor_scalar_mul(spn_ctx* ctx, const spn_tensor* a, double re, double i
 int spn_tensor_conj(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
   API_TRY
   tensor_elementwise(ctx, EW_CONJ, a, a, make_double2(0, 0), out);
+  return SPN_OK;
+  API_CATCH
+}
+
+int spn_tensor_recip(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  tensor_elementwise(ctx, EW_RECIP, a, a, make_double2(0, 0), out);
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_clone(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  if (a->batched()) {
+    std::unique_ptr<spn_tensor> r(new_batched(ctx, a->st, a->n_points, a->dtype, a->layout, nullptr));
+    cuda_check(cudaMemcpyAsync(r->dptr, a->dptr, a->n_points * a->size() * a->elem_bytes(), cudaMemcpyDeviceToDevice, ctx->stream),
+               "clone");
+    *out = r.release();
+  } else {
+    *out = a->sparse() ? new_shared_sparse(ctx, a->st, a->entries) : new_shared_dense(ctx, a->st, a->host_dense.data());
+  }
+  return SPN_OK;
+  API_CATCH
+}
+// DataTensor::to_dense / to_sparse (tensors/data/sparse.rs:688-708, dense.rs:523-535): index bookkeeping on the host
+// copies every shared tensor keeps, no arithmetic
+int spn_tensor_to_dense(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  if (a->batched()) return spn_tensor_clone(ctx, a, out);   // batched tensors are dense
+  *out = new_shared_dense(ctx, a->st, a->host_dense.data());
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_to_sparse(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
+  API_TRY
+  if (a->batched()) throw Error(SPN_ERR_INVALID, "to_sparse: a batched tensor is one DenseTensor per point");
+  std::map<uint64_t, double2> ent;
+  if (a->sparse()) {
+    ent = a->entries;
+  } else {
+    for (uint64_t f = 0; f < a->host_dense.size(); ++f)   // values equal to T::default() are not stored (dense.rs:529-532)
+      if (a->host_dense[f].x != 0.0 || a->host_dense[f].y != 0.0) ent[f] = a->host_dense[f];
+  }
+  *out = new_shared_sparse(ctx, a->st, ent);
+  return SPN_OK;
+  API_CATCH
+}
+// element access by canonical flat index: GetTensorData::get_ref_linear / SetTensorData::set_flat
+// (tensors/data/dense.rs, sparse.rs).  A sparse tensor reports an absent entry as SPN_ERR_EMPTY_SPARSE on get and
+// stores whatever is set (zeros included, like SparseTensor::set_flat).
+int spn_tensor_get(const spn_tensor* t, uint64_t point, uint64_t flat, double* reim) {
+  API_TRY
+  if (flat >= t->size()) throw Error(SPN_ERR_DIMENSION, "get: flat index out of bounds");
+  if (!t->batched()) {
+    if (point != 0) throw Error(SPN_ERR_INVALID, "get: shared tensors have one point");
+    if (t->sparse() && !t->entries.count(flat)) throw Error(SPN_ERR_EMPTY_SPARSE, "get: no stored entry at this index");
+    reim[0] = t->host_dense[flat].x;
+    reim[1] = t->host_dense[flat].y;
+    return SPN_OK;
+  }
+  if (point >= t->n_points) throw Error(SPN_ERR_INVALID, "get: point out of bounds");
+  const size_t eb = t->elem_bytes();
+  const uint64_t idx = t->layout == SPN_POINT_MAJOR ? point * t->size() + flat : flat * t->n_points + point;
+  reim[1] = 0.0;
+  cuda_check(cudaMemcpyAsync(reim, (const char*)t->dptr + idx * eb, eb, cudaMemcpyDeviceToHost, t->ctx->stream), "get");
+  cuda_check(cudaStreamSynchronize(t->ctx->stream), "get");
+  return SPN_OK;
+  API_CATCH
+}
+int spn_tensor_set(spn_tensor* t, uint64_t point, uint64_t flat, double re, double im) {
+  API_TRY
+  if (flat >= t->size()) throw Error(SPN_ERR_DIMENSION, "set: flat index out of bounds");
+  const double v[2] = {re, im};
+  if (!t->batched()) {
+    if (point != 0) throw Error(SPN_ERR_INVALID, "set: shared tensors have one point");
+    t->host_dense[flat] = make_double2(re, im);
+    if (t->sparse()) t->entries[flat] = make_double2(re, im);
+    t->uid = g_next_uid.fetch_add(1);   // the content is part of the identity the plan cache and the JIT kernels key on
+    cuda_check(cudaMemcpyAsync((char*)t->dptr + flat * sizeof(double2), v, sizeof(double2), cudaMemcpyHostToDevice, t->ctx->stream), "set");
+    cuda_check(cudaStreamSynchronize(t->ctx->stream), "set");
+    return SPN_OK;
+  }
+  if (point >= t->n_points) throw Error(SPN_ERR_INVALID, "set: point out of bounds");
+  if (t->dtype == SPN_F64 && im != 0.0) throw Error(SPN_ERR_INVALID, "set: complex value into an f64 tensor");
+  const size_t eb = t->elem_bytes();
+  const uint64_t idx = t->layout == SPN_POINT_MAJOR ? point * t->size() + flat : flat * t->n_points + point;
+  cuda_check(cudaMemcpyAsync((char*)t->dptr + idx * eb, v, eb, cudaMemcpyHostToDevice, t->ctx->stream), "set");
+  cuda_check(cudaStreamSynchronize(t->ctx->stream), "set");
   return SPN_OK;
   API_CATCH
 }

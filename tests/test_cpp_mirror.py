@@ -11,15 +11,32 @@ CPP = os.path.join(ROOT, "tests", "cpp")
 EXE = os.path.join(CPP, "reference_style_tests")
 
 
+BLANKET = os.path.join(CPP, "blanket_executor_test")
+
+
 def build_cpp_tests():
-    subprocess.check_call(
-        ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", EXE, os.path.join(CPP, "reference_style_tests.cpp"),
-         "-L" + os.path.join(ROOT, "spenso_b200"), "-lspenso_b200", "-Wl,-rpath," + os.path.join(ROOT, "spenso_b200")])
+    for exe, src in ((EXE, "reference_style_tests.cpp"), (BLANKET, "blanket_executor_test.cpp")):
+        subprocess.check_call(
+            ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", exe, os.path.join(CPP, src),
+             "-L" + os.path.join(ROOT, "spenso_b200"), "-lspenso_b200", "-Wl,-rpath," + os.path.join(ROOT, "spenso_b200")])
 
 
 def test_cpp_mirror_compiles_and_links():
     build_cpp_tests()
     assert subprocess.run([EXE, "--compile-check"]).returncode == 0
+    assert subprocess.run([BLANKET, "--compile-check"]).returncode == 0
+
+
+@pytest.mark.gpu
+def test_blanket_executor_call_sequence_over_the_c_abi():
+    """tests/cpp/blanket_executor_test.cpp: the reference's `impl ExecuteOp for NetworkStore<T, Sc>` (network.rs:1244-1706)
+    and SmallestDegree (network/contract.rs:43-498) restated with every trait method = one C-ABI call — the calls a
+    Rust shim would make — against the engine's own executor replaying that run's contraction order."""
+    build_cpp_tests()
+    r = subprocess.run([BLANKET], capture_output=True, text=True, timeout=600)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("... ok") == 5
 
 
 @pytest.mark.gpu

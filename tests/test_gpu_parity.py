@@ -1097,3 +1097,46 @@ def test_plan_cache_serves_repeated_contractions(ctx):
         assert np.array_equal(r1, r2)
         want = np.einsum("pij,pjk->pik", da, db)
         assert rel_err(r1, want) <= TOL
+
+
+def test_data_tensor_conversions_and_element_access(ctx):
+    """DataTensor::to_dense / to_sparse (tensors/data/sparse.rs:688-708, dense.rs:523-535), get / set by flat index,
+    clone, reciprocal, and library tensors with concrete indices (get_lib_data, network/graph.rs:291-322)."""
+    e = [sp.Euclidean.new_slot(3, 1), sp.Euclidean.new_slot(2, 2)]
+    d = sp.DenseTensor.from_data(ctx, e, [1, 0, 0, 2j, 0, 3])
+    s = d.to_sparse()
+    assert s.is_sparse and s.entries() == {0: 1, 3: 2j, 5: 3}              # zeros are not stored
+    back = s.to_dense()
+    assert not back.is_sparse and np.array_equal(back.to_numpy(), d.to_numpy())
+    assert s.get(3) == 2j and d.get(1) == 0
+    with pytest.raises(sp.SpensoError) as err:
+        s.get(1)                                                             # no stored entry there
+    assert err.value.code == 1
+    s.set(1, 0.0)                                                            # SparseTensor::set stores what it is given
+    assert s.entries()[1] == 0 and s.get(1) == 0
+    with pytest.raises(sp.SpensoError):
+        d.get(6)
+    # a set changes what the tensor contracts to (the plan cache keys shared tensors by identity + revision)
+    v = sp.DenseTensor.from_data(ctx, [sp.Euclidean.new_slot(2, 2)], [1, 1])
+    before = d.contract(v).to_numpy()
+    d.set(1, 5.0)
+    after = d.contract(v).to_numpy()
+    assert np.array_equal(before.reshape(-1), [1, 2j, 3]) and np.array_equal(after.reshape(-1), [6, 2j, 3])
+    # batched tensors: element access at a point, clone is a deep copy, to_sparse is refused
+    rng = np.random.default_rng(0)
+    for layout in (sp.POINT_MAJOR, sp.COMPONENT_MAJOR):
+        t, _, data = dense_pair(ctx, rng, O.slots(("bis", 4, 1), ("mink", 4, 2)), 37, layout)
+        assert t.get(7, point=11) == data[11].reshape(-1)[7]
+        c = t.clone()
+        t.set(7, 1 + 2j, point=11)
+        assert t.get(7, point=11) == 1 + 2j and c.get(7, point=11) == data[11].reshape(-1)[7]
+        assert np.array_equal(t.to_dense().to_numpy(), t.to_numpy())
+        with pytest.raises(sp.SpensoError):
+            t.to_sparse()
+    r = sp.BatchTensor.from_numpy(ctx, [], np.array([2.0, 4.0, 1j]).reshape(3)).recip().to_numpy()
+    assert np.allclose(r, [0.5, 0.25, -1j], rtol=0, atol=0)
+    # library tensor with concrete indices == the oracle's instantiation
+    b = lambda a: sp.Bispinor.new_slot(4, a)
+    g = sp.library_tensor(ctx, sp.LIB_GAMMA_WEYL, [b(2), b(1), sp.Minkowski.new_slot(4, 3)])
+    og = O.OLib.builtin(0).instantiate(O.slots(("bis", 4, 2), ("bis", 4, 1), ("mink", 4, 3)))
+    assert g.is_sparse and g.entries() == {k: complex(v) for k, v in og.entries().items()}
