@@ -7,6 +7,7 @@
 //!
 //! This crate is NOT compiled in the repository that ships libspenso_b200.so (its build image has no Rust
 //! toolchain); it is the binding a spenso maintainer adds.  See INTEGRATION.md.
+pub mod executor;
 pub mod sys;
 
 use std::ffi::CStr;
@@ -18,7 +19,7 @@ use spenso::structure::abstract_index::AbstractIndex;
 use spenso::structure::dimension::Dimension;
 use spenso::structure::representation::LibraryRep;
 use spenso::structure::slot::{IsAbstractSlot, Slot};
-use spenso::structure::{OrderedStructure, TensorStructure};
+use spenso::structure::{HasStructure, OrderedStructure, TensorStructure};
 use spenso::tensors::data::DenseTensor;
 
 use sys::*;
@@ -27,10 +28,17 @@ fn last_error() -> String {
     unsafe { CStr::from_ptr(spn_last_error()) }.to_string_lossy().into_owned()
 }
 
+/// Status code -> `ContractionError` (spenso/src/contraction.rs:20-30), variant for variant as INTEGRATION.md section 3
+/// lists them; codes without a counterpart in the reference (CUDA, no device, invalid argument, JIT) are `Other`.
 fn check(rc: i32) -> Result<(), ContractionError> {
     match rc {
         SPN_OK => Ok(()),
         SPN_ERR_EMPTY_SPARSE => Err(ContractionError::EmptySparse),
+        SPN_ERR_STRUCTURE => Err(ContractionError::StructureError(spenso::structure::StructureError::Other(anyhow::anyhow!(
+            "spenso_b200: {}",
+            last_error()
+        )))),
+        SPN_ERR_DIMENSION => Err(ContractionError::DimensionError(anyhow::anyhow!("spenso_b200: {}", last_error()).into())),
         _ => Err(ContractionError::Other(anyhow::anyhow!("spenso_b200 ({rc}): {}", last_error()))),
     }
 }
@@ -81,17 +89,25 @@ impl Drop for Device {
     }
 }
 
-/// `n_points` dense complex tensors of one structure, resident on the device.
+/// Owner of one device tensor handle.
+struct Handle(*mut spn_tensor);
+unsafe impl Send for Handle {}
+unsafe impl Sync for Handle {}
+impl Drop for Handle {
+    fn drop(&mut self) {
+        unsafe { spn_tensor_free(self.0) }
+    }
+}
+
+/// `n_points` dense complex tensors of one structure, resident on the device (or one shared, point-independent
+/// tensor).  Device tensors are immutable once built, so `Clone` shares the handle (the reference's executor clones
+/// tensors only to consume them in `neg()` / `+=`, network.rs:1320-1325, 1381).
+#[derive(Clone)]
 pub struct DeviceBatchTensor {
-    h: *mut spn_tensor,
+    h: Arc<Handle>,
     dev: Arc<Device>,
     pub structure: OrderedStructure,
     pub n_points: u64,
-}
-impl Drop for DeviceBatchTensor {
-    fn drop(&mut self) {
-        unsafe { spn_tensor_free(self.h) }
-    }
 }
 
 impl DeviceBatchTensor {
@@ -104,24 +120,58 @@ impl DeviceBatchTensor {
         check(unsafe {
             spn_tensor_batched(dev.0, slots.as_ptr(), slots.len() as u32, points.len() as u64, SPN_C64, SPN_POINT_MAJOR, &mut h)
         })?;
-        // Complex<f64> is two f64 (spenso/src/algebra/complex.rs:55-58): a point's Vec is already the wire format
-        for (p, t) in points.iter().enumerate() {
+        // Complex<f64> is two f64 (spenso/src/algebra/complex.rs:55-58): the points are packed end to end — the wire
+        // format — and cross the bus in ONE copy (a copy per point would pay the launch latency n_points times)
+        let mut packed: Vec<Complex<f64>> = Vec::with_capacity(size * points.len());
+        for t in points {
             debug_assert_eq!(t.data.len(), size);
-            check(unsafe { spn_tensor_upload(h, t.data.as_ptr().cast(), p as u64, 1) })?;
+            packed.extend_from_slice(&t.data);
         }
-        Ok(Self { h, dev: dev.clone(), structure, n_points: points.len() as u64 })
+        let this = Self { h: Arc::new(Handle(h)), dev: dev.clone(), structure, n_points: points.len() as u64 };
+        check(unsafe { spn_tensor_upload(h, packed.as_ptr().cast(), 0, points.len() as u64) })?;
+        Ok(this)
+    }
+
+    /// A point-independent rank-0 tensor (`Sc::ref_one()` and scalar leaves).
+    pub fn shared_scalar(dev: &Arc<Device>, re: f64, im: f64) -> Result<Self, ContractionError> {
+        let v = [re, im];
+        let mut h = std::ptr::null_mut();
+        check(unsafe { spn_tensor_shared_dense(dev.0, std::ptr::null(), 0, v.as_ptr(), &mut h) })?;
+        Ok(Self { h: Arc::new(Handle(h)), dev: dev.clone(), structure: OrderedStructure::default(), n_points: 1 })
+    }
+
+    pub fn is_scalar(&self) -> bool {
+        unsafe { spn_tensor_order(self.h.0) == 0 }
+    }
+
+    fn unary(&self, f: unsafe extern "C" fn(*mut spn_ctx, *const spn_tensor, *mut *mut spn_tensor) -> i32) -> Result<Self, ContractionError> {
+        let mut out = std::ptr::null_mut();
+        check(unsafe { f(self.dev.0, self.h.0, &mut out) })?;
+        Ok(self.wrap(out, self.structure.clone()))
+    }
+    /// `Neg`
+    pub fn neg(&self) -> Result<Self, ContractionError> { self.unary(spn_tensor_neg) }
+    /// FUN_LIB conj (spenso-hep-lib/src/lib.rs:511-520)
+    pub fn conj(&self) -> Result<Self, ContractionError> { self.unary(spn_tensor_conj) }
+    /// `s.ref_one() / s`
+    pub fn recip(&self) -> Result<Self, ContractionError> { self.unary(spn_tensor_recip) }
+    /// `self += rhs` as a new tensor (`AddAssign<T::Ref>`)
+    pub fn add(&self, rhs: &Self) -> Result<Self, ContractionError> {
+        let mut out = std::ptr::null_mut();
+        check(unsafe { spn_tensor_add(self.dev.0, self.h.0, rhs.h.0, 0, &mut out) })?;
+        Ok(self.wrap(out, self.structure.clone()))
     }
 
     /// Download point `p` as a reference `DenseTensor`.
     pub fn point(&self, p: u64) -> Result<DenseTensor<Complex<f64>, OrderedStructure>, ContractionError> {
-        let size = unsafe { spn_tensor_size(self.h) } as usize;
+        let size = unsafe { spn_tensor_size(self.h.0) } as usize;
         let mut data = vec![Complex { re: 0.0, im: 0.0 }; size];
-        check(unsafe { spn_tensor_download(self.h, data.as_mut_ptr().cast(), p, 1) })?;
+        check(unsafe { spn_tensor_download(self.h.0, data.as_mut_ptr().cast(), p, 1) })?;
         Ok(DenseTensor { data, structure: self.structure.clone() })
     }
 
     fn wrap(&self, h: *mut spn_tensor, structure: OrderedStructure) -> Self {
-        Self { h, dev: self.dev.clone(), structure, n_points: unsafe { spn_tensor_n_points(h) } }
+        Self { h: Arc::new(Handle(h)), dev: self.dev.clone(), structure, n_points: unsafe { spn_tensor_n_points(h) } }
     }
 }
 
@@ -133,7 +183,7 @@ impl Contract<DeviceBatchTensor> for DeviceBatchTensor {
         // the engine computes the same merge for its stride plan and re-checks it
         let (structure, _, _, _) = self.structure.merge(&other.structure).map_err(ContractionError::StructureError)?;
         let mut out = std::ptr::null_mut();
-        check(unsafe { spn_tensor_contract(self.dev.0, self.h, other.h, &mut out) })?;
+        check(unsafe { spn_tensor_contract(self.dev.0, self.h.0, other.h.0, &mut out) })?;
         Ok(self.wrap(out, structure))
     }
 }
@@ -141,18 +191,38 @@ impl Contract<DeviceBatchTensor> for DeviceBatchTensor {
 impl std::ops::Neg for &DeviceBatchTensor {
     type Output = DeviceBatchTensor;
     fn neg(self) -> DeviceBatchTensor {
-        let mut out = std::ptr::null_mut();
-        check(unsafe { spn_tensor_neg(self.dev.0, self.h, &mut out) }).expect("neg");
-        self.wrap(out, self.structure.clone())
+        DeviceBatchTensor::neg(self).expect("neg")
     }
 }
 
 impl std::ops::Add for &DeviceBatchTensor {
     type Output = DeviceBatchTensor;
     fn add(self, rhs: &DeviceBatchTensor) -> DeviceBatchTensor {
-        let mut out = std::ptr::null_mut();
-        check(unsafe { spn_tensor_add(self.dev.0, self.h, rhs.h, 0, &mut out) }).expect("add");
-        self.wrap(out, self.structure.clone())
+        DeviceBatchTensor::add(self, rhs).expect("add")
+    }
+}
+
+/// Host data tensors -> shared device tensors (library tensors with concrete indices, local point-independent tensors).
+impl executor::ToDevice for spenso::tensors::data::DataTensor<Complex<f64>, OrderedStructure> {
+    fn to_device(&self, dev: &Arc<Device>) -> Result<DeviceBatchTensor, ContractionError> {
+        use spenso::tensors::data::DataTensor;
+        let structure = self.structure().clone();
+        let slots = slots_of(&structure);
+        let mut h = std::ptr::null_mut();
+        match self {
+            DataTensor::Dense(d) => check(unsafe {
+                spn_tensor_shared_dense(dev.0, slots.as_ptr(), slots.len() as u32, d.data.as_ptr().cast(), &mut h)
+            })?,
+            DataTensor::Sparse(s) => {
+                // HashMap order is irrelevant: entries are keyed by flat index (spenso/src/tensors/data/sparse.rs:48-53)
+                let flat: Vec<u64> = s.elements.keys().map(|k| usize::from(*k) as u64).collect();
+                let vals: Vec<Complex<f64>> = s.elements.values().cloned().collect();
+                check(unsafe {
+                    spn_tensor_shared_sparse(dev.0, slots.as_ptr(), slots.len() as u32, flat.as_ptr(), vals.as_ptr().cast(), flat.len() as u64, &mut h)
+                })?
+            }
+        }
+        Ok(DeviceBatchTensor { h: Arc::new(Handle(h)), dev: dev.clone(), structure, n_points: 1 })
     }
 }
 
@@ -160,7 +230,7 @@ impl DeviceBatchTensor {
     /// `ScalarMul<Complex<f64>>` (spenso/src/algebra/scalar_mul.rs:11-57)
     pub fn scalar_mul(&self, s: Complex<f64>) -> DeviceBatchTensor {
         let mut out = std::ptr::null_mut();
-        check(unsafe { spn_tensor_scalar_mul(self.dev.0, self.h, s.re, s.im, &mut out) }).expect("scalar_mul");
+        check(unsafe { spn_tensor_scalar_mul(self.dev.0, self.h.0, s.re, s.im, &mut out) }).expect("scalar_mul");
         self.wrap(out, self.structure.clone())
     }
 }

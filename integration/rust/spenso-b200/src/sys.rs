@@ -49,6 +49,10 @@ pub const SPN_EXEC_STEPWISE: c_int = 1;
 pub const SPN_EXEC_AUTO: c_int = 2;
 
 unsafe extern "C" {
+    pub fn spn_tensor_recip(ctx: *mut spn_ctx, a: *const spn_tensor, out: *mut *mut spn_tensor) -> c_int;
+    pub fn spn_tensor_clone(ctx: *mut spn_ctx, a: *const spn_tensor, out: *mut *mut spn_tensor) -> c_int;
+    pub fn spn_tensor_conj(ctx: *mut spn_ctx, a: *const spn_tensor, out: *mut *mut spn_tensor) -> c_int;
+    pub fn spn_net_set_schedule(net: *mut spn_net, pairs: *const i32, n_pairs: u32) -> c_int;
     pub fn spn_last_error() -> *const c_char;
     pub fn spn_ctx_create(device: c_int, out: *mut *mut spn_ctx) -> c_int;
     pub fn spn_ctx_destroy(ctx: *mut spn_ctx);
