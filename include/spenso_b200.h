@@ -295,6 +295,10 @@ const char* spn_net_cuda_source(const spn_net* net);
 const char* spn_net_prepare_variant(spn_net* net, const char* key);
 /* FP64 arithmetic instructions (DMUL/DADD/DFMA) per point of the compiled fused program */
 uint64_t spn_net_macs_per_point(const spn_net* net);
+/* the same for one kernel variant (key as in spn_net_prepare_variant), including what the variant adds: a sum variant
+ * ('s') accumulates every real result component once per point, except the components whose multiply-add chain is
+ * accumulated link by link.  0 on error. */
+uint64_t spn_net_variant_fp64_instr(spn_net* net, const char* key);
 /* bytes of per-point input the fused kernel actually reads (components multiplied by structural
  * zeros of the shared tensors are never loaded) */
 uint64_t spn_net_input_bytes_per_point(const spn_net* net);

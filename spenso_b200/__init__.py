@@ -686,6 +686,10 @@ class Network:
     def fp64_instr_per_point(self) -> int:
         return int(lib().spn_net_macs_per_point(self.h))
 
+    def variant_fp64_instr(self, key: str) -> int:
+        """FP64 instructions per point of one kernel variant, the accumulation of a Monte-Carlo sum included."""
+        return int(lib().spn_net_variant_fp64_instr(self.h, key.encode()))
+
     @property
     def input_bytes_per_point(self) -> int:
         return int(lib().spn_net_input_bytes_per_point(self.h))

@@ -116,6 +116,7 @@ SYMBOLS = {
     "spn_net_cuda_source": (C.c_char_p, [_P]),
     "spn_net_prepare_variant": (C.c_char_p, [_P, C.c_char_p]),
     "spn_net_macs_per_point": (_U64, [_P]),
+    "spn_net_variant_fp64_instr": (_U64, [_P, C.c_char_p]),
     "spn_net_input_bytes_per_point": (_U64, [_P]),
     "spn_net_execute": (_I, [_P, _P, _U32, _P, _P, _U64, _U64]),
     "spn_net_execute_host": (_I, [_P, _P, _U32, _U64, _P, _P, _U64]),

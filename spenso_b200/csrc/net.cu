@@ -111,6 +111,7 @@ struct spn_net {
     std::unique_ptr<JitKernel> k;
   };
   std::map<std::string, Variant> variants;
+
   std::string default_source, json;
   double2* sum_scratch = nullptr;  // per-block partials of the fused Monte-Carlo sum
   spn_comm* comm = nullptr;        // optional: sums are exchanged with the peer GPUs (comm.cu)
@@ -631,6 +632,16 @@ struct spn_net {
       roots.push_back(result_el[f].im.var);
     }
     stats = prog.eliminate_dead(roots);
+    if (!getenv("SPN_NO_RESCALE")) {
+      std::vector<RR*> outs;
+      for (CE& e : result_el) {
+        outs.push_back(&e.re);
+        outs.push_back(&e.im);
+      }
+      for (int round = 0; round < 4 && prog.rescale_pass(outs) > 0; ++round) {
+      }
+      stats = prog.eliminate_dead(roots);
+    }
   }
 
   // ---- fused: print the kernel -------------------------------------------------------------------
@@ -711,6 +722,130 @@ struct spn_net {
     return pf;
   }
 
+  // ---- the Monte-Carlo sum inside the fused kernel ---------------------------------------------------------------
+  // sum over points of result[c] for a variant that stores no per-point result.  Two things are exploited:
+  //  * LINEARITY: the trailing part of the program that is linear with constant coefficients (the last contractions
+  //    with gamma matrices / metrics are sign flips and additions) commutes with the sum over points.  Results are
+  //    expanded through such instructions down to a BASIS of values that really depend on the point in a non-linear way;
+  //    only the basis is accumulated per point, the linear map is applied once per thread after the loop.
+  //  * a basis value that is the end of a multiply-add chain nobody else reads is accumulated LINK BY LINK —
+  //    a = fma(x1, y1, a); a = fma(x2, y2, a); ... — instead of being formed and then added: one instruction less.
+  // cfg5: 32 trailing additions and 32 accumulations per point become 32 fused chains: 339 -> 259 FP64 instructions.
+  struct SumPlan {
+    struct Basis {
+      int var;      // value accumulated (-1: the constant 1, i.e. the number of points)
+      bool fused;   // fed link by link
+    };
+    std::vector<Basis> basis;
+    std::vector<std::map<size_t, double>> rows;   // [2*c + part]: accumulator index -> coefficient
+    struct Link {
+      size_t acc;
+      double k;
+    };
+    std::map<size_t, Link> fused;    // instruction index -> accumulate k * (its product) into accumulator acc
+    std::set<size_t> skipped;        // instructions of the linear tail (not emitted)
+    uint64_t per_point_instr = 0;    // FP64 instructions per point this plan costs beyond prog (adds) minus what it removes
+    uint64_t removed_instr = 0;
+  };
+  SumPlan plan_sum(const std::string& variant) const {
+    SumPlan sp;
+    const uint64_t size_out = result_el.size();
+    const bool want_sum = variant.back() == 's';
+    sp.rows.resize(2 * size_out);
+    if (!want_sum) return sp;
+    const bool free_form = variant[n_inputs] == 'n' && !getenv("SPN_NO_SUM_FUSION");
+    std::vector<int> def((size_t)prog.n_vals, -1), uses((size_t)prog.n_vals, 0);
+    for (size_t n = 0; n < prog.ins.size(); ++n) {
+      const Ins& i = prog.ins[n];
+      def[(size_t)i.dst] = (int)n;
+      if (i.op == I_LOADC) def[(size_t)i.dst + 1] = (int)n;
+    }
+    // expandable(v): defined by k*x (+-) z and read only by results or by other expandable values
+    std::vector<char> expandable((size_t)prog.n_vals, 0), pinned((size_t)prog.n_vals, 0);
+    if (free_form) {
+      for (size_t n = prog.ins.size(); n-- > 0;) {
+        const Ins& i = prog.ins[n];
+        if (i.op == I_LOADC || i.op == I_LOADR) continue;
+        const bool linear = i.op == I_FMAK || i.op == I_MULK;
+        const bool exp = linear && !pinned[(size_t)i.dst];
+        expandable[(size_t)i.dst] = exp;
+        if (!exp) {
+          if (i.x >= 0) pinned[(size_t)i.x] = 1;
+          if (i.y >= 0) pinned[(size_t)i.y] = 1;
+          if (i.z >= 0) pinned[(size_t)i.z] = 1;
+        }
+      }
+    }
+    std::map<int, size_t> acc_of;   // basis value -> accumulator
+    auto acc_index = [&](int var) {
+      auto it = acc_of.find(var);
+      if (it != acc_of.end()) return it->second;
+      sp.basis.push_back({var, false});
+      acc_of[var] = sp.basis.size() - 1;
+      return sp.basis.size() - 1;
+    };
+    std::function<void(std::map<size_t, double>&, int, double)> expand = [&](std::map<size_t, double>& row, int var, double k) {
+      if (k == 0.0) return;
+      if (var >= 0 && expandable[(size_t)var]) {
+        const size_t n = (size_t)def[(size_t)var];
+        const Ins& i = prog.ins[n];
+        sp.skipped.insert(n);
+        expand(row, i.x, k * i.k);
+        if (i.op == I_FMAK) expand(row, i.z, k * (double)i.sz);
+        return;
+      }
+      row[acc_index(var)] += k;
+    };
+    for (uint64_t c = 0; c < size_out; ++c)
+      for (int part = 0; part < 2; ++part) {
+        const RR& r = part ? result_el[c].im : result_el[c].re;
+        if (r.is_zero()) continue;
+        if (r.var < 0)
+          sp.rows[2 * c + (uint64_t)part][acc_index(-1)] += r.coef;   // a constant: coef * n_points
+        else
+          expand(sp.rows[2 * c + (uint64_t)part], r.var, r.coef);
+      }
+    // remaining instruction uses of every value (skipped instructions do not read anything any more)
+    for (size_t n = 0; n < prog.ins.size(); ++n) {
+      const Ins& i = prog.ins[n];
+      if (i.op == I_LOADC || i.op == I_LOADR || sp.skipped.count(n)) continue;
+      if (i.x >= 0) uses[(size_t)i.x]++;
+      if (i.y >= 0) uses[(size_t)i.y]++;
+      if (i.z >= 0) uses[(size_t)i.z]++;
+    }
+    // link-by-link accumulation of basis values that end an unshared multiply-add chain
+    if (free_form)
+      for (size_t j = 0; j < sp.basis.size(); ++j) {
+        const int top = sp.basis[j].var;
+        if (top < 0 || uses[(size_t)top] != 0) continue;
+        std::vector<std::pair<size_t, double>> links;
+        double mult = 1.0;
+        int cur = top;
+        bool ok = false;
+        while (cur >= 0 && def[(size_t)cur] >= 0 && uses[(size_t)cur] == (cur == top ? 0 : 1)) {
+          const Ins& d = prog.ins[(size_t)def[(size_t)cur]];
+          if (d.op == I_FMA || d.op == I_FMAK) {
+            links.emplace_back((size_t)def[(size_t)cur], mult * d.k);
+            mult *= (double)d.sz;
+            cur = d.z;
+          } else if (d.op == I_MUL || d.op == I_MULK) {
+            links.emplace_back((size_t)def[(size_t)cur], mult * d.k);
+            ok = true;
+            break;
+          } else {
+            break;
+          }
+        }
+        if (!ok) continue;
+        for (auto& l : links) sp.fused[l.first] = SumPlan::Link{j, l.second};
+        sp.basis[j].fused = true;
+      }
+    for (auto& bs : sp.basis) sp.per_point_instr += bs.fused ? 0 : 1;
+    for (size_t n : sp.skipped) sp.removed_instr += 1 + 0 * n;
+    for (auto& bs : sp.basis) sp.removed_instr += bs.fused ? 1 : 0;   // the chain head: a multiply became a multiply-add
+    return sp;
+  }
+
   std::string gen_source(const std::string& variant, const std::string& kname) const {
     const uint64_t size_out = result_el.size();
     const char out_mode = variant[n_inputs];
@@ -747,8 +882,10 @@ struct spn_net {
     o << "extern \"C\" __global__ void __launch_bounds__(" << kBlock << (kMinBlocks ? ", " + std::to_string(kMinBlocks) : std::string()) << ") " << kname << "(";
     for (uint32_t k = 0; k < n_inputs; ++k) o << "const double* __restrict__ in" << k << ", ull cs" << k << ", ";
     o << "double* __restrict__ out, ull ocs, double2* __restrict__ block_sums, ull n_points) {\n";
-    if (want_sum)
-      for (uint64_t c = 0; c < size_out; ++c) o << "  double sr" << c << " = 0.0, si" << c << " = 0.0;\n";
+    if (want_sum) {
+      const SumPlan sp0 = plan_sum(variant);
+      for (size_t j = 0; j < sp0.basis.size(); ++j) o << "  double a" << j << " = 0.0;\n";
+    }
     // value names
     std::vector<std::string> name((size_t)prog.n_vals);
     auto vname = [&](int v) -> const std::string& { return name[(size_t)v]; };
@@ -966,7 +1103,24 @@ struct spn_net {
       o << "  for (ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x; p < n_points; p += (ull)gridDim.x * " << kBlock
         << ") {\n";
     }
+    const SumPlan sp = plan_sum(variant);
+    size_t ins_index = 0;
     for (const Ins& i : prog.ins) {
+      const size_t this_index = ins_index++;
+      if (sp.skipped.count(this_index)) continue;   // part of the linear tail: applied once, after the loop
+      if (auto fl = sp.fused.find(this_index); fl != sp.fused.end()) {
+        const std::string acc = "a" + std::to_string(fl->second.acc);
+        const double k = fl->second.k;
+        if (i.op == I_MUL || i.op == I_FMA)
+          o << "    " << acc << " = fma(" << scaled(k, i.x) << ", " << vname(i.y) << ", " << acc << ");\n";
+        else if (k == 1.0)
+          o << "    " << acc << " += " << vname(i.x) << ";\n";
+        else if (k == -1.0)
+          o << "    " << acc << " -= " << vname(i.x) << ";\n";
+        else
+          o << "    " << acc << " = fma(" << lit(k) << ", " << vname(i.x) << ", " << acc << ");\n";
+        continue;
+      }
       switch (i.op) {
         case I_LOADC:
         case I_LOADR: {
@@ -1023,7 +1177,7 @@ struct spn_net {
     };
     for (uint64_t c = 0; c < size_out; ++c) {
       const std::string re = rr_expr(result_el[c].re), im = rr_expr(result_el[c].im);
-      if (want_sum) o << "    sr" << c << " += " << re << "; si" << c << " += " << im << ";\n";
+
       if (out_mode == 'n') continue;
       std::string idx = out_mode == 'p' ? "(p * " + std::to_string(size_out) + "ull + " + std::to_string(c) + "ull)"
                                         : "(" + std::to_string(c) + "ull * ocs + p)";
@@ -1040,6 +1194,23 @@ struct spn_net {
            "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
     o << "  }\n";
     if (want_sum) {
+      // the linear tail: every result component is a fixed linear combination of the accumulators
+      for (uint64_t c = 0; c < size_out; ++c)
+        for (int part = 0; part < 2; ++part) {
+          o << "  const double " << (part ? "si" : "sr") << c << " = ";
+          const auto& row = sp.rows[2 * c + (uint64_t)part];
+          if (row.empty()) o << "0.0";
+          bool first = true;
+          for (auto& jk : row) {
+            if (!first) o << " + ";
+            first = false;
+            if (jk.second == 1.0)
+              o << "a" << jk.first;
+            else
+              o << lit(jk.second) << " * a" << jk.first;
+          }
+          o << ";\n";
+        }
       // per-block partial of the Monte-Carlo sum: fixed shuffle tree + fixed order over warps
       o << "  __shared__ double2 ws[" << (kBlock / 32) << "];\n";
       for (uint64_t c = 0; c < size_out; ++c) {
@@ -1740,6 +1911,29 @@ const char* spn_net_prepare_variant(spn_net* net, const char* variant) {
   }
 }
 uint64_t spn_net_macs_per_point(const spn_net* net) { return net->stats.n_fp; }
+uint64_t spn_net_variant_fp64_instr(spn_net* net, const char* variant) {
+  try {
+    if (!net->compiled || net->exec_mode != SPN_EXEC_FUSED) throw Error(SPN_ERR_INVALID, "not a compiled fused network");
+    const std::string v = variant;
+    if (v.size() < net->n_inputs + 1) throw Error(SPN_ERR_INVALID, "variant key too short");
+    net->get_variant(v);
+    uint64_t n = net->stats.n_fp;
+    if (v.back() == 's') {
+      // the sum over points: one add per accumulator that is not fed link by link, minus the linear tail that moved
+      // out of the loop and the chain heads that absorbed their accumulation
+      const spn_net::SumPlan sp = net->plan_sum(v);
+      uint64_t skipped_cost = 0;
+      for (size_t k : sp.skipped) skipped_cost += 1 + 0 * k;
+      uint64_t adds = 0;
+      for (auto& b : sp.basis) adds += b.fused ? 0 : 1;
+      n = n - skipped_cost + adds;
+    }
+    return n;
+  } catch (const std::exception& e) {
+    spn::set_error(e.what());
+    return 0;
+  }
+}
 uint64_t spn_net_input_bytes_per_point(const spn_net* net) { return net->stats.n_load_bytes; }
 
 // Network::execute on HOST data: the reference's calling convention (tensors are host Vec<Complex<f64>>).

@@ -94,17 +94,21 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
   uint64_t stage_units = 0;
   if (sa.staged) { sa.offset = stage_units; stage_units += 32 * sa.row; }
   if (sb.staged) { sb.offset = stage_units; stage_units += 32 * sb.row; }
-  int n_stages = (getenv("SPN_PAIR_STAGES") && atoi(getenv("SPN_PAIR_STAGES")) == 1) ? 1 : 2;
-  const bool force_stages = getenv("SPN_PAIR_STAGES") != nullptr;
-  uint64_t warp_units = n_stages * stage_units + (sc.staged ? 32 * sc.row : 0);
+  // Pipeline shape.  Every resident warp has (n_stages - 1) slabs on their way while it computes on one; with
+  // n_stages = 1 a warp loads, then computes, and the overlap comes from the other warps of the SM.  Measured
+  // (profiles/r02_pairwise_sweep.txt, 2^20 points, stages 1-4 x 2/4/8 warps per CTA): one stage is never slower and up to
+  // 1.5x faster than 3-4 stages on the 256-1024 B operands — shared memory spent on extra stages costs resident
+  // warps, and resident warps are what hides the latency here.  SPN_PAIR_STAGES=2..4 keeps the deeper rings reachable.
+  const uint64_t out_units = sc.staged ? 32 * sc.row : 0;
+  const uint64_t budget = 216 * 1024 / 16;   // 16-byte units of shared memory per SM the kernel may plan with
+  const int forced_stages = getenv("SPN_PAIR_STAGES") ? std::max(1, std::min(4, atoi(getenv("SPN_PAIR_STAGES")))) : 0;
+  int n_stages = forced_stages ? forced_stages : 1;
   int warps = kSlabWarps;
+  uint64_t warp_units = (uint64_t)n_stages * stage_units + out_units;
   if (gen.slab) {
-    // keep at least ~4 warps resident per SM: fall back to one stage, then to fewer warps per CTA
-    const uint64_t budget = 220 * 1024 / 16;
-    if (warp_units * 4 > budget && !force_stages) {
-      n_stages = 1;
-      warp_units = stage_units + (sc.staged ? 32 * sc.row : 0);
-    }
+    if (!forced_stages)
+      while (n_stages > 1 && ((uint64_t)n_stages * stage_units + out_units) * 8 > budget) --n_stages;
+    warp_units = (uint64_t)n_stages * stage_units + out_units;
     while (warps > 1 && warp_units * (uint64_t)warps > budget) warps /= 2;
     if (warp_units > budget) {  // does not fit at all: direct kernel
       gen.slab = false;
@@ -160,13 +164,23 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
       o << "      }\n    }\n";
     }
     o << "  };\n";
-    o << "  if (slab < n_slabs) issue(slab, 0u);\n";
-    o << "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
-    o << "  for (unsigned stage = 0; slab < n_slabs; slab += n_warps" << (n_stages == 2 ? ", stage ^= 1u" : "") << ") {\n";
-    if (n_stages == 2) {
-      o << "    if (slab + n_warps < n_slabs) issue(slab + n_warps, stage ^ 1u);\n";
-      o << "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
-      o << "    asm volatile(\"cp.async.wait_group 1;\" ::: \"memory\");\n";
+    // prologue: the first n_stages - 1 slabs of this warp (one commit group per slab, empty groups keep the count)
+    if (n_stages == 1) {
+      o << "  if (slab < n_slabs) issue(slab, 0u);\n";
+      o << "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
+    } else {
+      o << "#pragma unroll\n  for (unsigned d = 0; d < " << (n_stages - 1) << "u; ++d) {\n";
+      o << "    if (slab + d * n_warps < n_slabs) issue(slab + d * n_warps, d);\n";
+      o << "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n  }\n";
+    }
+    o << "  for (unsigned stage = 0; slab < n_slabs; slab += n_warps"
+      << (n_stages > 1 ? ", stage = (stage + 1u == " + std::to_string(n_stages) + "u ? 0u : stage + 1u)" : std::string()) << ") {\n";
+    if (n_stages > 1) {
+      // refill the stage consumed in the previous iteration with the slab n_stages - 1 ahead
+      o << "    {\n      const unsigned fill = stage == 0u ? " << (n_stages - 1) << "u : stage - 1u;\n";
+      o << "      if (slab + " << (n_stages - 1) << "ull * n_warps < n_slabs) issue(slab + " << (n_stages - 1) << "ull * n_warps, fill);\n";
+      o << "      asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n    }\n";
+      o << "    asm volatile(\"cp.async.wait_group " << (n_stages - 1) << ";\" ::: \"memory\");\n";
     } else {
       o << "    asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\");\n";
     }

@@ -294,6 +294,98 @@ struct Program {
     return RR{i.dst, 1.0};
   }
 
+  // ---- scale propagation --------------------------------------------------------------------------------------
+  // Value numbering normalises every sum to leading coefficient 1 and hands the factor to the consumer.  A consumer
+  // that is itself a product then multiplies by a non-unit constant, `(2.0 * v120) * v134`, which costs a DMUL of its
+  // own.  Where the producer can absorb the factor for free — k*x (+-) z with |c*k| = 1 becomes c*z (+-) x, one FMA
+  // either way; k*x becomes x; k*x*y takes the factor into k — and that makes more multiplicands unit than it
+  // breaks, the value is rescaled and its uses (results included) follow.  `results` are the program's outputs.
+  int rescale_pass(std::vector<RR*>& results) {
+    if (ins.size() > 200000) return 0;   // far beyond what runs as straight-line code anyway
+    std::vector<int> def(n_vals, -1);
+    std::vector<std::vector<int>> users((size_t)n_vals);   // instructions reading each value (once per instruction)
+    for (size_t n = 0; n < ins.size(); ++n) {
+      const Ins& i = ins[n];
+      def[i.dst] = (int)n;
+      if (i.op == I_LOADC) def[i.dst + 1] = (int)n;
+      if (i.op == I_LOADC || i.op == I_LOADR) continue;
+      for (int v : {i.x, i.y, i.z})
+        if (v >= 0 && (users[(size_t)v].empty() || users[(size_t)v].back() != (int)n)) users[(size_t)v].push_back((int)n);
+    }
+    std::vector<std::vector<RR*>> result_uses((size_t)n_vals);
+    for (RR* r : results)
+      if (r->var >= 0) result_uses[(size_t)r->var].push_back(r);
+    auto mul_cost = [](double k) { return std::fabs(k) == 1.0 ? 1 : 2; };
+    std::vector<char> frozen((size_t)n_vals, 0);   // operands of a rewritten definition: their user lists are stale
+    int changed = 0;
+    for (int v = 0; v < n_vals; ++v) {
+      if (def[v] < 0 || frozen[(size_t)v]) continue;
+      const Ins d = ins[(size_t)def[v]];
+      if (d.op != I_FMAK && d.op != I_MULK && d.op != I_MUL) continue;
+      // product uses vote for the factor that would make them unit; anything that cannot follow a rescaling pins v
+      std::map<double, int> votes;
+      bool pinned = false;
+      int unit_product_uses = 0;
+      for (int un : users[(size_t)v]) {
+        const Ins& u = ins[(size_t)un];
+        const bool is_prod = u.op == I_MUL || u.op == I_FMA;
+        const int mult = (u.x == v) + ((is_prod || u.op == I_DIV) && u.y == v);
+        if (u.z == v && (u.op == I_FMA || u.op == I_FMAK || u.op == I_ADDK)) pinned = true;  // addend: sign only
+        if (!mult) continue;
+        if (is_prod) {
+          if (mult == 2) {
+            pinned = true;
+          } else if (std::fabs(u.k) == 1.0) {
+            ++unit_product_uses;
+          } else {
+            votes[std::fabs(u.k)]++;
+          }
+        } else if (u.op != I_FMAK && u.op != I_MULK) {
+          pinned = true;  // division, square root (constant-times-value takes any constant at the same cost)
+        }
+      }
+      if (pinned || votes.empty()) continue;
+      double best_c = 0.0;
+      int best_gain = 0;
+      for (auto& cv : votes) {
+        const double c = cv.first;
+        int delta_def = 0;
+        if (d.op == I_FMAK) {
+          if (std::fabs(c * d.k) != 1.0) continue;
+        } else if (d.op == I_MUL) {
+          delta_def = mul_cost(c * d.k) - mul_cost(d.k);
+        }
+        const int gain = cv.second - unit_product_uses - delta_def;
+        if (gain > best_gain) {
+          best_gain = gain;
+          best_c = c;
+        }
+      }
+      if (best_gain <= 0) continue;
+      const double c = best_c;
+      Ins& D = ins[(size_t)def[v]];
+      if (D.op == I_FMAK) {            // k*x + sz*z  ->  (c*sz)*z + (c*k)*x with |c*k| = 1
+        const double ck = c * D.k;
+        const int x0 = D.x, z0 = D.z, sz0 = D.sz;
+        D.x = z0;
+        D.k = c * (double)sz0;
+        D.z = x0;
+        D.sz = ck > 0 ? 1 : -1;
+        frozen[(size_t)x0] = frozen[(size_t)z0] = 1;   // their roles in D changed; the next round sees fresh lists
+      } else {
+        D.k *= c;                      // I_MULK / I_MUL
+      }
+      for (int un : users[(size_t)v]) {
+        Ins& u = ins[(size_t)un];
+        const bool is_prod = u.op == I_MUL || u.op == I_FMA;
+        if (u.x == v || (is_prod && u.y == v)) u.k /= c;
+      }
+      for (RR* r : result_uses[(size_t)v]) r->coef /= c;
+      ++changed;
+    }
+    return changed;
+  }
+
   // ---- dead code elimination + statistics ---------------------------------------------------
   // keep only instructions that feed `roots`; returns the number of FP64 arithmetic instructions
   struct Stats {

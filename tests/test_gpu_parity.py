@@ -1102,7 +1102,7 @@ def test_plan_cache_serves_repeated_contractions(ctx):
 def test_data_tensor_conversions_and_element_access(ctx):
     """DataTensor::to_dense / to_sparse (tensors/data/sparse.rs:688-708, dense.rs:523-535), get / set by flat index,
     clone, reciprocal, and library tensors with concrete indices (get_lib_data, network/graph.rs:291-322)."""
-    e = [sp.Euclidean.new_slot(3, 1), sp.Euclidean.new_slot(2, 2)]
+    e = [sp.Euclidean.new_slot(2, 1), sp.Euclidean.new_slot(3, 2)]     # already canonical: flat = 3 * i + j
     d = sp.DenseTensor.from_data(ctx, e, [1, 0, 0, 2j, 0, 3])
     s = d.to_sparse()
     assert s.is_sparse and s.entries() == {0: 1, 3: 2j, 5: 3}              # zeros are not stored
@@ -1117,11 +1117,11 @@ def test_data_tensor_conversions_and_element_access(ctx):
     with pytest.raises(sp.SpensoError):
         d.get(6)
     # a set changes what the tensor contracts to (the plan cache keys shared tensors by identity + revision)
-    v = sp.DenseTensor.from_data(ctx, [sp.Euclidean.new_slot(2, 2)], [1, 1])
+    v = sp.DenseTensor.from_data(ctx, [sp.Euclidean.new_slot(3, 2)], [1, 1, 1])
     before = d.contract(v).to_numpy()
     d.set(1, 5.0)
     after = d.contract(v).to_numpy()
-    assert np.array_equal(before.reshape(-1), [1, 2j, 3]) and np.array_equal(after.reshape(-1), [6, 2j, 3])
+    assert np.array_equal(before.reshape(-1), [1, 3 + 2j]) and np.array_equal(after.reshape(-1), [6, 3 + 2j])
     # batched tensors: element access at a point, clone is a deep copy, to_sparse is refused
     rng = np.random.default_rng(0)
     for layout in (sp.POINT_MAJOR, sp.COMPONENT_MAJOR):
@@ -1140,3 +1140,42 @@ def test_data_tensor_conversions_and_element_access(ctx):
     g = sp.library_tensor(ctx, sp.LIB_GAMMA_WEYL, [b(2), b(1), sp.Minkowski.new_slot(4, 3)])
     og = O.OLib.builtin(0).instantiate(O.slots(("bis", 4, 2), ("bis", 4, 1), ("mink", 4, 3)))
     assert g.is_sparse and g.entries() == {k: complex(v) for k, v in og.entries().items()}
+
+
+@pytest.mark.parametrize("name,n_points,scale,real", [("cfg1", 777, 1.0, True), ("cfg2", 4099, 1.0, False), ("cfg3", 301, 1.0, False),
+                                                      ("cfg5", 5003, 100.0, True), ("cfg5r", 5003, 100.0, True)])
+@pytest.mark.parametrize("layout", [sp.POINT_MAJOR, sp.COMPONENT_MAJOR])
+def test_sum_only_kernels_commute_the_linear_tail(ctx, name, n_points, scale, real, layout):
+    """Monte-Carlo sum without a per-point store (the variant bench.py runs for cfg5): the kernel accumulates a basis
+    of non-linear values — link by link where a multiply-add chain ends in one — and applies the network's trailing
+    linear map once after the loop.  Same sums as the oracle's per-point results added up (1e-12), and as the variant
+    that also stores every point."""
+    import torch
+
+    spec = workloads.WORKLOADS[name]()
+    arrays = workloads.synthetic_inputs(spec, n_points, 4321, scale=scale, real=real)
+    if name == "cfg5r":
+        ref_arrays = arrays
+        arrays = [np.ascontiguousarray(a.real) for a in arrays]
+        ref, ref_sum, _ = O.eval_spec(workloads.one_loop_massive(), ref_arrays)
+    else:
+        ref, ref_sum, _ = O.eval_spec(spec, arrays)
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    inputs = []
+    for node, a, dt in zip([x for x in spec.nodes if x[0] == "batched"], arrays, spec.input_dtypes):
+        t = sp.BatchTensor.empty(ctx, node[1], n_points, dt, layout)
+        t.upload(a)
+        inputs.append(t)
+    s_only = torch.zeros(2 * net.result_size, dtype=torch.float64, device="cuda:0")
+    net.execute(inputs, None, sum_out_ptr=s_only.data_ptr())
+    out = sp.BatchTensor.empty(ctx, net.result_slots, n_points, sp.C64, layout)
+    s_both = torch.zeros_like(s_only)
+    net.execute(inputs, out, sum_out_ptr=s_both.data_ptr())
+    ctx.synchronize()
+    a = s_only.cpu().numpy().view(np.complex128)
+    b = s_both.cpu().numpy().view(np.complex128)
+    assert rel_err(a, ref_sum) <= TOL
+    assert rel_err(a, b) <= 1e-13
+    assert rel_err(out.to_numpy().reshape(n_points, -1), ref) <= TOL
+    key = ("p" if layout == sp.POINT_MAJOR else "c") * net.n_inputs
+    assert net.variant_fp64_instr(key + "ns") <= net.variant_fp64_instr(key + ("p" if layout == sp.POINT_MAJOR else "c") + "s")

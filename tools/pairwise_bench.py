@@ -1,5 +1,8 @@
 """Achieved HBM bandwidth of the pairwise (Contract-trait) kernels on batched physics-sized tensors.
-Usage (on a GPU box): python tools/pairwise_bench.py [n_points]"""
+Usage (on a GPU box): python tools/pairwise_bench.py [n_points]
+A 2^20-point launch of the small contractions lasts 65-95 us, where ramp-up and tail already cost several per cent (the
+torch controls printed first show what plain streaming kernels of the same size reach on the same box); 2^22 points
+show the kernels' steady state."""
 import os
 import sys
 import time
@@ -70,6 +73,15 @@ for name, fn, bytes_pp in cases:
     ms, r = timeit(fn)
     print(f"{name:62s} {ms*1e3:8.1f} us  {bytes_pp*n/ms/1e6:7.0f} GB/s  ({bytes_pp} B/point)", flush=True)
 del r
+# control: pure write and pure read streams on this box
+xw = torch.empty(n * 32, dtype=torch.float64, device="cuda")
+ms_ctl, _ = timeit(lambda: xw.fill_(1.0))
+print(f"{'control: torch fill (write only), 256 B/point':62s} {ms_ctl*1e3:8.1f} us  {256*n/ms_ctl/1e6:7.0f} GB/s", flush=True)
+ms_ctl, _ = timeit(lambda: torch.sum(xw))
+print(f"{'control: torch sum (read only), 256 B/point':62s} {ms_ctl*1e3:8.1f} us  {256*n/ms_ctl/1e6:7.0f} GB/s", flush=True)
+del xw
+if os.environ.get("SPN_PWB_SMALL"):
+    sys.exit(0)
 # shapes outside the specialised-kernel thresholds: table-driven generic kernel / CSR gather
 cases = []
 co = lambda a: sp.ColorAdjoint.new_slot(8, a)
