@@ -45,7 +45,12 @@ enum {
 /* LibraryRep, spenso/src/structure/representation.rs:583-620 */
 enum { SPN_REP_DUMMY = 0, SPN_REP_SELF_DUAL = 1, SPN_REP_INLINE_METRIC = 2, SPN_REP_DUALIZABLE = 3 };
 /* AbstractIndex, spenso/src/structure/abstract_index.rs:267-294 */
-enum { SPN_AIND_NORMAL = 0, SPN_AIND_DUALIZE = 1, SPN_AIND_DOUBLE = 2, SPN_AIND_DUMMY = 3, SPN_AIND_ADDED = 4 };
+enum { SPN_AIND_NORMAL = 0, SPN_AIND_DUALIZE = 1, SPN_AIND_DOUBLE = 2, SPN_AIND_DUMMY = 3, SPN_AIND_ADDED = 4,
+       /* AbstractIndex::Symbol (feature "shadowing"): the payload is the interned id of the symbol.  The derived Ord
+        * compares symbols by their id in symbolica's state, i.e. by creation order; spn_symbol_intern hands out ids in
+        * first-seen order, which reproduces that order when the host interns its symbols in the order it created them
+        * (or the host passes symbolica's own ids). */
+       SPN_AIND_SYMBOL = 5 };
 
 /* Slot<LibraryRep, AbstractIndex>, spenso/src/structure/slot.rs:53-56 (16 bytes) */
 typedef struct spn_slot {
@@ -88,6 +93,11 @@ typedef struct spn_contract_plan {
 
 const char* spn_last_error(void);
 int spn_version(void);
+/* process-wide symbol table for SPN_AIND_SYMBOL payloads: the same name always maps to the same id, ids grow in
+ * first-seen order from 0.  Thread-safe. */
+uint64_t spn_symbol_intern(const char* name);
+/* the name behind an id (NULL if unknown); valid for the life of the process */
+const char* spn_symbol_name(uint64_t id);
 
 /* PermutedStructure::from(Vec<Slot>) — ordered.rs:321-380.  out[i] = in[perm[i]]. */
 int spn_structure_canonicalize(const spn_slot* in, uint32_t n, spn_slot* out, int32_t* perm,
@@ -318,6 +328,13 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
  * Synchronous: host_out / host_sum are complete on return. */
 int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
                          void* host_out, double* host_sum, uint64_t chunk_points);
+/* The same without the final wait: returns when the chunks are enqueued.  Successive calls keep the pipeline full —
+ * the first chunks of call k+1 cross the bus while the last kernels and result copies of call k are still running (a
+ * Monte-Carlo driver submits batch after batch) — and complete in order.  host_inputs must stay valid and unchanged,
+ * host_out / host_sum must not be read, until spn_net_host_wait returns. */
+int spn_net_execute_host_async(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
+                               void* host_out, double* host_sum, uint64_t chunk_points);
+int spn_net_host_wait(spn_net* net);
 /* ---- Monte-Carlo sum exchange between the GPUs of one node ----------------------------------
  * The one collective of the path: the all-reduce (SUM) of the per-rank Monte-Carlo partial sums,
  * 2*result_size doubles.  Nothing in the reference corresponds to it (it is single-process); its callers
@@ -352,8 +369,12 @@ void spn_comm_destroy(spn_comm* comm);
  * after the network kernel instead of a fold kernel plus a library all-reduce). */
 int spn_net_set_comm(spn_net* net, spn_comm* comm);
 
-/* pinned host memory for the host-buffer entry points (cudaHostAlloc / cudaFreeHost) */
+/* pinned host memory for the host-buffer entry points (cudaHostAlloc / cudaFreeHost).  SPN_HOST_WRITE_COMBINED: for
+ * buffers the CPU only ever WRITES sequentially (the kinematics handed to spn_net_execute_host): the copy engine reads
+ * them without snooping the CPU caches; reading such memory from the CPU is very slow. */
+enum { SPN_HOST_WRITE_COMBINED = 1 };
 void* spn_host_alloc(uint64_t bytes);
+void* spn_host_alloc_flags(uint64_t bytes, int flags);
 void spn_host_free(void* p);
 
 #ifdef __cplusplus

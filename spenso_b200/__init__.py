@@ -24,7 +24,7 @@ from ._capi import SLOT_DTYPE, ContractPlan, SpensoError, build_library, check, 
 
 __all__ = [
     "Representation", "Euclidean", "Minkowski", "Lorentz", "Bispinor", "SpinFundamental", "ColorAdjoint",
-    "ColorFundamental", "ColorSextet", "Slot", "slots", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
+    "ColorFundamental", "ColorSextet", "Slot", "slots", "symbol_slot", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
     "Network", "NetExpr", "PeerComm", "SpensoError", "canonicalize", "plan_contract", "build_library", "library_tensor",
     "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE", "AUTO",
 ]
@@ -84,6 +84,15 @@ class Slot:
 
     def __repr__(self):
         return f"{self.rep}{self.dim}|{self.aind}"
+
+
+AIND_NORMAL, AIND_DUALIZE, AIND_DOUBLE, AIND_DUMMY, AIND_ADDED, AIND_SYMBOL = range(6)
+
+
+def symbol_slot(rep: Representation, dim: int, name: str) -> Slot:
+    """A slot whose abstract index is a symbol (AbstractIndex::Symbol, abstract_index.rs:267-294): the name is interned
+    to an integer id (first-seen order, like symbol creation order in the reference)."""
+    return Slot(rep, dim, int(lib().spn_symbol_intern(name.encode())), AIND_SYMBOL)
 
 
 def slots(items: Iterable) -> np.ndarray:
@@ -700,6 +709,22 @@ class Network:
         arr = (C.c_void_p * max(len(inputs), 1))(*[t.h for t in inputs])
         check(lib().spn_net_execute(self.h, C.cast(arr, C.c_void_p), len(inputs), out.h if out is not None else None,
                                     C.c_void_p(sum_out_ptr) if sum_out_ptr else None, first_point, n_points))
+
+    def execute_host_async(self, host_inputs: Sequence[np.ndarray], out: Optional[np.ndarray] = None,
+                           sum_out: Optional[np.ndarray] = None, chunk_points: int = 0):
+        """spn_net_execute_host_async: enqueue one batch and return; call host_wait() before reading `out` / `sum_out`
+        (a preallocated complex128 [result_size]) or touching the inputs.  Successive calls keep the pipeline full."""
+        for a in host_inputs:
+            if not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("asynchronous execution needs contiguous input arrays (no temporary copies)")
+        n = host_inputs[0].shape[0] if host_inputs else (out.shape[0] if out is not None else 1)
+        ptrs = (C.c_void_p * max(len(host_inputs), 1))(*[a.ctypes.data for a in host_inputs])
+        check(lib().spn_net_execute_host_async(self.h, C.cast(ptrs, C.c_void_p), len(host_inputs), n,
+                                               ptr(out) if out is not None else None,
+                                               ptr(sum_out) if sum_out is not None else None, chunk_points))
+
+    def host_wait(self):
+        check(lib().spn_net_host_wait(self.h))
 
     def execute_host(self, host_inputs: Sequence[np.ndarray], out: Optional[np.ndarray] = None,
                      want_sum: bool = False, chunk_points: int = 0):

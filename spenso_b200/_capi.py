@@ -48,6 +48,8 @@ _P, _U32, _U64, _I, _D = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_double
 SYMBOLS = {
     "spn_last_error": (C.c_char_p, []),
     "spn_version": (_I, []),
+    "spn_symbol_intern": (_U64, [C.c_char_p]),
+    "spn_symbol_name": (C.c_char_p, [_U64]),
     "spn_structure_canonicalize": (_I, [_P, _U32, _P, _P, _P, _P]),
     "spn_plan_contract": (_I, [_P, _U32, _P, _U32, C.POINTER(ContractPlan)]),
     "spn_ctx_create": (_I, [_I, C.POINTER(_P)]),
@@ -120,7 +122,10 @@ SYMBOLS = {
     "spn_net_input_bytes_per_point": (_U64, [_P]),
     "spn_net_execute": (_I, [_P, _P, _U32, _P, _P, _U64, _U64]),
     "spn_net_execute_host": (_I, [_P, _P, _U32, _U64, _P, _P, _U64]),
+    "spn_net_execute_host_async": (_I, [_P, _P, _U32, _U64, _P, _P, _U64]),
+    "spn_net_host_wait": (_I, [_P]),
     "spn_host_alloc": (_P, [_U64]),
+    "spn_host_alloc_flags": (_P, [_U64, _I]),
     "spn_host_free": (None, [_P]),
     "spn_comm_create": (_I, [_P, _I, _I, _U32, C.POINTER(_P)]),
     "spn_comm_handle": (_I, [_P, _P]),

@@ -3,7 +3,9 @@
 // launches the sm_100a kernels of kernels.cu; there is no host execution path.
 #include <atomic>
 #include <cstring>
+#include <deque>
 #include <memory>
+#include <mutex>
 
 #include "library.hpp"
 #include "tensor.hpp"
@@ -103,7 +105,8 @@ spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, in
     // stream-ordered allocation from the device's memory pool: no implicit synchronisation, and memory freed by
     // an earlier intermediate is reused without a round trip to the driver
     const size_t bytes = n_points * st.size() * t->elem_bytes();
-    if (ctx && cudaMallocAsync(&t->dptr, bytes ? bytes : 16, ctx->stream) == cudaSuccess) {
+    static const bool no_pool = getenv("SPN_NO_POOL") != nullptr;
+    if (ctx && !no_pool && cudaMallocAsync(&t->dptr, bytes ? bytes : 16, ctx->stream) == cudaSuccess) {
       t->pooled = true;
       t->alloc_stream = ctx->stream;
     } else {
@@ -190,8 +193,9 @@ static bool zgemm_applicable(const spn_contract_plan& p, const spn_tensor* a, co
                              long long res_fs, uint64_t n_points, const KTables& kt) {
   if (getenv("SPN_NO_ZGEMM")) return false;
   if (a->sparse() || b->sparse()) return false;
-  // complex x complex -> ZGEMM, real x real -> DGEMM; mixed operands take the streaming kernel
-  if (a->dtype != b->dtype || a->dtype != res_dtype) return false;
+  // complex x complex -> ZGEMM, real x real -> DGEMM, real x complex -> DGEMM over the complex operand seen as a real
+  // matrix with twice the columns (or rows): its (re, im) pairs are two adjacent real entries, and so are the result's
+  if (a->dtype == b->dtype && a->dtype != res_dtype) return false;
   if (p.n_partition != p.order_out || p.n_common == 0) return false;
   // element stride 1 within a point (point-major batched, or shared)
   if (a->operand().fs != 1 || b->operand().fs != 1 || res_fs != 1) return false;
@@ -226,11 +230,13 @@ struct ContractEntry {
   DevTable<long long> d_row_a, d_out_row, d_col_b, d_out_col;
   DevTable<double> d_ksign;
   bool any_sign = false, vec_tables = false;
+  int mixed = 0;   // 0: both operands of one type; 1: a real, b complex; 2: a complex, b real (DGEMM on doubled tables)
 };
 
-static void build_gemm_tables(ContractEntry& e) {
+static void build_gemm_tables(ContractEntry& e, int mixed) {
   const spn_contract_plan& p = e.plan;
   e.g = gemm_shape(p);
+  e.mixed = mixed;
   std::vector<uint64_t> ostride(p.order_out, 1);
   for (uint32_t r = p.order_out; r-- > 1;) ostride[r - 1] = ostride[r] * p.out_dim[r];
   std::vector<long long> row_a, out_row, col_b, out_col;
@@ -258,7 +264,35 @@ static void build_gemm_tables(ContractEntry& e) {
   };
   enumerate(true, row_a, out_row);
   enumerate(false, col_b, out_col);
-  const std::vector<long long>&k_a = e.kt.off_a, &k_b = e.kt.off_b;
+  std::vector<long long> k_a = e.kt.off_a, k_b = e.kt.off_b;
+  if (mixed) {
+    // element offsets -> offsets in doubles of a real view: the complex side (operand and result) doubles, with the
+    // (re, im) pair as two adjacent columns (a real, b complex) or rows (a complex, b real)
+    auto twice = [](std::vector<long long>& v) {
+      for (auto& x : v) x *= 2;
+    };
+    auto interleave = [](std::vector<long long>& v) {
+      std::vector<long long> w(2 * v.size());
+      for (size_t i = 0; i < v.size(); ++i) {
+        w[2 * i] = 2 * v[i];
+        w[2 * i + 1] = 2 * v[i] + 1;
+      }
+      v.swap(w);
+    };
+    if (mixed == 1) {   // C[r, (c, e)] = sum_k A[r, k] * B[k, (c, e)]
+      interleave(col_b);
+      interleave(out_col);
+      twice(out_row);
+      twice(k_b);
+      e.g.N *= 2;
+    } else {            // C[(r, e), c] = sum_k A[(r, e), k] * B[k, c]
+      interleave(row_a);
+      interleave(out_row);
+      twice(out_col);
+      twice(k_a);
+      e.g.M *= 2;
+    }
+  }
   std::vector<double> ks;
   for (auto s : e.kt.sign) e.any_sign |= s != 0;
   if (e.any_sign)
@@ -395,7 +429,7 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
       build_csr_tables(e, a, b);
     } else if (zgemm_applicable(plan, a, b, out_dtype, res->operand().fs, n_points, e.kt)) {
       e.path = PATH_GEMM;  // K6: the contraction reshapes to a GEMM large enough for the FP64 tensor pipe
-      build_gemm_tables(e);
+      build_gemm_tables(e, a->dtype == b->dtype ? 0 : (a->dtype == SPN_F64 ? 1 : 2));
     } else {
       // K1/K5/K7 (and sparse x sparse over the densified shared copies; the structural/zero filter of the sparse
       // result is applied below)
@@ -448,7 +482,16 @@ void tensor_contract(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b, spn
     }
     case PATH_GEMM: {
       const long long K = (long long)e.kt.off_a.size();
-      if (a->dtype == SPN_C64)
+      if (e.mixed) {
+        // point strides in doubles of the real views
+        const long long psa = a->operand().ps * (a->dtype == SPN_C64 ? 2 : 1), psb = b->operand().ps * (b->dtype == SPN_C64 ? 2 : 1);
+        const bool vec = e.vec_tables && psa % 2 == 0 && psb % 2 == 0 && (uintptr_t)a->dptr % 16 == 0 && (uintptr_t)b->dptr % 16 == 0;
+        cuda_check(launch_contract_dgemm(static_cast<const double*>(a->dptr), static_cast<const double*>(b->dptr),
+                                         static_cast<double*>(res->dptr), e.d_row_a.p, e.d_ka.p, e.d_col_b.p, e.d_kb.p,
+                                         e.d_out_row.p, e.d_out_col.p, e.any_sign ? e.d_ksign.p : nullptr, e.g.M, e.g.N, K, psa,
+                                         psb, res->operand().ps * 2, n_points, vec, ctx->stream),
+                   "contract_dgemm_kernel (mixed f64 x c64)");
+      } else if (a->dtype == SPN_C64)
         cuda_check(launch_contract_zgemm(static_cast<const double2*>(a->dptr), static_cast<const double2*>(b->dptr),
                                          static_cast<double2*>(res->dptr), e.d_row_a.p, e.d_ka.p, e.d_col_b.p, e.d_kb.p,
                                          e.d_out_row.p, e.d_out_col.p, e.any_sign ? e.d_ksign.p : nullptr, e.g.M, e.g.N, K,
@@ -576,6 +619,33 @@ void tensor_elementwise(spn_ctx* ctx, int op, const spn_tensor* a, const spn_ten
 extern "C" {
 
 const char* spn_last_error(void) { return g_err.c_str(); }
+
+namespace {
+struct SymbolTable {
+  std::mutex m;
+  std::map<std::string, uint64_t> id_of;
+  std::deque<std::string> names;   // deque: references stay valid as it grows
+};
+SymbolTable& symbols() {
+  static SymbolTable t;
+  return t;
+}
+}  // namespace
+uint64_t spn_symbol_intern(const char* name) {
+  SymbolTable& t = symbols();
+  std::lock_guard<std::mutex> lock(t.m);
+  const std::string key = name ? name : "";
+  auto it = t.id_of.find(key);
+  if (it != t.id_of.end()) return it->second;
+  t.names.push_back(key);
+  t.id_of[key] = t.names.size() - 1;
+  return t.names.size() - 1;
+}
+const char* spn_symbol_name(uint64_t id) {
+  SymbolTable& t = symbols();
+  std::lock_guard<std::mutex> lock(t.m);
+  return id < t.names.size() ? t.names[(size_t)id].c_str() : nullptr;
+}
 int spn_version(void) { return SPN_VERSION; }
 
 int spn_structure_canonicalize(const spn_slot* in, uint32_t n, spn_slot* out, int32_t* perm, int64_t* base_start,
@@ -631,6 +701,7 @@ int spn_ctx_create(int device, spn_ctx** out) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       uint64_t keep = 4ull << 30;  // up to 4 GiB of freed intermediates stay cached across synchronisations
+      if (const char* e = getenv("SPN_POOL_KEEP_GB")) keep = (uint64_t)atof(e) << 30;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     cudaGetLastError();

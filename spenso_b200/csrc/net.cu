@@ -123,9 +123,17 @@ struct spn_net {
     std::vector<void*> in[kPipe];
     void* out[kPipe] = {nullptr, nullptr, nullptr};
     double2* partial[kPipe] = {nullptr, nullptr, nullptr};
-    double2* chunk_sums = nullptr;
+    double2* chunk_sums = nullptr;   // [2 call parities][n_chunks_cap][size_out]
+    double2* final_sum[2] = {nullptr, nullptr};
     uint64_t chunk_points = 0, n_chunks_cap = 0;
     size_t partial_elems = 0;
+    // a call's last stage (fold of the per-chunk sums + D2H of the result) runs on `fin`, so that the chunk streams can
+    // take the next call's chunks at once: the pipeline does not drain between calls
+    cudaStream_t fin = nullptr;
+    cudaEvent_t chunk_done[kPipe] = {nullptr, nullptr, nullptr};   // last chunk of the current call on each stream
+    cudaEvent_t fin_done[2] = {nullptr, nullptr};                  // final stage of the call with this parity
+    bool fin_pending[2] = {false, false};
+    uint64_t calls = 0;
     void release() {
       for (int s = 0; s < kPipe; ++s) {
         for (void* p : in[s]) cudaFree(p);
@@ -137,6 +145,11 @@ struct spn_net {
       }
       if (chunk_sums) cudaFree(chunk_sums);
       chunk_sums = nullptr;
+      for (int q = 0; q < 2; ++q) {
+        if (final_sum[q]) cudaFree(final_sum[q]);
+        final_sum[q] = nullptr;
+        fin_pending[q] = false;
+      }
       chunk_points = n_chunks_cap = 0;
       partial_elems = 0;
     }
@@ -144,8 +157,13 @@ struct spn_net {
   ~spn_net() {
     if (sum_scratch) cudaFree(sum_scratch);
     pipe.release();
-    for (int s = 0; s < kPipe; ++s)
+    for (int s = 0; s < kPipe; ++s) {
       if (pipe.stream[s]) cudaStreamDestroy(pipe.stream[s]);
+      if (pipe.chunk_done[s]) cudaEventDestroy(pipe.chunk_done[s]);
+    }
+    for (int q = 0; q < 2; ++q)
+      if (pipe.fin_done[q]) cudaEventDestroy(pipe.fin_done[q]);
+    if (pipe.fin) cudaStreamDestroy(pipe.fin);
   }
   // stepwise
   std::vector<std::unique_ptr<spn_tensor>> const_tensors;  // per value id (leaf consts), lazily uploaded
@@ -884,7 +902,7 @@ struct spn_net {
     o << "double* __restrict__ out, ull ocs, double2* __restrict__ block_sums, ull n_points) {\n";
     if (want_sum) {
       const SumPlan sp0 = plan_sum(variant);
-      for (size_t j = 0; j < sp0.basis.size(); ++j) o << "  double a" << j << " = 0.0;\n";
+      for (size_t j = 0; j < sp0.basis.size(); ++j) o << "  double acc" << j << " = 0.0;\n";
     }
     // value names
     std::vector<std::string> name((size_t)prog.n_vals);
@@ -1109,7 +1127,7 @@ struct spn_net {
       const size_t this_index = ins_index++;
       if (sp.skipped.count(this_index)) continue;   // part of the linear tail: applied once, after the loop
       if (auto fl = sp.fused.find(this_index); fl != sp.fused.end()) {
-        const std::string acc = "a" + std::to_string(fl->second.acc);
+        const std::string acc = "acc" + std::to_string(fl->second.acc);
         const double k = fl->second.k;
         if (i.op == I_MUL || i.op == I_FMA)
           o << "    " << acc << " = fma(" << scaled(k, i.x) << ", " << vname(i.y) << ", " << acc << ");\n";
@@ -1175,9 +1193,11 @@ struct spn_net {
       if (r.is_const()) return lit(r.coef);
       return scaled(r.coef, r.var);
     };
+    if (want_sum)   // the accumulators of the Monte-Carlo sum that are not fed link by link
+      for (size_t j = 0; j < sp.basis.size(); ++j)
+        if (!sp.basis[j].fused) o << "    acc" << j << " += " << (sp.basis[j].var < 0 ? lit(1.0) : vname(sp.basis[j].var)) << ";\n";
     for (uint64_t c = 0; c < size_out; ++c) {
       const std::string re = rr_expr(result_el[c].re), im = rr_expr(result_el[c].im);
-
       if (out_mode == 'n') continue;
       std::string idx = out_mode == 'p' ? "(p * " + std::to_string(size_out) + "ull + " + std::to_string(c) + "ull)"
                                         : "(" + std::to_string(c) + "ull * ocs + p)";
@@ -1205,9 +1225,9 @@ struct spn_net {
             if (!first) o << " + ";
             first = false;
             if (jk.second == 1.0)
-              o << "a" << jk.first;
+              o << "acc" << jk.first;
             else
-              o << lit(jk.second) << " * a" << jk.first;
+              o << lit(jk.second) << " * acc" << jk.first;
           }
           o << ";\n";
         }
@@ -1943,9 +1963,8 @@ uint64_t spn_net_input_bytes_per_point(const spn_net* net) { return net->stats.n
 // k and the D2H of chunk k-1 (both copy engines busy) — so device memory use is 3 chunks, whatever n_points is
 // (this is how 1e8-point Monte-Carlo batches run).  Host buffers should be pinned (spn_host_alloc) for the copies
 // to be asynchronous.  Synchronous: returns when host_out / host_sum are complete.
-int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
-                         void* host_out, double* host_sum, uint64_t chunk_points) {
-  NET_TRY
+static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
+                              void* host_out, double* host_sum, uint64_t chunk_points) {
   if (!net->compiled) throw Error(SPN_ERR_INVALID, "network is not compiled");
   if (!net->ctx) throw Error(SPN_ERR_NO_DEVICE, "plan-only network (created without a context) cannot execute");
   if (net->exec_mode != SPN_EXEC_FUSED) throw Error(SPN_ERR_INVALID, "execute_host needs a fused network");
@@ -1969,8 +1988,14 @@ int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t 
   const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
 
   auto& P = net->pipe;
-  for (int s = 0; s < spn_net::kPipe; ++s)
-    if (!P.stream[s]) cuda_check(cudaStreamCreateWithFlags(&P.stream[s], cudaStreamNonBlocking), "pipeline stream");
+  if (!P.fin) {
+    for (int s = 0; s < spn_net::kPipe; ++s) {
+      cuda_check(cudaStreamCreateWithFlags(&P.stream[s], cudaStreamNonBlocking), "pipeline stream");
+      cuda_check(cudaEventCreateWithFlags(&P.chunk_done[s], cudaEventDisableTiming), "pipeline event");
+    }
+    cuda_check(cudaStreamCreateWithFlags(&P.fin, cudaStreamNonBlocking), "pipeline stream");
+    for (int q = 0; q < 2; ++q) cuda_check(cudaEventCreateWithFlags(&P.fin_done[q], cudaEventDisableTiming), "pipeline event");
+  }
   if (P.chunk_points < chunk_points || P.partial_elems < cap * size_out || P.n_chunks_cap < n_chunks) {
     cuda_check(cudaDeviceSynchronize(), "pipeline resize");
     P.release();
@@ -1983,17 +2008,19 @@ int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t 
       cuda_check(cudaMalloc(&P.out[s], std::max<size_t>(chunk_points * size_out * 16, 32)), "pipeline staging");
       cuda_check(cudaMalloc((void**)&P.partial[s], std::max<size_t>(cap * size_out, 1) * sizeof(double2)), "pipeline staging");
     }
-    cuda_check(cudaMalloc((void**)&P.chunk_sums, std::max<uint64_t>(n_chunks, 1) * size_out * sizeof(double2)), "pipeline staging");
+    cuda_check(cudaMalloc((void**)&P.chunk_sums, 2 * std::max<uint64_t>(n_chunks, 1) * size_out * sizeof(double2)), "pipeline staging");
+    for (int q = 0; q < 2; ++q)
+      cuda_check(cudaMalloc((void**)&P.final_sum[q], std::max<uint64_t>(size_out, 1) * sizeof(double2)), "pipeline staging");
     P.chunk_points = chunk_points;
     P.partial_elems = cap * size_out;
     P.n_chunks_cap = n_chunks;
   }
-  // order the pipeline after whatever the context's stream has queued
-  cudaEvent_t ev;
-  cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
-  cuda_check(cudaEventRecord(ev, ctx->stream), "event");
-  for (int s = 0; s < spn_net::kPipe; ++s) cuda_check(cudaStreamWaitEvent(P.stream[s], ev, 0), "event");
-  cudaEventDestroy(ev);
+  const int parity = (int)(P.calls & 1);
+  ++P.calls;
+  double2* chunk_sums = P.chunk_sums + (size_t)parity * P.n_chunks_cap * size_out;
+  // the per-chunk sums of this parity were last read by the final stage two calls ago
+  if (host_sum && P.fin_pending[parity])
+    for (int s = 0; s < spn_net::kPipe; ++s) cuda_check(cudaStreamWaitEvent(P.stream[s], P.fin_done[parity], 0), "event");
 
   for (uint64_t c = 0; c < n_chunks; ++c) {
     const int s = (int)(c % spn_net::kPipe);
@@ -2024,7 +2051,7 @@ int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t 
                "launch fused network kernel");
     ctx->launches++;
     if (host_sum) {
-      cuda_check(launch_reduce_partials(partial, (int)grid, size_out, P.chunk_sums + c * size_out, st), "reduce_partials_kernel");
+      cuda_check(launch_reduce_partials(partial, (int)grid, size_out, chunk_sums + c * size_out, st), "reduce_partials_kernel");
       ctx->launches++;
     }
     if (host_out)
@@ -2032,22 +2059,60 @@ int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t 
                                  cudaMemcpyDeviceToHost, st),
                  "D2H of a chunk");
   }
-  for (int s = 0; s < spn_net::kPipe; ++s) cuda_check(cudaStreamSynchronize(P.stream[s]), "pipeline drain");
   if (host_sum) {
     if (n_chunks == 0) {
       std::memset(host_sum, 0, size_out * 16);
     } else {
-      // deterministic: one fixed-shape reduction over the per-chunk sums, on the context's stream
-      cuda_check(launch_reduce_partials(P.chunk_sums, (int)n_chunks, size_out, P.partial[0], ctx->stream), "reduce_partials_kernel");
+      // deterministic: one fixed-shape reduction over the per-chunk sums, after the last chunk of every stream
+      for (int s = 0; s < spn_net::kPipe; ++s) {
+        cuda_check(cudaEventRecord(P.chunk_done[s], P.stream[s]), "event");
+        cuda_check(cudaStreamWaitEvent(P.fin, P.chunk_done[s], 0), "event");
+      }
+      cuda_check(launch_reduce_partials(chunk_sums, (int)n_chunks, size_out, P.final_sum[parity], P.fin), "reduce_partials_kernel");
       ctx->launches++;
-      cuda_check(cudaMemcpyAsync(host_sum, P.partial[0], size_out * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H of the sum");
-      cuda_check(cudaStreamSynchronize(ctx->stream), "D2H of the sum");
+      cuda_check(cudaMemcpyAsync(host_sum, P.final_sum[parity], size_out * 16, cudaMemcpyDeviceToHost, P.fin), "D2H of the sum");
+      cuda_check(cudaEventRecord(P.fin_done[parity], P.fin), "event");
+      P.fin_pending[parity] = true;
     }
   }
+}
+
+int spn_net_host_wait(spn_net* net) {
+  NET_TRY
+  auto& P = net->pipe;
+  for (int s = 0; s < spn_net::kPipe; ++s)
+    if (P.stream[s]) cuda_check(cudaStreamSynchronize(P.stream[s]), "pipeline drain");
+  if (P.fin) cuda_check(cudaStreamSynchronize(P.fin), "pipeline drain");
   return SPN_OK;
   NET_CATCH(false)
 }
 
+int spn_net_execute_host_async(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
+                               void* host_out, double* host_sum, uint64_t chunk_points) {
+  NET_TRY
+  execute_host_impl(net, host_inputs, n_inputs, n_points, host_out, host_sum, chunk_points);
+  return SPN_OK;
+  NET_CATCH(false)
+}
+
+int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
+                         void* host_out, double* host_sum, uint64_t chunk_points) {
+  NET_TRY
+  execute_host_impl(net, host_inputs, n_inputs, n_points, host_out, host_sum, chunk_points);
+  return spn_net_host_wait(net);
+  NET_CATCH(false)
+}
+
+void* spn_host_alloc_flags(uint64_t bytes, int flags) {
+  void* p = nullptr;
+  const unsigned f = (flags & SPN_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : cudaHostAllocDefault;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, f) != cudaSuccess) {
+    spn::set_error("cudaHostAlloc failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
 void* spn_host_alloc(uint64_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {

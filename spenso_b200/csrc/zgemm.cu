@@ -204,9 +204,14 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
 }
 
 // ---- real (f64 x f64) variant: DGEMM on the same pipe -------------------------------------------------------------
-// CTA tile 128x128, 8 warps of 32(m) x 64(n), BK = 8, 4-stage cp.async pipeline of 8-byte gathers; 64-bit fragment
-// loads with conflict-free strides (A: BK+4 = 12, B: 128+4 = 132 doubles, both == 4 mod 16).
-constexpr int DBM = 128, DBN = 128, DSA = BK + 4, DSB = DBN + 4;
+// CTA tile 128x128, 8 warps of 32(m) x 64(n), BK = 8, 4-stage cp.async pipeline of 8-byte (or, VEC, 16-byte) gathers.
+// Fragments are read with 128-bit shared loads — half the load instructions per DMMA of 64-bit fragment loads:
+//   A: the two DMMA k-steps of a BK = 8 tile take the even and the odd k, so a lane's two A operands (k = 2 fk, 2 fk + 1)
+//      are adjacent in the natural [row][k] tile;
+//   B: the 8x8 tiles of a warp are paired and tile (j', e) owns the columns 16 j' + 2 c + e, so a lane's operands for a
+//      pair of tiles (columns 2 fr, 2 fr + 1) are adjacent in the natural [k][n] tile; the epilogue un-permutes.
+// Conflict-free strides in 16-byte units: A rows 4 (DSA = 8 doubles, no padding), B rows 65 (DSB = 130 doubles).
+constexpr int DBM = 128, DBN = 128, DSA = BK, DSB = DBN + 2;
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -348,23 +353,40 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     const int stage = (int)(kt % STAGES);
     const double* as = As + stage * DBM * DSA;
     const double* bs = Bs + stage * BK * DSB;
+    {
+      // a2[i] = A[row i][k = 2 fk, 2 fk + 1]; b2[s][j'] = B[k = 2 fk + s][columns 16 j' + 2 fr, + 1]
+      double2 a2[4], b2[2][4];
 #pragma unroll
-    for (int k4 = 0; k4 < BK / 4; ++k4) {
-      double a[4], b[8];
+      for (int i = 0; i < 4; ++i) a2[i] = *reinterpret_cast<const double2*>(as + (wm + 8 * i + fr) * DSA + 2 * fk);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = as[(wm + 8 * i + fr) * DSA + k4 * 4 + fk];
+      for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) b[j] = bs[(k4 * 4 + fk) * DSB + wn + 8 * j + fr];
+        for (int jp = 0; jp < 4; ++jp)
+          b2[s2][jp] = *reinterpret_cast<const double2*>(bs + (2 * fk + s2) * DSB + wn + 16 * jp + 2 * fr);
       if (SIGN) {
-        const ll k = kt * BK + k4 * 4 + fk;
-        const double sg = (k < K) ? __ldg(ksign + k) : 1.0;
+        const ll k = kt * BK + 2 * fk;
+        const double sg0 = (k < K) ? __ldg(ksign + k) : 1.0, sg1 = (k + 1 < K) ? __ldg(ksign + k + 1) : 1.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] *= sg;
+        for (int i = 0; i < 4; ++i) {
+          a2[i].x *= sg0;
+          a2[i].y *= sg1;
+        }
       }
+      // even k, then odd k; tile j = 2 j' + e
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dmma884(c[i][j][0], c[i][j][1], a[i], b[j]);
+        for (int jp = 0; jp < 4; ++jp) {
+          dmma884(c[i][2 * jp][0], c[i][2 * jp][1], a2[i].x, b2[0][jp].x);
+          dmma884(c[i][2 * jp + 1][0], c[i][2 * jp + 1][1], a2[i].x, b2[0][jp].y);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          dmma884(c[i][2 * jp][0], c[i][2 * jp][1], a2[i].y, b2[1][jp].x);
+          dmma884(c[i][2 * jp + 1][0], c[i][2 * jp + 1][1], a2[i].y, b2[1][jp].y);
+        }
     }
   }
   cp_async_wait<0>();
@@ -378,7 +400,8 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const ll cc = n0 + wn + 8 * j + 2 * fk + e;
+        // tile j = 2 j' + t holds, in its fragment column c8 = 2 fk + e, the tile column 16 j' + 2 c8 + t
+        const ll cc = n0 + wn + 16 * (j >> 1) + 2 * (2 * fk + e) + (j & 1);
         if (cc < N) C[orow + __ldg(out_col + cc)] = c[i][j][e];
       }
     }

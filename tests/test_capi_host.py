@@ -367,6 +367,26 @@ def test_sum_kernel_instruction_counts():
     assert net.variant_fp64_instr("ppns") <= 260
     assert net.variant_fp64_instr("ppps") == net.fp64_instr_per_point + 32     # with a per-point store nothing moves
     src = net.prepare_variant("ppns")
-    assert "a0 = fma(" in src and "const double sr0 = " in src
+    assert "acc0 = fma(" in src and "const double sr0 = " in src
     real = workloads.build_engine(workloads.one_loop_massive_real(), None)
     assert real.variant_fp64_instr("ppns") <= 146
+
+
+def test_symbolic_abstract_indices_are_interned_and_ordered_last():
+    """AbstractIndex::Symbol (abstract_index.rs:267-294) sorts after Normal < Dualize < Double < Dummy < Added, and among
+    symbols by creation order: names are interned to ids in first-seen order.  Canonical order and merge are bit-exact
+    with the oracle, and a contraction over a symbolic index is matched like any other."""
+    mu, nu, rho = (sp.symbol_slot(sp.Minkowski, 4, n) for n in ("test_mu", "test_nu", "test_rho"))
+    assert sp.symbol_slot(sp.Minkowski, 4, "test_mu").aind == mu.aind and nu.aind == mu.aind + 1 and rho.aind == nu.aind + 1
+    assert sp.lib().spn_symbol_name(mu.aind) == b"test_mu" and sp.lib().spn_symbol_name(1 << 40) is None
+    given = sp.slots([rho, sp.Minkowski.new_slot(4, 7), mu, sp.Slot(sp.Minkowski, 4, 3, sp.AIND_ADDED), nu])
+    canon, perm, _, _ = sp.canonicalize(given)
+    ocanon, operm, _, _ = O.order_structure(given)
+    assert canon.tobytes() == ocanon.tobytes() and list(perm) == list(operm)
+    assert [int(k) for k in canon["aind_kind"]] == [0, 4, 5, 5, 5] and [int(a) for a in canon["aind"][2:]] == [mu.aind, nu.aind, rho.aind]
+    a = sp.canonicalize([sp.Bispinor.new_slot(4, 1), mu, nu])[0]
+    b = sp.canonicalize([nu, sp.Bispinor.new_slot(4, 2), rho])[0]
+    p = sp.plan_contract(a, b)
+    assert p.n_common == 1 and p.order_out == 4 and p.k_metric[0] == 1          # the Minkowski index nu is contracted
+    om = O.merge(a, b)
+    assert bytes(p.out_slots)[:16 * 4] == om["slots"].tobytes()

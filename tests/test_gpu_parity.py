@@ -954,6 +954,34 @@ def test_dgemm_path_vs_oracle(ctx, case):
     assert not want.imag.any() and rel_err(c.to_numpy(), want.real) <= TOL
 
 
+@pytest.mark.parametrize("case", range(len(GEMM_CASES)))
+@pytest.mark.parametrize("real_first", [True, False])
+def test_mixed_real_complex_gemm_path_vs_oracle(ctx, case, real_first):
+    """f64 x Complex<f64> GEMM-shaped contractions run on the DMMA pipe too: the complex operand (and the result) is a
+    real matrix with twice the columns / rows, so one real GEMM over doubled gather tables does it.  The reference
+    upgrades the real operand to (x, 0.0) and multiplies complex numbers (upgrading_arithmetic.rs:1285-1318): same
+    values to 1e-12."""
+    rng = np.random.default_rng(700 + case)
+    a, b = (O.slots(*x) for x in GEMM_CASES[case])
+    ca, cb = O.order_structure(a)[0], O.order_structure(b)[0]
+    n_points = 2
+    shape_a, shape_b = [n_points] + [int(d) for d in ca["dim"]], [n_points] + [int(d) for d in cb["dim"]]
+    da = rng.uniform(-1, 1, size=shape_a) + (0 if real_first else 1j * rng.uniform(-1, 1, size=shape_a))
+    db = rng.uniform(-1, 1, size=shape_b) + (1j * rng.uniform(-1, 1, size=shape_b) if real_first else 0)
+    ta = sp.BatchTensor.empty(ctx, ca, n_points, sp.F64 if real_first else sp.C64)
+    ta.upload(np.ascontiguousarray(da.real if real_first else da).reshape(n_points, -1))
+    tb = sp.BatchTensor.empty(ctx, cb, n_points, sp.C64 if real_first else sp.F64)
+    tb.upload(np.ascontiguousarray(db if real_first else db.real).reshape(n_points, -1))
+    launches = ctx.launch_count
+    c = ta.contract(tb)
+    assert c.dtype == sp.C64 and ctx.launch_count == launches + 1
+    refs = [O.OTensor.dense(ca, da[p].astype(complex), canonicalize=False).contract(
+        O.OTensor.dense(cb, db[p].astype(complex), canonicalize=False)) for p in range(n_points)]
+    want = np.stack([r.to_dense() for r in refs])
+    assert c.slots.tobytes() == refs[0].slots.tobytes()
+    assert rel_err(c.to_numpy(), want) <= TOL
+
+
 def test_trace_of_shared_tensors_keeps_storage(ctx):
     """Trace::internal_contract on one-point tensors: dense stays dense, sparse stays sparse with exact zeros dropped
     (contraction/trace.rs:12-83); values and the stored index set equal the oracle's."""
@@ -1179,3 +1207,38 @@ def test_sum_only_kernels_commute_the_linear_tail(ctx, name, n_points, scale, re
     assert rel_err(out.to_numpy().reshape(n_points, -1), ref) <= TOL
     key = ("p" if layout == sp.POINT_MAJOR else "c") * net.n_inputs
     assert net.variant_fp64_instr(key + "ns") <= net.variant_fp64_instr(key + ("p" if layout == sp.POINT_MAJOR else "c") + "s")
+
+
+@pytest.mark.parametrize("name,scale,real", [("cfg2", 1.0, False), ("cfg5", 100.0, True)])
+def test_execute_host_async_keeps_order_and_results(ctx, name, scale, real):
+    """spn_net_execute_host_async: batches submitted back to back (the pipeline does not drain between calls) give,
+    after spn_net_host_wait, what the synchronous calls give — per-point results and Monte-Carlo sums, several calls in
+    flight, ragged chunking."""
+    import torch
+
+    spec = workloads.WORKLOADS[name]()
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    n = 10_007
+    batches, pinned = [], []
+    for k in range(5):
+        arrs = workloads.synthetic_inputs(spec, n, 100 + k, scale=scale, real=real)
+        pins = [torch.from_numpy(a.view(np.float64).reshape(n, -1)).pin_memory() for a in arrs]
+        pinned.append(pins)
+        batches.append([p.numpy().view(np.complex128).reshape(n, -1) for p in pins])
+    size = net.result_size
+    want_out, want_sum = [], []
+    for b in batches:
+        o = np.zeros((n, size), dtype=np.complex128)
+        _, s = net.execute_host(b, out=o, want_sum=True, chunk_points=1500)
+        want_out.append(o)
+        want_sum.append(s.copy())
+    outs = [torch.zeros(n * size * 2, dtype=torch.float64).pin_memory() for _ in batches]
+    sums = [np.zeros(size, dtype=np.complex128) for _ in batches]
+    for b, o, s in zip(batches, outs, sums):
+        net.execute_host_async(b, out=o.numpy().view(np.complex128).reshape(n, size), sum_out=s, chunk_points=1500)
+    net.host_wait()
+    for o, s, wo, ws in zip(outs, sums, want_out, want_sum):
+        assert np.array_equal(o.numpy().view(np.complex128).reshape(n, size), wo)
+        assert np.array_equal(s, ws)
+    ref, ref_sum, _ = O.eval_spec(spec, [b for b in batches[0]])
+    assert rel_err(want_out[0], ref) <= TOL and rel_err(want_sum[0], ref_sum) <= TOL
