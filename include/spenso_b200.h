@@ -120,8 +120,9 @@ void spn_ctx_destroy(spn_ctx* ctx);
 /* use an existing cudaStream_t (e.g. torch's current stream); NULL = the legacy default stream */
 int spn_ctx_set_stream(spn_ctx* ctx, void* cuda_stream);
 int spn_ctx_synchronize(spn_ctx* ctx);
-/* Results of the pairwise ops are allocated stream-ordered from the device's default memory pool, which keeps up
- * to 4 GiB of freed intermediates cached; this returns the cache to the driver (synchronises the stream). */
+/* Results of the pairwise ops are allocated stream-ordered from the device's default memory pool, which keeps freed
+ * intermediates cached for reuse (no release threshold: a finite one makes the driver unmap and remap result buffers
+ * at every synchronisation once the pool is large); this returns the cache to the driver (synchronises the stream). */
 int spn_ctx_release_cached_memory(spn_ctx* ctx);
 /* Parity triage switch.  emulate_interleaved_pairing != 0: contractions whose result interleaves the operands'
  * slots (MergeInfo::Interleaved) and that contract >= 2 indices enumerate each operand's contracted indices in its

@@ -697,10 +697,14 @@ int spn_ctx_create(int device, spn_ctx** out) {
   c->device = device;
   cuda_check(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "device attribute");
   cuda_check(cudaFree(0), "context init");
-  {  // keep freed intermediates in the pool instead of returning them to the OS at every synchronisation
+  {  // Freed intermediates stay in the device's memory pool until spn_ctx_release_cached_memory.  With a finite release
+     // threshold the driver returns "surplus" memory to the OS at synchronisation points as soon as the pool holds more
+     // than the threshold — resident inputs included — and the next result has to be mapped again: measured at 2^22
+     // points (profiles/r02_pairwise_pool.txt) every pairwise kernel that writes a 1 GiB result ran at 2.5-4.7 TB/s with
+     // a 4 GiB threshold and at 5.5-7.3 TB/s with none.  SPN_POOL_KEEP_GB restores a finite threshold.
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t keep = 4ull << 30;  // up to 4 GiB of freed intermediates stay cached across synchronisations
+      uint64_t keep = ~0ull;
       if (const char* e = getenv("SPN_POOL_KEEP_GB")) keep = (uint64_t)atof(e) << 30;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
