@@ -54,12 +54,21 @@ bool stageable(const spn_tensor* t) {
   const uint64_t bytes = t->size() * t->elem_bytes();
   return bytes % 16 == 0 && bytes >= 32 && ((uintptr_t)t->dptr % 16) == 0;
 }
-Staging staging_of(const spn_tensor* t) {
+// SPN_LOAD_MODE=tma: the operand slabs are moved by the TMA engine — one cp.async.bulk per operand and slab, completion
+// on an mbarrier (UBLKCP + SYNCS in SASS) — instead of per-lane 16-byte cp.async.  A bulk copy is linear, so the slab
+// lands UNPADDED and the thread = point reads that follow hit the same bank group 2..8 ways whenever the per-point size
+// is a multiple of 32 bytes.  Kept for measurement (profiles/r02_pairwise_tma.txt): it is slower than the padded
+// LDGSTS slabs on every shape of tools/pairwise_bench.py.
+bool tma_mode() {
+  static const bool on = getenv("SPN_LOAD_MODE") && std::string(getenv("SPN_LOAD_MODE")) == "tma";
+  return on;
+}
+Staging staging_of(const spn_tensor* t, bool operand) {
   Staging s;
   s.staged = stageable(t);
   if (s.staged) {
     s.units = t->size() * t->elem_bytes() / 16;
-    s.row = s.units | 1ull;  // odd: 8 consecutive rows start in 8 different 16-byte bank groups
+    s.row = (operand && tma_mode()) ? s.units : (s.units | 1ull);  // odd: 8 consecutive rows start in 8 different 16-byte bank groups
   }
   return s;
 }
@@ -88,7 +97,8 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
                    const spn_tensor* res, const std::string& kname, bool wide_stores) {
   const bool wide_loads = !getenv("SPN_NO_WIDE_LOADS");
   Generated gen;
-  Staging sa = a->sparse() ? Staging() : staging_of(a), sb = b->sparse() ? Staging() : staging_of(b), sc = staging_of(res);
+  Staging sa = a->sparse() ? Staging() : staging_of(a, true), sb = b->sparse() ? Staging() : staging_of(b, true), sc = staging_of(res, false);
+  const bool tma = tma_mode() && (sa.staged || sb.staged);
   gen.slab = sa.staged || sb.staged || sc.staged;
   // shared memory of one warp: [2 stages][A slab | B slab] then the result slab
   uint64_t stage_units = 0;
@@ -99,7 +109,7 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
   // (profiles/r02_pairwise_sweep.txt, 2^20 points, stages 1-4 x 2/4/8 warps per CTA): one stage is never slower and up to
   // 1.5x faster than 3-4 stages on the 256-1024 B operands — shared memory spent on extra stages costs resident
   // warps, and resident warps are what hides the latency here.  SPN_PAIR_STAGES=2..4 keeps the deeper rings reachable.
-  const uint64_t out_units = sc.staged ? 32 * sc.row : 0;
+  const uint64_t out_units = (sc.staged ? 32 * sc.row : 0) + (tma_mode() ? 2 : 0);   // + the mbarriers of the TMA variant
   const uint64_t budget = 216 * 1024 / 16;   // 16-byte units of shared memory per SM the kernel may plan with
   const int forced_stages = getenv("SPN_PAIR_STAGES") ? std::max(1, std::min(4, atoi(getenv("SPN_PAIR_STAGES")))) : 0;
   int n_stages = forced_stages ? forced_stages : 1;
@@ -142,6 +152,14 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
     o << "  extern __shared__ __align__(16) double2 smem[];\n";
     o << "  const unsigned lane = threadIdx.x & 31u;\n";
     o << "  double2* const ws = smem + (threadIdx.x >> 5) * " << warp_units << "u;   // this warp's slabs\n";
+    if (tma) {
+      o << "  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(ws + " << (warp_units - 2) << "u);   // one mbarrier per stage\n";
+      o << "  if (lane == 0) {\n";
+      o << "    for (unsigned s = 0; s < " << n_stages << "u; ++s)\n";
+      o << "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" :: \"r\"((unsigned)__cvta_generic_to_shared(bars + s)) : \"memory\");\n";
+      o << "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n";
+      o << "  }\n  __syncwarp();\n  unsigned phases = 0;\n";
+    }
     o << "  const ull n_slabs = (n_points + 31ull) >> 5;\n";
     o << "  const ull n_warps = (ull)gridDim.x * " << warps << "ull;\n";
     o << "  ull slab = (ull)blockIdx.x * " << warps << "ull + (threadIdx.x >> 5);\n";
@@ -149,9 +167,27 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
     o << "  auto issue = [&](ull sl, unsigned stage) {\n";
     o << "    const ull p0 = sl << 5;\n";
     o << "    const unsigned np = (unsigned)(n_points - p0 < 32ull ? n_points - p0 : 32ull);\n";
+    if (tma) {
+      // one elected lane arms the stage's mbarrier with the byte count and launches the bulk copies
+      o << "    if (lane == 0) {\n";
+      o << "      const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + stage);\n";
+      o << "      unsigned bytes = 0;\n";
+      for (auto pr : {std::make_pair(&sa, 'A'), std::make_pair(&sb, 'B')})
+        if (pr.first->staged) o << "      bytes += np * " << pr.first->units * 16 << "u;\n";
+      o << "      asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");   // earlier generic reads of this stage are done\n";
+      o << "      asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\" :: \"r\"(bar), \"r\"(bytes) : \"memory\");\n";
+      for (auto pr : {std::make_pair(&sa, 'A'), std::make_pair(&sb, 'B')}) {
+        const Staging& s = *pr.first;
+        if (!s.staged) continue;
+        o << "      asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\" :: "
+             "\"r\"((unsigned)__cvta_generic_to_shared(ws + stage * " << stage_units << "u + " << s.offset << "u)), \"l\"(reinterpret_cast<const double2*>("
+          << pr.second << ") + p0 * " << s.units << "ull), \"r\"(np * " << s.units * 16 << "u), \"r\"(bar) : \"memory\");\n";
+      }
+      o << "    }\n";
+    }
     for (auto pr : {std::make_pair(&sa, 'A'), std::make_pair(&sb, 'B')}) {
       const Staging& s = *pr.first;
-      if (!s.staged) continue;
+      if (!s.staged || tma) continue;
       o << "    {\n      const double2* src = reinterpret_cast<const double2*>(" << pr.second << ") + p0 * " << s.units << "ull;\n";
       o << "      double2* dst = ws + stage * " << stage_units << "u + " << s.offset << "u;\n";
       o << "      const unsigned lim = np * " << s.units << "u;\n";
@@ -183,6 +219,13 @@ Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_t
       o << "    asm volatile(\"cp.async.wait_group " << (n_stages - 1) << ";\" ::: \"memory\");\n";
     } else {
       o << "    asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\");\n";
+    }
+    if (tma) {
+      o << "    {\n      const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + stage), ph = (phases >> stage) & 1u;\n";
+      o << "      unsigned done = 0;\n";
+      o << "      while (!done)\n";
+      o << "        asm volatile(\"{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\" : \"=r\"(done) : \"r\"(bar), \"r\"(ph) : \"memory\");\n";
+      o << "      phases ^= 1u << stage;\n    }\n";
     }
     o << "    __syncwarp();\n";
     o << "    const ull p0 = slab << 5;\n    const ull p = p0 + lane;\n";
@@ -355,6 +398,7 @@ PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTable
     key.push_back(stageable(t) ? 'S' : 'd');
   }
   key.push_back(wide ? 'w' : 'n');
+  key.push_back(tma_mode() ? 'T' : 'L');
   key.append(reinterpret_cast<const char*>(kt.off_a.data()), kt.off_a.size() * sizeof(long long));
   key.append(reinterpret_cast<const char*>(kt.off_b.data()), kt.off_b.size() * sizeof(long long));
   key.append(reinterpret_cast<const char*>(kt.sign.data()), kt.sign.size());
