@@ -16,6 +16,7 @@ struct JitKernel {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t kernel = nullptr;
   int blocks_per_sm = 0;
+  int block = 0;          // threads per CTA this kernel was generated for (0: the caller's default)
   int num_regs = 0;
   size_t smem_bytes = 0;  // dynamic shared memory (prefetch ring)
   ~JitKernel() {

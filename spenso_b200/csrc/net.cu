@@ -676,7 +676,13 @@ struct spn_net {
   // measured: L1::no_allocate on the once-read streaming loads is +1 % (cfg2 point-major), +3 % (cfg2mr), +7-8 %
   // (component-major cfg2, cfg3) over plain ld.global.nc; evict_first is equivalent
   static constexpr const char* kDefaultLoadHint = ".L1::no_allocate";
-  enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2 };
+  //   GATHER sparse-touch networks on large point-major records (cfg3: 71 of 584 components of a 9 KB record): read
+  //         thread = point, every 16-byte load of a warp lands in a different record, 9 KB apart — one sector per DRAM row.
+  //         Instead a warp owns slabs of 32 points and gathers them point by point: lane L copies the needed units L,
+  //         L + 32, ... of ONE record per cp.async instruction (the accesses of an instruction stay inside one record),
+  //         into a padded [point][unit] slab; then lane = point computes from shared memory.
+  enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2, PF_GATHER = 3 };
+  static constexpr int kGatherBlock = 64;   // threads per CTA of a GATHER kernel: 2 warps, each with its own slab
   const int kRingDepth = (getenv("SPN_RING_DEPTH") && (atoi(getenv("SPN_RING_DEPTH")) == 2 || atoi(getenv("SPN_RING_DEPTH")) == 8)) ? atoi(getenv("SPN_RING_DEPTH")) : 4;  // power of two
   struct PrefetchPlan {
     int mode = PF_NONE;
@@ -731,7 +737,33 @@ struct spn_net {
     const uint64_t size_out = result_el.size();
     const double t_fp = (double)stats.n_fp / (64.0 * 148.0 * 1.9e9);
     const double t_hbm = (double)(stats.n_load_bytes + (out_mode == 'n' ? 0 : 16 * size_out)) / 6.5e12;
-    if (stats.n_load_bytes == 0 || stats.n_load_bytes > 512 || t_fp <= 0.5 * t_hbm || getenv("SPN_NO_PREFETCH")) return pf;
+    if (stats.n_load_bytes == 0 || getenv("SPN_NO_PREFETCH")) return pf;
+    {
+      // GATHER: all inputs point-major, only 16-byte units, at most half of the input bytes touched, records >= 1 KB
+      bool all_p = n_inputs > 0;
+      uint64_t total_bytes = 0, max_record = 0;
+      for (uint32_t in = 0; in < n_inputs; ++in) {
+        all_p = all_p && (variant[in] == 'p' || variant[in] == 'q');
+        const Node& nd = nodes[input_nodes[(size_t)in]];
+        const uint64_t rec = nd.st.size() * (nd.dtype == SPN_C64 ? 16 : 8);
+        total_bytes += rec;
+        max_record = std::max(max_record, rec);
+      }
+      if (all_p && max_record >= 1024 && 2 * stats.n_load_bytes <= total_bytes && getenv("SPN_GATHER")) {
+        const std::vector<RingUnit> units = ring_units(variant);
+        bool all16 = units.size() >= 16;
+        for (auto& u : units) all16 = all16 && u.kind != 2;
+        const size_t row = units.size() | 1u;
+        const size_t bytes = (size_t)(kGatherBlock / 32) * 32 * row * 16;
+        if (all16 && bytes <= 200 * 1024) {
+          pf.mode = PF_GATHER;
+          pf.n_loads = (uint32_t)units.size();
+          pf.smem_bytes = bytes;
+          return pf;
+        }
+      }
+    }
+    if (stats.n_load_bytes > 512 || t_fp <= 0.5 * t_hbm) return pf;
     pf.n_loads = (uint32_t)ring_units(variant).size();
     pf.smem_bytes = (size_t)kRingDepth * pf.n_loads * (size_t)kBlock * 16;
     const size_t ring_max = (size_t)(getenv("SPN_RING_MAX_KB") ? atoi(getenv("SPN_RING_MAX_KB")) : 200) * 1024;
@@ -864,7 +896,10 @@ struct spn_net {
     return sp;
   }
 
+  int variant_block(const std::string& variant) const { return plan_prefetch(variant).mode == PF_GATHER ? kGatherBlock : kBlock; }
+
   std::string gen_source(const std::string& variant, const std::string& kname) const {
+    const int kBlock = variant_block(variant);   // shadows the member: threads per CTA of THIS variant
     const uint64_t size_out = result_el.size();
     const char out_mode = variant[n_inputs];
     const bool out_real = variant.find('r', n_inputs) != std::string::npos;
@@ -1025,7 +1060,56 @@ struct spn_net {
         a << "in" << i.in << " + (" << pv << " * " << n.st.size() << "ull + " << i.flat << "ull) * " << w;
       return a.str();
     };
-    if (pf.mode == PF_RING) {
+    if (pf.mode == PF_GATHER) {
+      std::vector<RingUnit> units = ring_units(variant);
+      // ascending addresses inside a record: neighbouring lanes fetch neighbouring sectors
+      std::stable_sort(units.begin(), units.end(), [](const RingUnit& x, const RingUnit& y) {
+        return x.in != y.in ? x.in < y.in : x.flat < y.flat;
+      });
+      const size_t nu = units.size(), row = nu | 1u, per_lane = (nu + 31) / 32;
+      o << "  extern __shared__ __align__(16) double2 ring[];   // [" << kBlock / 32 << " warps][32 points][" << row << " units]\n";
+      o << "  const unsigned lane = threadIdx.x & 31u;\n";
+      o << "  double2* const slab = ring + (threadIdx.x >> 5) * " << 32 * row << "u;\n";
+      // the units this lane gathers of every record: (input, byte offset inside the record)
+      o << "  const unsigned char* ub[" << per_lane << "]; ull us[" << per_lane << "];\n";
+      for (size_t j = 0; j < per_lane; ++j) {
+        o << "  {\n    const unsigned u = lane + " << 32 * j << "u;\n";
+        o << "    const unsigned char* b = nullptr; ull st = 0, off = 0;\n    switch (u) {\n";
+        for (size_t e = 32 * j; e < std::min(nu, 32 * (j + 1)); ++e) {
+          const Node& n = nodes[input_nodes[(size_t)units[e].in]];
+          const uint64_t eb = n.dtype == SPN_C64 ? 16 : 8;
+          o << "      case " << e << ": b = reinterpret_cast<const unsigned char*>(in" << units[e].in << "); st = " << n.st.size() * eb
+            << "ull; off = " << units[e].flat * eb << "ull; break;\n";
+        }
+        o << "      default: break;\n    }\n    ub[" << j << "] = b ? b + off : nullptr; us[" << j << "] = st;\n  }\n";
+      }
+      o << "  const ull n_slabs = (n_points + 31ull) >> 5;\n";
+      o << "  for (ull sl = (ull)blockIdx.x * " << kBlock / 32 << "ull + (threadIdx.x >> 5); sl < n_slabs; sl += (ull)gridDim.x * "
+        << kBlock / 32 << "ull) {\n";
+      o << "    const ull p0 = sl << 5;\n";
+      o << "    const unsigned np = (unsigned)(n_points - p0 < 32ull ? n_points - p0 : 32ull);\n";
+      o << "#pragma unroll 4\n    for (unsigned q = 0; q < np; ++q) {\n";
+      for (size_t j = 0; j < per_lane; ++j)
+        o << "      if (ub[" << j << "]) cp_async16(slab + q * " << row << "u + lane + " << 32 * j << "u, reinterpret_cast<const double*>(ub["
+          << j << "] + (p0 + q) * us[" << j << "]));\n";
+      o << "    }\n";
+      o << "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
+      o << "    asm volatile(\"cp.async.wait_group 0;\" ::: \"memory\");\n";
+      o << "    __syncwarp();\n";
+      o << "    const ull p = p0 + lane;\n";
+      o << "    if (lane < np) {\n";
+      o << "    const double2* const mine = slab + lane * " << row << "u;\n";
+      for (size_t e = 0; e < nu; ++e) {
+        const RingUnit& u = units[e];
+        if (u.kind == 0) {
+          o << "    const double2 l" << u.dst0 << " = mine[" << e << "];\n";
+        } else {
+          o << "    const double2 u" << e << " = mine[" << e << "];\n";
+          if (u.dst0 >= 0) o << "    const double l" << u.dst0 << " = u" << e << ".x;\n";
+          if (u.dst1 >= 0) o << "    const double l" << u.dst1 << " = u" << e << ".y;\n";
+        }
+      }
+    } else if (pf.mode == PF_RING) {
       o << "  extern __shared__ __align__(16) double2 ring[];   // [" << kRingDepth << " slots][" << pf.n_loads << " loads]["
         << kBlock << " threads]\n";
       o << "  ull p = (ull)blockIdx.x * " << kBlock << " + threadIdx.x;\n  const ull stride = (ull)gridDim.x * " << kBlock << ";\n";
@@ -1209,6 +1293,7 @@ struct spn_net {
     if (pf.mode == PF_REGS)
       for (const Ins& i : prog.ins)
         if (i.op == I_LOADC || i.op == I_LOADR) o << "    l" << i.dst << " = n" << i.dst << ";\n";
+    if (pf.mode == PF_GATHER) o << "    }\n    __syncwarp();   // the slab is re-used by the next iteration\n";
     if (pf.mode == PF_RING)  // refill the slot just consumed with the point kRingDepth iterations ahead
       o << "    if (p + " << kRingDepth << " * stride < n_points) issue(p + " << kRingDepth << " * stride, slot);\n"
            "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";
@@ -1258,6 +1343,7 @@ struct spn_net {
     k->name = nm;
     k->source = gen_source(variant, k->name);
     k->smem_bytes = plan_prefetch(variant).smem_bytes;
+    k->block = variant_block(variant);
     // occupancy experiments: SPN_PAD_SMEM_KB adds unused dynamic shared memory (fewer CTAs per SM, grid follows)
     if (const char* e = getenv("SPN_PAD_SMEM_KB")) k->smem_bytes += (size_t)atoi(e) * 1024;
     jit_compile(*k);
@@ -1984,7 +2070,8 @@ static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint
   variant += host_out ? 'p' : 'n';
   if (host_sum) variant += 's';
   JitKernel& k = net->get_variant(variant);
-  jit_load(k, net->kBlock);
+  const int kblock = k.block ? k.block : net->kBlock;
+  jit_load(k, kblock);
   const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
 
   auto& P = net->pipe;
@@ -2037,7 +2124,7 @@ static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint
     double* out_ptr = host_out ? static_cast<double*>(P.out[s]) : nullptr;
     unsigned long long ocs = chunk_points, np = cnt;
     double2* partial = host_sum ? P.partial[s] : nullptr;
-    const unsigned grid = (unsigned)std::min<uint64_t>((cnt + net->kBlock - 1) / net->kBlock, cap);
+    const unsigned grid = (unsigned)std::min<uint64_t>((cnt + kblock - 1) / kblock, cap);
     std::vector<void*> args;
     for (uint32_t i = 0; i < n_inputs; ++i) {
       args.push_back(&in_ptr[i]);
@@ -2047,7 +2134,7 @@ static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint
     args.push_back(&ocs);
     args.push_back(&partial);
     args.push_back(&np);
-    cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), k.smem_bytes, st),
+    cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3((unsigned)kblock), args.data(), k.smem_bytes, st),
                "launch fused network kernel");
     ctx->launches++;
     if (host_sum) {
@@ -2181,7 +2268,8 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   if (out && out->dtype == SPN_F64) variant += 'r';
   if (sum_out_device) variant += 's';
   JitKernel& k = net->get_variant(variant);
-  jit_load(k, net->kBlock);
+  const int kblock = k.block ? k.block : net->kBlock;
+  jit_load(k, kblock);
 
   if (n_points == 0) {
     // an empty shard (world > n_points) still takes part in the exchange: its contribution is zero, and a rank that
@@ -2192,7 +2280,7 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
     }
     return SPN_OK;
   }
-  const uint64_t need = (n_points + net->kBlock - 1) / net->kBlock;
+  const uint64_t need = (n_points + kblock - 1) / kblock;
   const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
   const unsigned grid = (unsigned)std::min<uint64_t>(need, cap);
 
@@ -2235,7 +2323,7 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
   args.push_back(&ocs);
   args.push_back(&partial);
   args.push_back(&np);
-  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(net->kBlock), args.data(), k.smem_bytes, ctx->stream),
+  cuda_check(cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3((unsigned)kblock), args.data(), k.smem_bytes, ctx->stream),
              "launch fused network kernel");
   ctx->launches++;
   if (sum_out_device && net->comm) {
