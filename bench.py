@@ -939,7 +939,7 @@ def run_b200(args):
     suite = args.suite or ("full" if (wl == "cfg2" and args.exec_mode == "fused" and args.layout == "point" and not args.points) else "headline")
     n = args.points or DEFAULT_POINTS[wl]
     head = measure_network(job, args, wl, n, args.layout, K=args.steps, W=args.warmup, exec_mode=args.exec_mode,
-                           mc_sum=args.mc_sum, allreduce=args.allreduce, on_device_inputs=False, e2e=True, cpu=True,
+                           mc_sum=args.mc_sum, allreduce=args.allreduce, on_device_inputs=args.no_e2e, e2e=not args.no_e2e, cpu=True,
                            sustained_s=args.sustained_seconds)
     extra = run_suite(job, args) if suite == "full" else None
     if job.rank == 0:
