@@ -697,6 +697,17 @@ int spn_ctx_create(int device, spn_ctx** out) {
   c->device = device;
   cuda_check(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device), "device attribute");
   cuda_check(cudaFree(0), "context init");
+  // L2 fetch granularity (bytes an L2 miss brings in from HBM): SPN_L2_FETCH=32|64|128 overrides the default set below
+  if (const char* e = getenv("SPN_L2_FETCH")) {
+    const int g = atoi(e);
+    if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)g);
+    cudaGetLastError();
+  }
+  {
+    size_t cur = 0;
+    if (cudaDeviceGetLimit(&cur, cudaLimitMaxL2FetchGranularity) == cudaSuccess) c->l2_fetch_granularity = (int)cur;
+    cudaGetLastError();
+  }
   {  // Freed intermediates stay in the device's memory pool until spn_ctx_release_cached_memory.  With a finite release
      // threshold the driver returns "surplus" memory to the OS at synchronisation points as soon as the pool holds more
      // than the threshold — resident inputs included — and the next result has to be mapped again: measured at 2^22

@@ -31,6 +31,7 @@ struct spn_ctx {
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
   int sm_count = 148;
+  int l2_fetch_granularity = 0;   // cudaLimitMaxL2FetchGranularity in effect when the context was created
   bool emulate_reference_pairing = false;  // SURVEY K-note 3, see build_k_tables
   // specialised pairwise kernels (pairwise_jit.cu), keyed by a hash of (plan, storage, dtype, layout)
   std::map<uint64_t, spn::PairJit> pair_kernels;

@@ -204,14 +204,16 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
 }
 
 // ---- real (f64 x f64) variant: DGEMM on the same pipe -------------------------------------------------------------
-// CTA tile 128x128, 8 warps of 32(m) x 64(n), BK = 8, 4-stage cp.async pipeline of 8-byte (or, VEC, 16-byte) gathers.
+// CTA tile 128x128, 8 warps of 32(m) x 64(n), BK = 16 (round 2: one barrier per 128 DMMAs of a warp, like the complex
+// kernel; BK = 8 spent twice as many barriers and loop iterations per DMMA and ran at 0.83-0.85 of cuBLAS), 4-stage
+// cp.async pipeline of 8-byte (or, VEC, 16-byte) gathers.
 // Fragments are read with 128-bit shared loads — half the load instructions per DMMA of 64-bit fragment loads:
-//   A: the two DMMA k-steps of a BK = 8 tile take the even and the odd k, so a lane's two A operands (k = 2 fk, 2 fk + 1)
-//      are adjacent in the natural [row][k] tile;
+//   A: the two DMMA k-steps of each group of 8 k take its even and its odd k, so a lane's two A operands (k = 2 fk,
+//      2 fk + 1) are adjacent in the natural [row][k] tile;
 //   B: the 8x8 tiles of a warp are paired and tile (j', e) owns the columns 16 j' + 2 c + e, so a lane's operands for a
 //      pair of tiles (columns 2 fr, 2 fr + 1) are adjacent in the natural [k][n] tile; the epilogue un-permutes.
-// Conflict-free strides in 16-byte units: A rows 4 (DSA = 8 doubles, no padding), B rows 65 (DSB = 130 doubles).
-constexpr int DBM = 128, DBN = 128, DSA = BK, DSB = DBN + 2;
+// Conflict-free strides in 16-byte units: A rows 12 (DSA = 24 doubles), B rows 65 (DSB = 130 doubles).
+constexpr int DBM = 128, DBN = 128, DBK = 16, DSA = DBK + 8, DSB = DBN + 2;
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -229,8 +231,8 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
                       const double* __restrict__ ksign, ll M, ll N, ll K, ll ps_a, ll ps_b, ll ps_c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* As = reinterpret_cast<double*>(smem_raw);            // [STAGES][DBM][DSA]
-  double* Bs = As + STAGES * DBM * DSA;                         // [STAGES][BK][DSB]
-  ll* s_row = reinterpret_cast<ll*>(Bs + STAGES * BK * DSB);    // [DBM]
+  double* Bs = As + STAGES * DBM * DSA;                         // [STAGES][DBK][DSB]
+  ll* s_row = reinterpret_cast<ll*>(Bs + STAGES * DBK * DSB);   // [DBM]
   ll* s_col = s_row + DBM;                                      // [DBN]
 
   const ll tiles_m = (M + DBM - 1) / DBM, tiles_n = (N + DBN - 1) / DBN;
@@ -252,51 +254,53 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
   if (tid >= 128) s_col[tid - 128] = (n0 + tid - 128 < N) ? __ldg(col_b + n0 + tid - 128) : -1;
   __syncthreads();
 
-  // loaders: A tile 128 rows x 8 k -> 4 elements per thread (k fastest); B tile 8 k x 128 n -> 4 per thread (n fastest)
-  const int a_kk = tid & 7, a_r0 = tid >> 3;       // rows a_r0 + 32 i
-  const int b_n = tid & 127, b_k0 = tid >> 7;      // k rows b_k0 + 2 i
-  const ll KT = (K + BK - 1) / BK;
-  ll ka_next = 0, kb_next[4] = {0, 0, 0, 0};
+  // loaders (8-byte gathers): A tile 128 rows x 16 k -> 8 elements per thread (k fastest across threads: k = tid & 15,
+  //                           rows tid / 16 + 16 i); B tile 16 k x 128 n -> 8 per thread (n = tid & 127, k = tid / 128 + 2 i)
+  const int a_kk = tid & 15, a_r0 = tid >> 4;
+  const int b_n = tid & 127, b_k0 = tid >> 7;
+  const ll KT = (K + DBK - 1) / DBK;
+  ll ka_next = 0, kb_next[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto fetch_koffs = [&](ll kt) {
-    const ll kbase = kt * BK;
+    const ll kbase = kt * DBK;
     const ll k = kbase + a_kk;
     ka_next = (kt < KT && k < K) ? __ldg(k_a + k) : 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const ll kk = kbase + b_k0 + 2 * i;
       kb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
     }
   };
-  // VEC loaders: A 128 rows x 4 k-pairs -> 2 copies per thread; B 8 k x 64 n-pairs -> 2 copies per thread
-  const int va_kp = tid & 3, va_r0 = tid >> 2;     // rows va_r0 + 64 i, k = 2 va_kp
-  const int vb_np = tid & 63, vb_k0 = tid >> 6;    // k rows vb_k0 + 4 i, n = 2 vb_np
-  ll vka_next = 0, vkb_next[2] = {0, 0};
+  // VEC loaders: A 128 rows x 8 k-pairs -> 4 copies per thread (k pair = tid & 7, rows tid / 8 + 32 i);
+  //              B 16 k x 64 n-pairs -> 4 copies per thread (n pair = tid & 63, k = tid / 64 + 4 i)
+  const int va_kp = tid & 7, va_r0 = tid >> 3;
+  const int vb_np = tid & 63, vb_k0 = tid >> 6;
+  ll vka_next = 0, vkb_next[4] = {0, 0, 0, 0};
   auto fetch_koffs_vec = [&](ll kt) {
-    const ll kbase = kt * BK;
+    const ll kbase = kt * DBK;
     const ll k = kbase + 2 * va_kp;
     vka_next = (kt < KT && k < K) ? __ldg(k_a + k) : 0;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const ll kk = kbase + vb_k0 + 4 * i;
       vkb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
     }
   };
   auto load_tile = [&](int stage, ll kt) {
-    const ll kbase = kt * BK;
+    const ll kbase = kt * DBK;
     double* as = As + stage * DBM * DSA;
-    double* bs = Bs + stage * BK * DSB;
+    double* bs = Bs + stage * DBK * DSB;
     if (VEC) {
       const bool kv = kbase + 2 * va_kp < K;
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int r = va_r0 + 64 * i;
+      for (int i = 0; i < 4; ++i) {
+        const int r = va_r0 + 32 * i;
         const ll ro = s_row[r];
         const bool v = kv && ro >= 0;
         cp_async16(as + r * DSA + 2 * va_kp, A + (v ? ro + vka_next : 0), v);
       }
       const ll co = s_col[2 * vb_np];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int kk = vb_k0 + 4 * i;
         const bool v = kbase + kk < K && co >= 0;
         cp_async16(bs + kk * DSB + 2 * vb_np, B + (v ? co + vkb_next[i] : 0), v);
@@ -305,15 +309,15 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     }
     const bool kv = kbase + a_kk < K;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = a_r0 + 32 * i;
+    for (int i = 0; i < 8; ++i) {
+      const int r = a_r0 + 16 * i;
       const ll ro = s_row[r];
       const bool v = kv && ro >= 0;
       cp_async8(as + r * DSA + a_kk, A + (v ? ro + ka_next : 0), v);
     }
     const ll co = s_col[b_n];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int kk = b_k0 + 2 * i;
       const bool v = kbase + kk < K && co >= 0;
       cp_async8(bs + kk * DSB + b_n, B + (v ? co + kb_next[i] : 0), v);
@@ -352,19 +356,20 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     }
     const int stage = (int)(kt % STAGES);
     const double* as = As + stage * DBM * DSA;
-    const double* bs = Bs + stage * BK * DSB;
-    {
-      // a2[i] = A[row i][k = 2 fk, 2 fk + 1]; b2[s][j'] = B[k = 2 fk + s][columns 16 j' + 2 fr, + 1]
+    const double* bs = Bs + stage * DBK * DSB;
+#pragma unroll
+    for (int h = 0; h < DBK / 8; ++h) {   // groups of 8 k: two DMMA k-steps each (even k, odd k)
+      // a2[i] = A[row i][k = 8 h + 2 fk, + 1]; b2[s][j'] = B[k = 8 h + 2 fk + s][columns 16 j' + 2 fr, + 1]
       double2 a2[4], b2[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a2[i] = *reinterpret_cast<const double2*>(as + (wm + 8 * i + fr) * DSA + 2 * fk);
+      for (int i = 0; i < 4; ++i) a2[i] = *reinterpret_cast<const double2*>(as + (wm + 8 * i + fr) * DSA + 8 * h + 2 * fk);
 #pragma unroll
       for (int s2 = 0; s2 < 2; ++s2)
 #pragma unroll
         for (int jp = 0; jp < 4; ++jp)
-          b2[s2][jp] = *reinterpret_cast<const double2*>(bs + (2 * fk + s2) * DSB + wn + 16 * jp + 2 * fr);
+          b2[s2][jp] = *reinterpret_cast<const double2*>(bs + (8 * h + 2 * fk + s2) * DSB + wn + 16 * jp + 2 * fr);
       if (SIGN) {
-        const ll k = kt * BK + 2 * fk;
+        const ll k = kt * DBK + 8 * h + 2 * fk;
         const double sg0 = (k < K) ? __ldg(ksign + k) : 1.0, sg1 = (k + 1 < K) ? __ldg(ksign + k + 1) : 1.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -418,7 +423,7 @@ cudaError_t launch_contract_dgemm(const double* A, const double* B, double* C, c
   if (M == 0 || N == 0 || n_points == 0) return cudaSuccess;
   const ll tiles = ((M + DBM - 1) / DBM) * ((N + DBN - 1) / DBN);
   if (tiles > 0x7fffffffLL || n_points > 65535) return cudaErrorInvalidConfiguration;
-  const size_t smem = (size_t)STAGES * (DBM * DSA + BK * DSB) * sizeof(double) + (DBM + DBN) * sizeof(long long);
+  const size_t smem = (size_t)STAGES * (DBM * DSA + DBK * DSB) * sizeof(double) + (DBM + DBN) * sizeof(long long);
   dim3 grid((unsigned)tiles, (unsigned)n_points);
   cudaError_t e = cudaSuccess;
 #define SPN_LAUNCH_DGEMM(SG, VC)                                                                                          \
