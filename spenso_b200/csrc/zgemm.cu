@@ -204,16 +204,17 @@ contract_zgemm_kernel(const double2* __restrict__ A, const double2* __restrict__
 }
 
 // ---- real (f64 x f64) variant: DGEMM on the same pipe -------------------------------------------------------------
-// CTA tile 128x128, 8 warps of 32(m) x 64(n), BK = 16 (round 2: one barrier per 128 DMMAs of a warp, like the complex
-// kernel; BK = 8 spent twice as many barriers and loop iterations per DMMA and ran at 0.83-0.85 of cuBLAS), 4-stage
-// cp.async pipeline of 8-byte (or, VEC, 16-byte) gathers.
+// CTA tile 128(m) x 64(n), 4 warps of 32 x 64, two CTAs per SM (like the complex kernel: the barrier of one CTA is
+// covered by the other), BK = 16 (one barrier per 128 DMMAs of a warp), 3-stage cp.async pipeline of 8-byte (or, VEC,
+// 16-byte) gathers.  Round-2 history, fraction of cuBLAS DGEMM on 32768^3: 128x128 / 8 warps / BK 8 / 64-bit fragment
+// loads 0.83 -> 128-bit fragment loads 0.85 -> BK 16 0.87 -> this shape 0.95 (profiles/README.md).
 // Fragments are read with 128-bit shared loads — half the load instructions per DMMA of 64-bit fragment loads:
 //   A: the two DMMA k-steps of each group of 8 k take its even and its odd k, so a lane's two A operands (k = 2 fk,
 //      2 fk + 1) are adjacent in the natural [row][k] tile;
 //   B: the 8x8 tiles of a warp are paired and tile (j', e) owns the columns 16 j' + 2 c + e, so a lane's operands for a
 //      pair of tiles (columns 2 fr, 2 fr + 1) are adjacent in the natural [k][n] tile; the epilogue un-permutes.
-// Conflict-free strides in 16-byte units: A rows 12 (DSA = 24 doubles), B rows 65 (DSB = 130 doubles).
-constexpr int DBM = 128, DBN = 128, DBK = 16, DSA = DBK + 8, DSB = DBN + 2;
+// Conflict-free strides in 16-byte units: A rows 12 (DSA = 24 doubles), B rows 33 (DSB = 66 doubles).
+constexpr int DBM = 128, DBN = 64, DBK = 16, DSA = DBK + 8, DSB = DBN + 2, DSTAGES = 3, DTHREADS = 128;
 
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -224,15 +225,15 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool val
 // VEC: the gather tables are pairwise contiguous and even (k_a[2j+1] = k_a[2j] + 1, col_b[2j+1] = col_b[2j] + 1, all
 // base offsets even), so operands move with 16-byte cp.async — half the copy instructions of the 8-byte gather.
 template <bool SIGN, bool VEC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(DTHREADS, 2)
 contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                       const ll* __restrict__ row_a, const ll* __restrict__ k_a, const ll* __restrict__ col_b,
                       const ll* __restrict__ k_b, const ll* __restrict__ out_row, const ll* __restrict__ out_col,
                       const double* __restrict__ ksign, ll M, ll N, ll K, ll ps_a, ll ps_b, ll ps_c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* As = reinterpret_cast<double*>(smem_raw);            // [STAGES][DBM][DSA]
-  double* Bs = As + STAGES * DBM * DSA;                         // [STAGES][DBK][DSB]
-  ll* s_row = reinterpret_cast<ll*>(Bs + STAGES * DBK * DSB);   // [DBM]
+  double* As = reinterpret_cast<double*>(smem_raw);             // [DSTAGES][DBM][DSA]
+  double* Bs = As + DSTAGES * DBM * DSA;                         // [DSTAGES][DBK][DSB]
+  ll* s_row = reinterpret_cast<ll*>(Bs + DSTAGES * DBK * DSB);   // [DBM]
   ll* s_col = s_row + DBM;                                      // [DBN]
 
   const ll tiles_m = (M + DBM - 1) / DBM, tiles_n = (N + DBN - 1) / DBN;
@@ -249,15 +250,15 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
   C += p * ps_c;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 64;
-  if (tid < DBM) s_row[tid] = (m0 + tid < M) ? __ldg(row_a + m0 + tid) : -1;
-  if (tid >= 128) s_col[tid - 128] = (n0 + tid - 128 < N) ? __ldg(col_b + n0 + tid - 128) : -1;
+  const int wm = warp * 32, wn = 0;
+  s_row[tid] = (m0 + tid < M) ? __ldg(row_a + m0 + tid) : -1;
+  if (tid < DBN) s_col[tid] = (n0 + tid < N) ? __ldg(col_b + n0 + tid) : -1;
   __syncthreads();
 
-  // loaders (8-byte gathers): A tile 128 rows x 16 k -> 8 elements per thread (k fastest across threads: k = tid & 15,
-  //                           rows tid / 16 + 16 i); B tile 16 k x 128 n -> 8 per thread (n = tid & 127, k = tid / 128 + 2 i)
+  // loaders (8-byte gathers): A tile 128 rows x 16 k -> 16 elements per thread (k fastest across threads: k = tid & 15,
+  //                           rows tid / 16 + 8 i); B tile 16 k x 64 n -> 8 per thread (n = tid & 63, k = tid / 64 + 2 i)
   const int a_kk = tid & 15, a_r0 = tid >> 4;
-  const int b_n = tid & 127, b_k0 = tid >> 7;
+  const int b_n = tid & 63, b_k0 = tid >> 6;
   const ll KT = (K + DBK - 1) / DBK;
   ll ka_next = 0, kb_next[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto fetch_koffs = [&](ll kt) {
@@ -270,10 +271,10 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
       kb_next[i] = (kt < KT && kk < K) ? __ldg(k_b + kk) : 0;
     }
   };
-  // VEC loaders: A 128 rows x 8 k-pairs -> 4 copies per thread (k pair = tid & 7, rows tid / 8 + 32 i);
-  //              B 16 k x 64 n-pairs -> 4 copies per thread (n pair = tid & 63, k = tid / 64 + 4 i)
+  // VEC loaders: A 128 rows x 8 k-pairs -> 8 copies per thread (k pair = tid & 7, rows tid / 8 + 16 i);
+  //              B 16 k x 32 n-pairs -> 4 copies per thread (n pair = tid & 31, k = tid / 32 + 4 i)
   const int va_kp = tid & 7, va_r0 = tid >> 3;
-  const int vb_np = tid & 63, vb_k0 = tid >> 6;
+  const int vb_np = tid & 31, vb_k0 = tid >> 5;
   ll vka_next = 0, vkb_next[4] = {0, 0, 0, 0};
   auto fetch_koffs_vec = [&](ll kt) {
     const ll kbase = kt * DBK;
@@ -292,8 +293,8 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     if (VEC) {
       const bool kv = kbase + 2 * va_kp < K;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = va_r0 + 32 * i;
+      for (int i = 0; i < 8; ++i) {
+        const int r = va_r0 + 16 * i;
         const ll ro = s_row[r];
         const bool v = kv && ro >= 0;
         cp_async16(as + r * DSA + 2 * va_kp, A + (v ? ro + vka_next : 0), v);
@@ -309,8 +310,8 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     }
     const bool kv = kbase + a_kk < K;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = a_r0 + 16 * i;
+    for (int i = 0; i < 16; ++i) {
+      const int r = a_r0 + 8 * i;
       const ll ro = s_row[r];
       const bool v = kv && ro >= 0;
       cp_async8(as + r * DSA + a_kk, A + (v ? ro + ka_next : 0), v);
@@ -337,24 +338,24 @@ contract_dgemm_kernel(const double* __restrict__ A, const double* __restrict__ B
     for (int j = 0; j < 8; ++j) c[i][j][0] = c[i][j][1] = 0.0;
 
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
+  for (int s = 0; s < DSTAGES - 1; ++s) {
     fetch(s);
     if (s < KT) load_tile(s, s);
     cp_async_commit();
   }
-  fetch(STAGES - 1);
+  fetch(DSTAGES - 1);
 
   const int fr = lane >> 2, fk = lane & 3;
   for (ll kt = 0; kt < KT; ++kt) {
-    cp_async_wait<STAGES - 2>();
+    cp_async_wait<DSTAGES - 2>();
     __syncthreads();
     {
-      const ll nxt = kt + STAGES - 1;
-      if (nxt < KT) load_tile((int)(nxt % STAGES), nxt);
+      const ll nxt = kt + DSTAGES - 1;
+      if (nxt < KT) load_tile((int)(nxt % DSTAGES), nxt);
       cp_async_commit();
       fetch(nxt + 1);
     }
-    const int stage = (int)(kt % STAGES);
+    const int stage = (int)(kt % DSTAGES);
     const double* as = As + stage * DBM * DSA;
     const double* bs = Bs + stage * DBK * DSB;
 #pragma unroll
@@ -423,13 +424,13 @@ cudaError_t launch_contract_dgemm(const double* A, const double* B, double* C, c
   if (M == 0 || N == 0 || n_points == 0) return cudaSuccess;
   const ll tiles = ((M + DBM - 1) / DBM) * ((N + DBN - 1) / DBN);
   if (tiles > 0x7fffffffLL || n_points > 65535) return cudaErrorInvalidConfiguration;
-  const size_t smem = (size_t)STAGES * (DBM * DSA + DBK * DSB) * sizeof(double) + (DBM + DBN) * sizeof(long long);
+  const size_t smem = (size_t)DSTAGES * (DBM * DSA + DBK * DSB) * sizeof(double) + (DBM + DBN) * sizeof(long long);
   dim3 grid((unsigned)tiles, (unsigned)n_points);
   cudaError_t e = cudaSuccess;
 #define SPN_LAUNCH_DGEMM(SG, VC)                                                                                          \
   e = cudaFuncSetAttribute(contract_dgemm_kernel<SG, VC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
   if (e != cudaSuccess) return e;                                                                                         \
-  contract_dgemm_kernel<SG, VC><<<grid, 256, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, ksign, M, N, \
+  contract_dgemm_kernel<SG, VC><<<grid, DTHREADS, smem, stream>>>(A, B, C, row_a, k_a, col_b, k_b, out_row, out_col, ksign, M, N, \
                                                              K, ps_a, ps_b, ps_c)
   if (ksign) {
     if (vec) { SPN_LAUNCH_DGEMM(true, true); } else { SPN_LAUNCH_DGEMM(true, false); }
