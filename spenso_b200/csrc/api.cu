@@ -376,6 +376,11 @@ static void contract_key(std::string& key, const spn_ctx* ctx, const spn_tensor*
   key.push_back((char)(n_points >= 2048));
   key.push_back((char)(n_points <= 65535));
   key.push_back((char)ctx->emulate_reference_pairing);
+  // measurement switches that change which kernel is built (read per call so that tests can flip them)
+  const char* lm = getenv("SPN_LOAD_MODE");
+  key.push_back(lm ? lm[0] : '-');
+  key.push_back(getenv("SPN_NO_PAIR_JIT") ? 'g' : 'j');
+  key.push_back(getenv("SPN_PAIR_NO_SLAB") ? 'd' : 's');
 }
 
 static std::shared_ptr<ContractEntry> build_entry(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b,

@@ -60,8 +60,8 @@ bool stageable(const spn_tensor* t) {
 // is a multiple of 32 bytes.  Kept for measurement (profiles/r02_pairwise_tma.txt): it is slower than the padded
 // LDGSTS slabs on every shape of tools/pairwise_bench.py.
 bool tma_mode() {
-  static const bool on = getenv("SPN_LOAD_MODE") && std::string(getenv("SPN_LOAD_MODE")) == "tma";
-  return on;
+  const char* e = getenv("SPN_LOAD_MODE");   // read per call: a test flips it between contractions
+  return e && std::string(e) == "tma";
 }
 Staging staging_of(const spn_tensor* t, bool operand) {
   Staging s;

@@ -1242,3 +1242,56 @@ def test_execute_host_async_keeps_order_and_results(ctx, name, scale, real):
         assert np.array_equal(s, ws)
     ref, ref_sum, _ = O.eval_spec(spec, [b for b in batches[0]])
     assert rel_err(want_out[0], ref) <= TOL and rel_err(want_sum[0], ref_sum) <= TOL
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_slab_staged_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
+    """The specialised pairwise kernels in their three memory paths — warp-owned cp.async slabs (default), direct
+    thread = point loads (SPN_PAIR_NO_SLAB) and TMA bulk copies (SPN_LOAD_MODE=tma) — against the generic kernel
+    (SPN_NO_PAIR_JIT) on the same operands: identical bits, for a ragged point count (a partial last slab), c64 and f64
+    operands, both layouts, dense and shared-sparse partners."""
+    import os
+
+    rng = np.random.default_rng(9000 + seed)
+    n_points, done = 4099, 0
+    for it in range(8):
+        a, b = _cases.random_pair(rng, max_free=2, max_common=2)
+        layout = sp.POINT_MAJOR if it % 3 != 2 else sp.COMPONENT_MAJOR
+        ca = O.order_structure(a)[0] if len(a) else a
+        cb = O.order_structure(b)[0] if len(b) else b
+        dta = sp.F64 if it % 4 == 1 else sp.C64
+        dtb = sp.F64 if it % 4 in (1, 3) else sp.C64
+
+        def mk(c, dt):
+            shape = [n_points] + [int(d) for d in c["dim"]]
+            data = rng.uniform(-1, 1, size=shape) if dt == sp.F64 else _cases.random_complex(rng, shape)
+            t = sp.BatchTensor.empty(ctx, c, n_points, dt, layout)
+            t.upload(np.ascontiguousarray(data).reshape(n_points, -1))
+            return t
+
+        ta = mk(ca, dta)
+        if it % 5 == 4:
+            ent = _cases.random_sparse_entries(rng, [int(d) for d in cb["dim"]])
+            tb = sp.SparseTensor.from_entries(ctx, cb, ent)
+        else:
+            tb = mk(cb, dtb)
+        results = {}
+        for name, env in (("generic", {"SPN_NO_PAIR_JIT": "1"}), ("slab", {}), ("direct", {"SPN_PAIR_NO_SLAB": "1"}),
+                          ("tma", {"SPN_LOAD_MODE": "tma"})):
+            for k in ("SPN_NO_PAIR_JIT", "SPN_PAIR_NO_SLAB", "SPN_LOAD_MODE"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            try:
+                results[name] = ta.contract(tb).to_numpy()
+            except sp.SpensoError:
+                results = None
+                break
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        if results is None:
+            continue
+        for name in ("slab", "direct", "tma"):
+            assert np.array_equal(results[name], results["generic"]), f"case {it}: {name} differs from the generic kernel"
+        done += 1
+    assert done >= 4
