@@ -419,7 +419,7 @@ def traffic_of(wl, layout_name, kernel):
 
 
 def measure_network(job, args, wl, n, layout_name="point", K=20, W=3, exec_mode="fused", mc_sum="final", allreduce="peer",
-                    on_device_inputs=True, e2e=False, cpu=False, sustained_s=0.0, total_points_note=None):
+                    on_device_inputs=True, e2e=False, cpu=False, sustained_s=0.0, total_points_note=None, min_ms=0.0):
     """One workload on this job: returns the entry (rank 0) with value / roofline / clocks (+ e2e, cpu_baseline)."""
     torch, dist, sp = job.torch, job.dist, job.sp
     from spenso_b200 import workloads
@@ -467,10 +467,19 @@ def measure_network(job, args, wl, n, layout_name="point", K=20, W=3, exec_mode=
 
     W = max(W, 3)
     l0 = ctx.launch_count
-    for i in range(W):
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step(0)
+    w0.record(stream)
+    for i in range(1, W):
         step(i)
+    w1.record(stream)
     launches_per_step = (ctx.launch_count - l0) / W
     job.barrier()
+    if min_ms > 0:
+        # short steps (a few hundred microseconds at N = 8): enough of them that the skew between the ranks' start times
+        # (a fraction of a millisecond after a barrier) does not weigh on the timed region; every rank takes the same K
+        step_ms = job.max_over_ranks(w0.elapsed_time(w1) / (W - 1))
+        K = int(min(400, max(K, np.ceil(min_ms / max(step_ms, 1e-3)))))
 
     # ---- timed region: exactly K steps ------------------------------------------------------------------------
     # The K launches are captured into ONE CUDA graph (a step is a single 50 us .. few ms kernel: eager launches from
@@ -908,21 +917,23 @@ def run_suite(job, args):
     # cfg3: 2^22 points per GPU (39 GB of dense per-point operands), both layouts
     n3 = int(os.environ.get("SPN_BENCH_CFG3_POINTS", 1 << 22))
     if job.free_gib() > (n3 * 9344 / 2 ** 30) * 1.1 + 4:
-        guarded("cfg3_point_major", lambda: measure_network(job, args, "cfg3", n3, "point", K=K))
-        guarded("cfg3_component_major", lambda: measure_network(job, args, "cfg3", n3, "component", K=K))
+        guarded("cfg3_point_major", lambda: measure_network(job, args, "cfg3", n3, "point", K=K, min_ms=30.0))
+        guarded("cfg3_component_major", lambda: measure_network(job, args, "cfg3", n3, "component", K=K, min_ms=30.0))
     elif job.rank == 0:
         out["cfg3_point_major"] = {"skipped": f"needs {n3 * 9344 / 2**30:.0f} GiB free, have {job.free_gib():.0f}"}
     # cfg5 / cfg5r: 1e8 points in total, sharded over the ranks (BASELINE configs[4]) => strong scaling
     total5 = int(os.environ.get("SPN_BENCH_CFG5_POINTS", 100_000_000))
     n5 = -(-total5 // world)
     note5 = f"{n5 * world} points in total = {n5} per GPU x {world} GPU(s) (1e8 sharded; strong scaling)"
-    guarded("cfg5", lambda: measure_network(job, args, "cfg5", n5, "point", K=K, total_points_note=note5))
-    guarded("cfg5r", lambda: measure_network(job, args, "cfg5r", n5, "point", K=K, total_points_note=note5))
+    guarded("cfg5", lambda: measure_network(job, args, "cfg5", n5, "point", K=K, total_points_note=note5, min_ms=30.0))
+    guarded("cfg5r", lambda: measure_network(job, args, "cfg5r", n5, "point", K=K, total_points_note=note5, min_ms=30.0))
     if world > 1:
         guarded("cfg5_mc_sum_every_step_peer_kernel",
-                lambda: measure_network(job, args, "cfg5", n5, "point", K=K, mc_sum="step", allreduce="peer", total_points_note=note5))
+                lambda: measure_network(job, args, "cfg5", n5, "point", K=K, mc_sum="step", allreduce="peer", total_points_note=note5,
+                                        min_ms=30.0))
         guarded("cfg5_mc_sum_every_step_nccl",
-                lambda: measure_network(job, args, "cfg5", n5, "point", K=K, mc_sum="step", allreduce="nccl", total_points_note=note5))
+                lambda: measure_network(job, args, "cfg5", n5, "point", K=K, mc_sum="step", allreduce="nccl", total_points_note=note5,
+                                        min_ms=30.0))
     guarded("mc_sum_exchange", lambda: measure_exchange(job))
     # cfg4: one ZGEMM-shaped contraction (48 GiB of operands at N = 1)
     need4 = (2 + 1.0 / world) * 16.0 + 6
