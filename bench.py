@@ -533,7 +533,7 @@ def measure_network(job, args, wl, n, layout_name="point", K=20, W=3, exec_mode=
     # sustained: the same graph replayed back to back for >= sustained_s seconds (power/clock steady state)
     sustained = None
     if sustained_s > 0 and graph is not None:
-        reps = max(1, int(np.ceil(sustained_s * 1e3 / max(elapsed_ms_local, 1e-3))))
+        reps = max(1, int(np.ceil(1.2 * sustained_s * 1e3 / max(elapsed_ms_local, 1e-3))))   # margin: at least sustained_s
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(job.local_rank) as sclocks:
             job.barrier()
