@@ -376,6 +376,11 @@ int spn_net_set_comm(spn_net* net, spn_comm* comm);
 enum { SPN_HOST_WRITE_COMBINED = 1 };
 void* spn_host_alloc(uint64_t bytes);
 void* spn_host_alloc_flags(uint64_t bytes, int flags);
+/* Pin memory the host already owns (a Rust Vec<Complex<f64>>, a numpy array) in place, so that the host-buffer entry
+ * points copy from / to it asynchronously without an intermediate pinned copy (cudaHostRegister / cudaHostUnregister).
+ * Copies from unpinned memory still work, but synchronously and at a fraction of the link rate. */
+int spn_host_register(void* p, uint64_t bytes);
+int spn_host_unregister(void* p);
 void spn_host_free(void* p);
 
 #ifdef __cplusplus

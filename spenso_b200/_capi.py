@@ -126,6 +126,8 @@ SYMBOLS = {
     "spn_net_host_wait": (_I, [_P]),
     "spn_host_alloc": (_P, [_U64]),
     "spn_host_alloc_flags": (_P, [_U64, _I]),
+    "spn_host_register": (_I, [_P, _U64]),
+    "spn_host_unregister": (_I, [_P]),
     "spn_host_free": (None, [_P]),
     "spn_comm_create": (_I, [_P, _I, _I, _U32, C.POINTER(_P)]),
     "spn_comm_handle": (_I, [_P, _P]),

@@ -2212,6 +2212,19 @@ void* spn_host_alloc(uint64_t bytes) {
 void spn_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
+int spn_host_register(void* p, uint64_t bytes) {
+  NET_TRY
+  if (!p || !bytes) throw Error(SPN_ERR_INVALID, "spn_host_register: null or empty range");
+  cuda_check(cudaHostRegister(p, bytes, cudaHostRegisterDefault), "cudaHostRegister");
+  return SPN_OK;
+  NET_CATCH(false)
+}
+int spn_host_unregister(void* p) {
+  NET_TRY
+  cuda_check(cudaHostUnregister(p), "cudaHostUnregister");
+  return SPN_OK;
+  NET_CATCH(false)
+}
 
 int spn_net_set_comm(spn_net* net, spn_comm* comm) {
   if (!net) return SPN_ERR_INVALID;

@@ -1295,3 +1295,30 @@ def test_slab_staged_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
             assert np.array_equal(results[name], results["generic"]), f"case {it}: {name} differs from the generic kernel"
         done += 1
     assert done >= 4
+
+
+def test_host_memory_registered_in_place(ctx):
+    """spn_host_register pins memory the host already owns (what a Rust Vec or a numpy array is) so that
+    spn_net_execute_host streams from / to it without a pinned staging copy: same results as from unpinned memory."""
+    from spenso_b200._capi import check, lib
+
+    spec = workloads.eemumu()
+    net = workloads.build_engine(spec, ctx, sp.FUSED)
+    n = 20_000
+    arrs = workloads.synthetic_inputs(spec, n, 3)
+    out_a = np.zeros((n, 1), dtype=np.complex128)
+    net.execute_host(arrs, out=out_a)                      # pageable memory: works, synchronously
+    out_b = np.zeros((n, 1), dtype=np.complex128)
+    regs = arrs + [out_b]
+    for a in regs:
+        check(lib().spn_host_register(a.ctypes.data, a.nbytes))
+    try:
+        net.execute_host_async(arrs, out=out_b)
+        net.host_wait()
+    finally:
+        for a in regs:
+            check(lib().spn_host_unregister(a.ctypes.data))
+    assert np.array_equal(out_a, out_b)
+    ref, _, _ = O.eval_spec(spec, arrs)
+    assert rel_err(out_b, ref) <= TOL
+    assert lib().spn_host_register(None, 16) != 0
