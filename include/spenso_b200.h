@@ -199,6 +199,11 @@ int spn_tensor_scalar_mul(spn_ctx* ctx, const spn_tensor* a, double re, double i
 int spn_tensor_conj(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
 /* element-wise 1/x: `Sc::ref_one() / s` of the Power op on scalars (network.rs:1526-1703) */
 int spn_tensor_recip(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
+/* the same batched tensor in the other device layout (SPN_POINT_MAJOR <-> SPN_COMPONENT_MAJOR), converted on the device.
+ * A network whose shared partners are sparse reads only the components that meet a non-zero: in component-major layout
+ * those are contiguous streams (cfg3: 5.8e9 evals/s), in point-major layout 16-byte gathers whose 128-byte lines are
+ * fetched whole (7.9e8) — converting once pays off from the third evaluation on. */
+int spn_tensor_relayout(spn_ctx* ctx, const spn_tensor* a, int layout, spn_tensor** out);
 /* deep copy (trait Clone of the reference's tensors) */
 int spn_tensor_clone(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out);
 /* DataTensor::to_dense / to_sparse (tensors/data/sparse.rs:688-708, dense.rs:523-535): to_sparse stores the values

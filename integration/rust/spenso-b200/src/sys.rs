@@ -52,6 +52,12 @@ unsafe extern "C" {
     pub fn spn_tensor_recip(ctx: *mut spn_ctx, a: *const spn_tensor, out: *mut *mut spn_tensor) -> c_int;
     pub fn spn_tensor_clone(ctx: *mut spn_ctx, a: *const spn_tensor, out: *mut *mut spn_tensor) -> c_int;
     pub fn spn_tensor_conj(ctx: *mut spn_ctx, a: *const spn_tensor, out: *mut *mut spn_tensor) -> c_int;
+    pub fn spn_tensor_relayout(ctx: *mut spn_ctx, a: *const spn_tensor, layout: c_int, out: *mut *mut spn_tensor) -> c_int;
+    pub fn spn_host_register(p: *mut c_void, bytes: u64) -> c_int;
+    pub fn spn_host_unregister(p: *mut c_void) -> c_int;
+    pub fn spn_net_execute_host_async(net: *mut spn_net, host_inputs: *const *const c_void, n_inputs: u32, n_points: u64,
+                                      host_out: *mut c_void, host_sum: *mut c_double, chunk_points: u64) -> c_int;
+    pub fn spn_net_host_wait(net: *mut spn_net) -> c_int;
     pub fn spn_net_set_schedule(net: *mut spn_net, pairs: *const i32, n_pairs: u32) -> c_int;
     pub fn spn_last_error() -> *const c_char;
     pub fn spn_ctx_create(device: c_int, out: *mut *mut spn_ctx) -> c_int;

@@ -307,6 +307,12 @@ class _Tensor:
         check(lib().spn_tensor_clone(self.ctx.h, self.h, C.byref(out)))
         return self._wrap(out)
 
+    def relayout(self, layout: int):
+        """The same batched tensor in the other device layout (device-side transpose)."""
+        out = C.c_void_p()
+        check(lib().spn_tensor_relayout(self.ctx.h, self.h, layout, C.byref(out)))
+        return self._wrap(out)
+
     def to_dense(self):
         """DataTensor::to_dense (tensors/data/sparse.rs:688-708)."""
         out = C.c_void_p()

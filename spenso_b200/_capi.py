@@ -87,6 +87,7 @@ SYMBOLS = {
     "spn_tensor_conj": (_I, [_P, _P, C.POINTER(_P)]),
     "spn_tensor_recip": (_I, [_P, _P, C.POINTER(_P)]),
     "spn_tensor_clone": (_I, [_P, _P, C.POINTER(_P)]),
+    "spn_tensor_relayout": (_I, [_P, _P, _I, C.POINTER(_P)]),
     "spn_tensor_to_dense": (_I, [_P, _P, C.POINTER(_P)]),
     "spn_tensor_to_sparse": (_I, [_P, _P, C.POINTER(_P)]),
     "spn_tensor_get": (_I, [_P, _U64, _U64, _P]),

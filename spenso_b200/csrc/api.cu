@@ -953,6 +953,22 @@ int spn_tensor_clone(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
   return SPN_OK;
   API_CATCH
 }
+// point-major <-> component-major copy of a batched tensor, on the device (tiled shared-memory transpose)
+int spn_tensor_relayout(spn_ctx* ctx, const spn_tensor* a, int layout, spn_tensor** out) {
+  API_TRY
+  if (!a->batched()) throw Error(SPN_ERR_INVALID, "relayout: only batched tensors have a layout");
+  if (layout != SPN_POINT_MAJOR && layout != SPN_COMPONENT_MAJOR) throw Error(SPN_ERR_INVALID, "relayout: unknown layout");
+  if (layout == a->layout) return spn_tensor_clone(ctx, a, out);
+  std::unique_ptr<spn_tensor> r(new_batched(ctx, a->st, a->n_points, a->dtype, layout, nullptr));
+  const uint64_t sz = a->size(), np = a->n_points;
+  // source viewed as a [rows][cols] matrix: point-major [np][sz] -> [sz][np], component-major [sz][np] -> [np][sz]
+  const uint64_t rows = a->layout == SPN_POINT_MAJOR ? np : sz, cols = a->layout == SPN_POINT_MAJOR ? sz : np;
+  cuda_check(launch_transpose(a->dptr, r->dptr, rows, cols, cols, rows, (int)a->elem_bytes(), ctx->stream), "layout transpose");
+  ctx->launches++;
+  *out = r.release();
+  return SPN_OK;
+  API_CATCH
+}
 // DataTensor::to_dense / to_sparse (tensors/data/sparse.rs:688-708, dense.rs:523-535): index bookkeeping on the host
 // copies every shared tensor keeps, no arithmetic
 int spn_tensor_to_dense(spn_ctx* ctx, const spn_tensor* a, spn_tensor** out) {
