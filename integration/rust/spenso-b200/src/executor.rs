@@ -4,10 +4,10 @@
 //! The reference's blanket `impl ExecuteOp for NetworkStore<T, Sc>` (network.rs:1244-1706) and its
 //! `SmallestDegree` / `ContractScalars` / `SingleSmallestDegree` strategies (network/contract.rs:43-498) are written for
 //! `NetworkStore<T, Sc>`; the orphan rule does not let this crate implement them for `NetworkStore<DeviceBatchTensor, _>`,
-//! so the store is a local type, [`DeviceStore`], and the two impls below follow the reference's match arms one for
-//! one — the graph surgery (`iter_nodes`, `involved_node_id`, `get_lib_data`, `identify_nodes_without_self_edges*`)
-//! is the reference's own code path, every tensor operation is one call into libspenso_b200.so, for ALL phase-space
-//! points at once:
+//! so the store is a local type, [`DeviceStore`], and the two impls below reproduce the reference's decisions — which
+//! leaf is folded, contracted or summed when, in which operand order, and how the graph is rewired (`iter_nodes`,
+//! `involved_node_id`, `get_lib_data`, `identify_nodes_without_self_edges*`) — while every tensor operation is one call
+//! into libspenso_b200.so, for ALL phase-space points at once:
 //!
 //! | reference (per point, host)                   | here (all points, device)                       |
 //! |-----------------------------------------------|-------------------------------------------------|
@@ -106,7 +106,32 @@ where
     }
 }
 
-/// ContractScalars::contract — network/contract.rs:73-208, arm for arm.
+/// A leaf of the graph as a device tensor: a store entry, or a library tensor instantiated with the node's indices
+/// (`graph.get_lib_data`, network/graph.rs:291-322) and uploaded as a shared tensor.  The flag says "library key".
+fn leaf_on_device<LT, L, K, FK, Aind>(
+    store: &DeviceStore,
+    graph: &NetworkGraph<K, FK, Aind>,
+    lib: &L,
+    nid: spenso::network::graph::NodeIndex,
+) -> Result<Option<(DeviceBatchTensor, bool)>, TensorNetworkError<K, FK>>
+where
+    LT: LibraryTensor + Clone,
+    LT::WithIndices: PermuteTensor<Permuted = LT::WithIndices> + ToDevice,
+    <<LT::WithIndices as HasStructure>::Structure as TensorStructure>::Slot: IsAbstractSlot<Aind = Aind>,
+    L: Library<<LT as HasStructure>::Structure, Key = K, Value = PermutedStructure<LT>>,
+    K: Display + Debug + Clone,
+    FK: Display + Debug + Clone,
+    Aind: AbsInd,
+{
+    Ok(match &graph.graph[nid] {
+        NetworkNode::Leaf(NetworkLeaf::LocalTensor(i)) => Some((store.tensors[*i].clone(), false)),
+        NetworkNode::Leaf(NetworkLeaf::LibraryKey(_)) => Some((graph.get_lib_data(lib, nid).unwrap().to_device(&store.dev)?, true)),
+        _ => None,
+    })
+}
+
+/// What ContractScalars does (network/contract.rs:73-208), for a device store: fold every Scalar leaf of the product into
+/// one; when at most one tensor factor is left, multiply it in and dissolve the op node.
 fn contract_scalars<LT, L, K, FK, Aind>(
     executor: &mut DeviceStore,
     mut graph: NetworkGraph<K, FK, Aind>,
@@ -122,89 +147,64 @@ where
     Aind: AbsInd,
 {
     graph.sync_order();
-    let mut other = None;
-    let mut remove_op_node = true;
-    let mut head = None;
-    let (mut scalars, mut scalar_nodes): (Vec<_>, Vec<_>) = graph
-        .graph
-        .iter_nodes()
-        .filter_map(|(nid, _, c)| {
-            if let NetworkNode::Leaf(l) = c {
-                match l {
-                    NetworkLeaf::Scalar(i) => Some((*i, nid)),
-                    _ => {
-                        if other.is_none() {
-                            other = Some(nid);
-                        } else {
-                            remove_op_node = false;
-                        }
-                        None
-                    }
-                }
-            } else {
-                if let NetworkNode::Op(NetworkOp::Product) = c {
-                    head = Some(nid);
-                }
-                None
-            }
-        })
-        .collect();
-
-    if let Some(f) = scalars.pop() {
-        let mut acc = executor.scalar[f].clone();
-        let mut more_than_one_scalar = false;
-        for si in scalars {
-            more_than_one_scalar = true;
-            acc = acc.contract(&executor.scalar[si])?; // acc *= scalar[si]
+    // census of the product: scalar leaves (store position, node), tensor factors, the op node itself
+    let mut scalar_leaves = Vec::new();
+    let mut tensor_factors = Vec::new();
+    let mut op_node = None;
+    for (nid, _, node) in graph.graph.iter_nodes() {
+        match node {
+            NetworkNode::Leaf(NetworkLeaf::Scalar(pos)) => scalar_leaves.push((*pos, nid)),
+            NetworkNode::Leaf(_) => tensor_factors.push(nid),
+            NetworkNode::Op(NetworkOp::Product) => op_node = Some(nid),
+            NetworkNode::Op(_) => {}
         }
-        let new_node = if remove_op_node {
-            if let Some(head) = head {
-                scalar_nodes.push(head);
-            }
-            if let Some(other) = other {
-                scalar_nodes.push(other);
-                let NetworkNode::Leaf(l) = &graph.graph[other] else { unreachable!() };
-                match l {
-                    NetworkLeaf::LocalTensor(l) => {
-                        let a = executor.tensors[*l].contract(&acc)?; // scalar_mul
-                        NetworkLeaf::LocalTensor(executor.add_tensor(a))
-                    }
-                    NetworkLeaf::LibraryKey(_) => {
-                        let inds = graph.get_lib_data(lib, other).unwrap().to_device(&executor.dev)?;
-                        let a = inds.contract(&acc)?;
-                        NetworkLeaf::LocalTensor(executor.add_tensor(a))
-                    }
-                    _ => unreachable!(),
-                }
-            } else {
-                NetworkLeaf::Scalar(executor.add_scalar(acc))
-            }
-        } else if more_than_one_scalar {
-            NetworkLeaf::Scalar(executor.add_scalar(acc))
-        } else {
-            return Ok((graph, false));
-        };
-        if !remove_op_node {
-            graph.identify_nodes_without_self_edges_merge_heads(&scalar_nodes, NetworkNode::Leaf(new_node));
-        } else {
-            graph.identify_nodes_without_self_edges(&scalar_nodes, NetworkNode::Leaf(new_node));
-        }
-        Ok((graph, true))
-    } else {
-        let mut didsmth = false;
-        if remove_op_node
-            && let Some(other) = other
-            && let Some(head) = head
-        {
-            let v = graph.graph[other].clone();
-            graph.identify_nodes_without_self_edges(&[head, other], v);
-            didsmth = true;
-        }
-        Ok((graph, didsmth))
     }
+    let dissolves = tensor_factors.len() <= 1; // nothing left to contract afterwards: the op node goes away
+
+    if scalar_leaves.is_empty() {
+        // no scalar at all: a product of one tensor is that tensor
+        if let (true, Some(&only), Some(op)) = (dissolves, tensor_factors.first(), op_node) {
+            let leaf = graph.graph[only].clone();
+            graph.identify_nodes_without_self_edges(&[op, only], leaf);
+            return Ok((graph, true));
+        }
+        return Ok((graph, false));
+    }
+    if !dissolves && scalar_leaves.len() == 1 {
+        return Ok((graph, false)); // a single scalar beside several tensors stays where it is
+    }
+
+    // the reference starts from the LAST scalar and multiplies the others in, in node order
+    let (last_pos, _) = *scalar_leaves.last().unwrap();
+    let mut product = executor.scalar[last_pos].clone();
+    for (pos, _) in &scalar_leaves[..scalar_leaves.len() - 1] {
+        product = product.contract(&executor.scalar[*pos])?;
+    }
+    let mut merged: Vec<_> = scalar_leaves.iter().map(|(_, nid)| *nid).collect();
+    let replacement = if dissolves {
+        merged.extend(op_node);
+        match tensor_factors.first() {
+            Some(&only) => {
+                merged.push(only);
+                let (t, _) = leaf_on_device::<LT, L, K, FK, Aind>(executor, &graph, lib, only)?.expect("a tensor factor");
+                NetworkLeaf::LocalTensor(executor.add_tensor(t.contract(&product)?)) // scalar_mul
+            }
+            None => NetworkLeaf::Scalar(executor.add_scalar(product)),
+        }
+    } else {
+        NetworkLeaf::Scalar(executor.add_scalar(product))
+    };
+    if dissolves {
+        graph.identify_nodes_without_self_edges(&merged, NetworkNode::Leaf(replacement));
+    } else {
+        graph.identify_nodes_without_self_edges_merge_heads(&merged, NetworkNode::Leaf(replacement));
+    }
+    Ok((graph, true))
 }
 
-/// SingleSmallestDegree::contract — network/contract.rs:346-497, arm for arm.
+/// One step of SingleSmallestDegree (network/contract.rs:346-497): among the tensor leaves take the one with the fewest
+/// internal slot edges (first minimum; a leaf without any pairs up with the tensor visited before it, at maximal
+/// weight), contract it with the neighbour its last internal edge leads to, and put the result in its place.
 fn single_smallest_degree<LT, L, K, FK, Aind>(
     executor: &mut DeviceStore,
     mut graph: NetworkGraph<K, FK, Aind>,
@@ -220,78 +220,53 @@ where
     Aind: AbsInd,
 {
     graph.sync_order();
-    let mut last_tensor = None;
-    let edge_to_contract = graph
-        .graph
-        .iter_nodes()
-        .filter(|(_, _, d)| d.is_tensor())
-        .filter_map(|(nid1, a, n1)| {
-            let mut degree = 0;
-            let mut first = None;
-            for h in a {
-                if graph.graph[[&h]].is_slot() && graph.graph.inv(h) != h {
-                    first = Some(h); // only slot hedges are contracted
-                    degree += 1
-                }
+    let mut choice: Option<(i32, _, _)> = None; // (weight, n1, n2)
+    let mut visited_before = None;
+    for (nid, hedges, node) in graph.graph.iter_nodes() {
+        if !node.is_tensor() {
+            continue;
+        }
+        let mut internal_edges = 0;
+        let mut last_internal = None;
+        for h in hedges {
+            if graph.graph[[&h]].is_slot() && graph.graph.inv(h) != h {
+                internal_edges += 1;
+                last_internal = Some(h);
             }
-            let nid2 = if degree == 0 {
-                degree = i32::MAX;
-                if let Some(last_tensor) = last_tensor {
-                    last_tensor
-                } else {
-                    last_tensor = Some(nid1);
-                    return None;
-                }
-            } else {
-                graph.graph.involved_node_id(first?)?
-            };
-            let n2 = &graph.graph[nid2];
-            last_tensor = Some(nid1);
-            Some((degree, nid1, n1, nid2, n2))
-        })
-        .min_by_key(|(degree, _, _, _, _)| *degree);
-
-    if let Some((_, nid1, n1, nid2, n2)) = edge_to_contract {
-        let new_node = match (n1, n2) {
-            (NetworkNode::Leaf(_), NetworkNode::Op(NetworkOp::Product))
-            | (NetworkNode::Op(NetworkOp::Product), NetworkNode::Leaf(_)) => {
-                return Err(TensorNetworkError::SlotEdgeToProdNode);
-            }
-            (NetworkNode::Leaf(l1), NetworkNode::Leaf(l2)) => match (l1, l2) {
-                (NetworkLeaf::Scalar(_), _) | (_, NetworkLeaf::Scalar(_)) => {
-                    return Err(TensorNetworkError::SlotEdgeToScalarNode);
-                }
-                (NetworkLeaf::LocalTensor(l1), NetworkLeaf::LocalTensor(l2)) => {
-                    let contracted = executor.tensors[*l1].contract(&executor.tensors[*l2])?;
-                    NetworkLeaf::LocalTensor(executor.add_tensor(contracted))
-                }
-                (NetworkLeaf::LibraryKey(_), NetworkLeaf::LocalTensor(l2)) => {
-                    let l1 = graph.get_lib_data(lib, nid1).unwrap().to_device(&executor.dev)?;
-                    let contracted = executor.tensors[*l2].contract(&l1)?;
-                    NetworkLeaf::LocalTensor(executor.add_tensor(contracted))
-                }
-                (NetworkLeaf::LocalTensor(l2), NetworkLeaf::LibraryKey(_)) => {
-                    let l1 = graph.get_lib_data(lib, nid2).unwrap().to_device(&executor.dev)?;
-                    let contracted = executor.tensors[*l2].contract(&l1)?;
-                    NetworkLeaf::LocalTensor(executor.add_tensor(contracted))
-                }
-                (NetworkLeaf::LibraryKey(_), NetworkLeaf::LibraryKey(_)) => {
-                    let l1 = graph.get_lib_data(lib, nid1).unwrap().to_device(&executor.dev)?;
-                    let l2 = graph.get_lib_data(lib, nid2).unwrap().to_device(&executor.dev)?;
-                    let contracted = l1.contract(&l2)?;
-                    NetworkLeaf::LocalTensor(executor.add_tensor(contracted))
-                }
-            },
-            (a, b) => {
-                return Err(TensorNetworkError::CannotContractEdgeBetween(a.clone(), b.clone()));
-            }
+        }
+        let (weight, partner) = match last_internal {
+            Some(h) => (internal_edges, graph.graph.involved_node_id(h)),
+            None => (i32::MAX, visited_before), // unconnected: outer product with the previous tensor, as a last resort
         };
-        executor.contraction_log.push((usize::from(nid1), usize::from(nid2)));
-        graph.identify_nodes_without_self_edges_merge_heads(&[nid1, nid2], NetworkNode::Leaf(new_node));
-        Ok((graph, true))
-    } else {
-        Ok((graph, false))
+        // (the first unconnected tensor has no partner yet: it only registers itself as "visited")
+        let pair = partner.map(|p| (weight, nid, p));
+        visited_before = Some(nid);
+        if let Some(candidate) = pair {
+            if choice.map_or(true, |(w, _, _)| candidate.0 < w) {
+                choice = Some(candidate);
+            }
+        }
     }
+    let Some((_, n1, n2)) = choice else { return Ok((graph, false)) };
+
+    if matches!((&graph.graph[n1], &graph.graph[n2]), (NetworkNode::Op(NetworkOp::Product), _) | (_, NetworkNode::Op(NetworkOp::Product))) {
+        return Err(TensorNetworkError::SlotEdgeToProdNode);
+    }
+    if matches!(&graph.graph[n1], NetworkNode::Leaf(NetworkLeaf::Scalar(_))) || matches!(&graph.graph[n2], NetworkNode::Leaf(NetworkLeaf::Scalar(_))) {
+        return Err(TensorNetworkError::SlotEdgeToScalarNode);
+    }
+    let a = leaf_on_device::<LT, L, K, FK, Aind>(executor, &graph, lib, n1)?;
+    let b = leaf_on_device::<LT, L, K, FK, Aind>(executor, &graph, lib, n2)?;
+    let (Some((a, a_is_lib)), Some((b, b_is_lib))) = (a, b) else {
+        return Err(TensorNetworkError::CannotContractEdgeBetween(graph.graph[n1].clone(), graph.graph[n2].clone()));
+    };
+    // the receiver is the local tensor whenever exactly one side is a library key (contract.rs:428-461): the operand
+    // order decides the rounding, so it is kept
+    let contracted = if a_is_lib && !b_is_lib { b.contract(&a)? } else { a.contract(&b)? };
+    executor.contraction_log.push((usize::from(n1), usize::from(n2)));
+    let leaf = NetworkLeaf::LocalTensor(executor.add_tensor(contracted));
+    graph.identify_nodes_without_self_edges_merge_heads(&[n1, n2], NetworkNode::Leaf(leaf));
+    Ok((graph, true))
 }
 
 /// `impl ExecuteOp for NetworkStore<T, Sc>` (network.rs:1244-1706) with T = Sc = [`DeviceBatchTensor`].
