@@ -307,13 +307,9 @@ struct Executor {
           return;
         }
         T t = leaf_tensor(c);
-        T sq = t.contract(t);
-        log.emplace_back(c, c);
+        T sq = t.contract(t);   // not part of the contraction log: Power is an op of its own, not a SmallestDegree step
         T v = sq;
-        for (int k = 1; k < np / 2; ++k) {
-          v = v.contract(sq);
-          log.emplace_back(c, c);
-        }
+        for (int k = 1; k < np / 2; ++k) v = v.contract(sq);
         if (pw < 0) v = v.recip();
         become_leaf(id, SCALAR, push_scalar(v));
         return;
