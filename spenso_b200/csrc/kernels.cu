@@ -90,17 +90,17 @@ contract_dense_kernel(const __grid_constant__ DevOutMap map, DevOperand a, DevOp
   }
 }
 
-// The same contraction without run-time index arithmetic: the base offsets of every result element come from two
-// host-built tables (toa[o], tob[o]: the plan-cache entry owns them), the contracted-loop tables sit in shared
-// memory, and a CTA works on tiles of 256 consecutive elements of the fastest axis — results of one point (point
-// major: consecutive threads = consecutive result elements, coalesced stores) or one result element over 256
-// points (component major).  One 32-bit division per tile instead of 2 x order 64-bit divisions per element.
+// The same contraction without per-dimension index arithmetic: the operand base offsets of every result element come
+// from two host-built tables (toa[o], tob[o]: the plan-cache entry owns them) and the contracted-loop tables sit in
+// shared memory.  One thread per (point, result element), element fastest for point-major results (consecutive threads
+// = consecutive result elements: coalesced stores), point fastest for component-major ones; one division per thread
+// (32-bit when the element count allows) instead of 2 x order 64-bit divisions.
 template <bool AC, bool BC, bool PF>
 __global__ void __launch_bounds__(256)
 contract_dense_tab_kernel(DevOperand a, DevOperand b, DevOut out, const ll* __restrict__ toa, const ll* __restrict__ tob,
                           const ll* __restrict__ koff_a, const ll* __restrict__ koff_b,
                           const unsigned char* __restrict__ ksign, unsigned n_k, unsigned size_out, ull n_points,
-                          unsigned inner_tiles, unsigned n_tiles, int stage_k) {
+                          int stage_k) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ll* ka = koff_a;
   const ll* kb = koff_b;
@@ -120,19 +120,20 @@ contract_dense_tab_kernel(DevOperand a, DevOperand b, DevOut out, const ll* __re
     ks = ss;
   }
   const ll fsa = stage_k ? 1 : a.fs, fsb = stage_k ? 1 : b.fs;
-  for (unsigned T = blockIdx.x; T < n_tiles; T += gridDim.x) {
-    const unsigned outer = T / inner_tiles;
-    const ull inner = (ull)(T - outer * inner_tiles) * 256ull + threadIdx.x;
-    ull p, o;
-    if (PF) {
-      o = outer;
-      p = inner;
-      if (p >= n_points) continue;
+  const ull total = (ull)size_out * n_points;
+  const bool narrow = total <= 0xffffffffull;   // uniform: 32-bit division
+  const ull inner = PF ? n_points : (ull)size_out;
+  for (ull t = (ull)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (ull)gridDim.x * blockDim.x) {
+    ull hi, lo;   // t = hi * inner + lo
+    if (narrow) {
+      const unsigned q = (unsigned)t / (unsigned)inner;
+      hi = q;
+      lo = (unsigned)t - q * (unsigned)inner;
     } else {
-      p = outer;
-      o = inner;
-      if (o >= size_out) continue;
+      hi = t / inner;
+      lo = t - hi * inner;
     }
+    const ull p = PF ? lo : hi, o = PF ? hi : lo;
     const ll offa = (ll)p * a.ps + __ldg(toa + o) * a.fs, offb = (ll)p * b.ps + __ldg(tob + o) * b.fs;
     double2 acc = make_double2(0.0, 0.0);
     for (unsigned k = 0; k < n_k; ++k) {
@@ -356,17 +357,15 @@ cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand
 cudaError_t launch_contract_dense_tab(DevOperand a, DevOperand b, DevOut out, const ll* toa, const ll* tob, const ll* koff_a,
                                       const ll* koff_b, const unsigned char* ksign, ull n_k, ull size_out, ull n_points,
                                       bool point_fastest, cudaStream_t stream) {
-  if (size_out * n_points == 0) return cudaSuccess;
-  const ull inner = point_fastest ? n_points : size_out, outer = point_fastest ? size_out : n_points;
-  const ull inner_tiles = (inner + 255) / 256, n_tiles = inner_tiles * outer;
-  if (n_tiles >= 0xffffffffull || n_k >= 0xffffffffull || size_out >= 0xffffffffull) return cudaErrorInvalidConfiguration;
+  const ull total = size_out * n_points;
+  if (total == 0) return cudaSuccess;
+  if (n_k >= 0xffffffffull || size_out >= 0xffffffffull) return cudaErrorInvalidConfiguration;
   const int stage_k = n_k <= 2048;
   const size_t smem = stage_k ? (size_t)n_k * 17 + 16 : 0;
-  const unsigned grid = (unsigned)std::min<ull>(n_tiles, (ull)sm_count() * 8);
+  const unsigned grid = grid_for(total, 256, 8);
 #define SPN_LAUNCH_DT(AC, BC, PF)                                                                                       \
   contract_dense_tab_kernel<AC, BC, PF><<<grid, 256, smem, stream>>>(a, b, out, toa, tob, koff_a, koff_b, ksign,         \
-                                                                     (unsigned)n_k, (unsigned)size_out, n_points,      \
-                                                                     (unsigned)inner_tiles, (unsigned)n_tiles, stage_k)
+                                                                     (unsigned)n_k, (unsigned)size_out, n_points, stage_k)
 #define SPN_LAUNCH_DT2(AC, BC) \
   if (point_fastest)           \
     SPN_LAUNCH_DT(AC, BC, true); \

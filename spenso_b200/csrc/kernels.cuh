@@ -40,7 +40,7 @@ cudaError_t launch_contract_dense(const DevOutMap& map, DevOperand a, DevOperand
                                   cudaStream_t stream);
 
 // the same with host-built per-result-element base offsets toa/tob (size_out entries each): no index arithmetic on
-// the device.  Needs size_out, n_k and the tile count below 2^32 (cudaErrorInvalidConfiguration otherwise).
+// the device.  Needs size_out and n_k below 2^32 (cudaErrorInvalidConfiguration otherwise).
 cudaError_t launch_contract_dense_tab(DevOperand a, DevOperand b, DevOut out, const long long* toa, const long long* tob,
                                       const long long* koff_a, const long long* koff_b, const unsigned char* ksign,
                                       unsigned long long n_k, unsigned long long size_out, unsigned long long n_points,
