@@ -330,7 +330,8 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
  * end (canonical order); host_out (optional): n_points result tensors; host_sum (optional): the sum over points
  * (2*result_size doubles, host).  The batch streams through a 3-deep chunk pipeline on private streams (H2D of
  * chunk k+1 || kernel of chunk k || D2H of chunk k-1), so device memory use does not depend on n_points.
- * chunk_points = 0: default (2^17).  Host buffers should be pinned (spn_host_alloc).  Fused networks only.
+ * chunk_points = 0: default (2^17).  Host buffers should be pinned (spn_host_alloc / spn_host_register).  Stepwise
+ * networks run chunk by chunk on the context's stream (default chunk 2^14 points), without overlap.
  * Synchronous: host_out / host_sum are complete on return. */
 int spn_net_execute_host(spn_net* net, const void* const* host_inputs, uint32_t n_inputs, uint64_t n_points,
                          void* host_out, double* host_sum, uint64_t chunk_points);

@@ -2053,10 +2053,58 @@ static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint
                               void* host_out, double* host_sum, uint64_t chunk_points) {
   if (!net->compiled) throw Error(SPN_ERR_INVALID, "network is not compiled");
   if (!net->ctx) throw Error(SPN_ERR_NO_DEVICE, "plan-only network (created without a context) cannot execute");
-  if (net->exec_mode != SPN_EXEC_FUSED) throw Error(SPN_ERR_INVALID, "execute_host needs a fused network");
   if (n_inputs != net->n_inputs) throw Error(SPN_ERR_INVALID, "wrong number of input buffers");
   if (!host_out && !host_sum) throw Error(SPN_ERR_INVALID, "nothing to compute: no output and no sum requested");
   spn_ctx* ctx = net->ctx;
+  if (net->exec_mode != SPN_EXEC_FUSED) {
+    // Stepwise networks (intermediates too large for straight-line code): chunk by chunk on the context's stream —
+    // upload, one pairwise kernel per schedule step, download.  No overlap between copies and kernels: such networks
+    // spend their time in the kernels, and their intermediates bound the chunk size.
+    const uint64_t size_res = net->values[(size_t)net->result_value].st.size();
+    if (chunk_points == 0) chunk_points = 1u << 14;
+    std::vector<double2> total(size_res, make_double2(0.0, 0.0)), part(size_res);
+    for (uint64_t first = 0; first < n_points; first += chunk_points) {
+      const uint64_t cnt = std::min(chunk_points, n_points - first);
+      std::vector<std::unique_ptr<spn_tensor>> ins;
+      std::vector<const spn_tensor*> in_ptrs;
+      for (uint32_t i = 0; i < n_inputs; ++i) {
+        const Node& nd = net->nodes[(size_t)net->input_nodes[i]];
+        ins.emplace_back(new_batched(ctx, nd.st, cnt, nd.dtype, SPN_POINT_MAJOR, nullptr));
+        const size_t bytes = nd.st.size() * (nd.dtype == SPN_C64 ? 16 : 8);
+        cuda_check(cudaMemcpyAsync(ins.back()->dptr, (const char*)host_inputs[i] + first * bytes, cnt * bytes, cudaMemcpyHostToDevice,
+                                   ctx->stream),
+                   "H2D of a chunk");
+        in_ptrs.push_back(ins.back().get());
+      }
+      std::unique_ptr<spn_tensor> out(new_batched(ctx, net->values[(size_t)net->result_value].st, cnt, SPN_C64, SPN_POINT_MAJOR, nullptr));
+      double2* dsum = nullptr;
+      if (host_sum) cuda_check(cudaMallocAsync((void**)&dsum, size_res * sizeof(double2) + 16, ctx->stream), "sum scratch");
+      spn_comm* const comm = net->comm;
+      net->comm = nullptr;   // chunk sums are local; a communicator (if any) sees the total once, below
+      try {
+        run_stepwise(net, in_ptrs.data(), out.get(), reinterpret_cast<double*>(dsum));
+      } catch (...) {
+        net->comm = comm;
+        throw;
+      }
+      net->comm = comm;
+      if (host_out)
+        cuda_check(cudaMemcpyAsync((char*)host_out + first * size_res * 16, out->dptr, cnt * size_res * 16, cudaMemcpyDeviceToHost, ctx->stream),
+                   "D2H of a chunk");
+      if (host_sum) {
+        cuda_check(cudaMemcpyAsync(part.data(), dsum, size_res * 16, cudaMemcpyDeviceToHost, ctx->stream), "D2H of a chunk sum");
+        cuda_check(cudaStreamSynchronize(ctx->stream), "chunk");
+        cudaFreeAsync(dsum, ctx->stream);
+        for (uint64_t c = 0; c < size_res; ++c) {   // fixed chunk order: deterministic
+          total[c].x += part[c].x;
+          total[c].y += part[c].y;
+        }
+      }
+      cuda_check(cudaStreamSynchronize(ctx->stream), "chunk");   // the staging tensors die here
+    }
+    if (host_sum) std::memcpy(host_sum, total.data(), size_res * 16);
+    return;
+  }
   const uint64_t size_out = net->values[(size_t)net->result_value].st.size();
   if (chunk_points == 0) chunk_points = 1u << 17;
   chunk_points = std::min<uint64_t>(chunk_points, std::max<uint64_t>(n_points, 1));
@@ -2166,6 +2214,7 @@ static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint
 
 int spn_net_host_wait(spn_net* net) {
   NET_TRY
+  if (net->exec_mode != SPN_EXEC_FUSED && net->ctx) cuda_check(cudaStreamSynchronize(net->ctx->stream), "stepwise drain");
   auto& P = net->pipe;
   for (int s = 0; s < spn_net::kPipe; ++s)
     if (P.stream[s]) cuda_check(cudaStreamSynchronize(P.stream[s]), "pipeline drain");
