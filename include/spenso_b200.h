@@ -254,7 +254,7 @@ int spn_net_leaf_reindex(spn_net* net, int leaf, const spn_slot* slots, uint32_t
  *   code:   n_code pairs (opcode, argument), postfix; one program per component in ARGUMENT-order row major,
  *           separated by (SPN_EXPR_END, 0).  SPN_EXPR_SQRT needs an argument whose imaginary part is structurally
  *           zero (use SPN_EXPR_RE) and non-negative at run time.
- * Fused executor only. */
+ * In a stepwise network a function leaf is materialised by a small fused kernel of its own, then used pairwise. */
 enum {
   SPN_EXPR_PARAM = 0, SPN_EXPR_CONST = 1, SPN_EXPR_ADD = 2, SPN_EXPR_SUB = 3, SPN_EXPR_MUL = 4, SPN_EXPR_DIV = 5,
   SPN_EXPR_NEG = 6, SPN_EXPR_CONJ = 7, SPN_EXPR_SQRT = 8, SPN_EXPR_RE = 9, SPN_EXPR_IM = 10, SPN_EXPR_END = 11
