@@ -106,9 +106,16 @@ spn_tensor* new_batched(spn_ctx* ctx, const Structure& st, uint64_t n_points, in
     // an earlier intermediate is reused without a round trip to the driver
     const size_t bytes = n_points * st.size() * t->elem_bytes();
     static const bool no_pool = getenv("SPN_NO_POOL") != nullptr;
-    if (ctx && !no_pool && cudaMallocAsync(&t->dptr, bytes ? bytes : 16, ctx->stream) == cudaSuccess) {
+    static const bool no_recycle = getenv("SPN_NO_BLOCK_CACHE") != nullptr;
+    const size_t want = bytes ? bytes : 16;
+    if (ctx && !no_pool && !no_recycle && (t->dptr = ctx->take_block(want)) != nullptr) {
       t->pooled = true;
       t->alloc_stream = ctx->stream;
+      t->alloc_bytes = want;
+    } else if (ctx && !no_pool && cudaMallocAsync(&t->dptr, want, ctx->stream) == cudaSuccess) {
+      t->pooled = true;
+      t->alloc_stream = ctx->stream;
+      t->alloc_bytes = no_recycle ? (size_t)-1 : want;   // (size_t)-1: larger than any limit => always freed
     } else {
       cudaGetLastError();
       t->dptr = dev_alloc(bytes);
@@ -732,11 +739,13 @@ int spn_ctx_create(int device, spn_ctx** out) {
 }
 void spn_ctx_destroy(spn_ctx* ctx) { delete ctx; }
 int spn_ctx_set_stream(spn_ctx* ctx, void* s) {
+  if (ctx->stream != (cudaStream_t)s) ctx->drop_blocks();   // recycled buffers are only ordered on the stream they ran on
   ctx->stream = (cudaStream_t)s;
   return SPN_OK;
 }
 int spn_ctx_release_cached_memory(spn_ctx* ctx) {
   API_TRY
+  ctx->drop_blocks();
   cuda_check(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize");
   cudaMemPool_t pool;
   cuda_check(cudaDeviceGetDefaultMemPool(&pool, ctx->device), "cudaDeviceGetDefaultMemPool");

@@ -44,6 +44,53 @@ struct spn_ctx {
   // sticky status words (pinned host memory) of the communicators created on this context (comm.cu): non-zero after
   // an exchange timed out; checked by spn_ctx_synchronize
   std::vector<const int*> comm_status;
+  // Result buffers of the pairwise ops, recycled by exact size.  Everything a context does is ordered on ONE stream, so
+  // a buffer released by the host (its tensor handle was freed) can be handed to the next kernel on that stream at
+  // once: a repeated a.contract(&b) then costs no allocator call at all, where even the stream-ordered pool costs two
+  // (cudaMallocAsync + cudaFreeAsync) and a few microseconds between consecutive kernels.  Buffers go back to the
+  // device's pool when the cache exceeds `block_cache_limit`, when the stream changes, on
+  // spn_ctx_release_cached_memory and when the context dies.
+  std::multimap<size_t, void*> block_cache;
+  size_t block_cache_bytes = 0, block_cache_limit = (size_t)8 << 30;
+  cudaStream_t block_cache_stream = nullptr;
+  void* take_block(size_t bytes) {
+    if (block_cache_stream != stream) return nullptr;
+    auto it = block_cache.find(bytes);
+    if (it == block_cache.end()) return nullptr;
+    void* p = it->second;
+    block_cache.erase(it);
+    block_cache_bytes -= bytes;
+    return p;
+  }
+  void give_block(void* p, size_t bytes, cudaStream_t allocated_on) {
+    if (allocated_on != stream || bytes > block_cache_limit) {
+      if (cudaFreeAsync(p, allocated_on) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+      }
+      return;
+    }
+    if (block_cache_stream != stream) drop_blocks();
+    block_cache_stream = stream;
+    while (block_cache_bytes + bytes > block_cache_limit && !block_cache.empty()) {   // make room: largest first
+      auto last = std::prev(block_cache.end());
+      cudaFreeAsync(last->second, stream);
+      block_cache_bytes -= last->first;
+      block_cache.erase(last);
+    }
+    block_cache.emplace(bytes, p);
+    block_cache_bytes += bytes;
+  }
+  void drop_blocks() {
+    for (auto& kv : block_cache)
+      if (cudaFreeAsync(kv.second, block_cache_stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(kv.second);
+      }
+    block_cache.clear();
+    block_cache_bytes = 0;
+  }
+  ~spn_ctx() { drop_blocks(); }
 };
 
 struct spn_tensor {
@@ -57,6 +104,7 @@ struct spn_tensor {
   bool owns = false;
   bool pooled = false;             // allocated with cudaMallocAsync on alloc_stream (results of pairwise ops)
   cudaStream_t alloc_stream = nullptr;
+  size_t alloc_bytes = 0;          // pooled: size of the allocation (the context recycles result buffers by size)
   // shared tensors: host copies (canonical row major)
   std::vector<double2> host_dense;
   std::map<uint64_t, double2> entries;  // sparse only, keyed (and therefore sorted) by flat index
@@ -94,7 +142,9 @@ struct spn_tensor {
   ~spn_tensor() {
     if (owns && dptr) {
       // stream-ordered free keeps the pairwise (stepwise) path free of device-wide synchronisation
-      if (!pooled || cudaFreeAsync(dptr, alloc_stream) != cudaSuccess) {
+      if (pooled && ctx) {
+        ctx->give_block(dptr, alloc_bytes, alloc_stream);
+      } else if (!pooled || cudaFreeAsync(dptr, alloc_stream) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(dptr);
       }
