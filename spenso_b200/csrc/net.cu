@@ -681,7 +681,12 @@ struct spn_net {
   //         Instead a warp owns slabs of 32 points and gathers them point by point: lane L copies the needed units L,
   //         L + 32, ... of ONE record per cp.async instruction (the accesses of an instruction stay inside one record),
   //         into a padded [point][unit] slab; then lane = point computes from shared memory.
-  enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2, PF_GATHER = 3 };
+  //   TMA   (SPN_LOAD_MODE=tma, measurement only) every CTA moves the slab of its next kBlock points — one contiguous range
+  //         per input — with the TMA engine: cp.async.bulk + mbarrier (UBLKCP / SYNCS in SASS), 2-3 stages; threads then
+  //         read their point from shared memory.  A bulk copy is linear, so 64-byte points are read 4-way bank-conflicted,
+  //         and the block barrier per slab is exposed at 1-2 CTAs per SM: slower than the direct 256-bit loads on every
+  //         workload (profiles/README.md), which already stream at the HBM roofline.
+  enum PrefetchMode { PF_NONE = 0, PF_REGS = 1, PF_RING = 2, PF_GATHER = 3, PF_TMA = 4 };
   static constexpr int kGatherBlock = 64;   // threads per CTA of a GATHER kernel: 2 warps, each with its own slab
   const int kRingDepth = (getenv("SPN_RING_DEPTH") && (atoi(getenv("SPN_RING_DEPTH")) == 2 || atoi(getenv("SPN_RING_DEPTH")) == 8)) ? atoi(getenv("SPN_RING_DEPTH")) : 4;  // power of two
   struct PrefetchPlan {
@@ -738,6 +743,22 @@ struct spn_net {
     const double t_fp = (double)stats.n_fp / (64.0 * 148.0 * 1.9e9);
     const double t_hbm = (double)(stats.n_load_bytes + (out_mode == 'n' ? 0 : 16 * size_out)) / 6.5e12;
     if (stats.n_load_bytes == 0 || getenv("SPN_NO_PREFETCH")) return pf;
+    if (const char* lm = getenv("SPN_LOAD_MODE"); lm && std::string(lm) == "tma") {
+      bool ok = n_inputs > 0;
+      size_t slab = 0;
+      for (uint32_t in = 0; in < n_inputs; ++in) {
+        const Node& nd = nodes[input_nodes[(size_t)in]];
+        const size_t rec = nd.st.size() * (nd.dtype == SPN_C64 ? 16 : 8);
+        ok = ok && variant[in] == 'p' && rec % 16 == 0;
+        slab += rec * (size_t)kBlock;
+      }
+      if (ok && 2 * slab + 64 <= 200 * 1024) {
+        pf.mode = PF_TMA;
+        pf.n_loads = 3 * slab + 64 <= 200 * 1024 ? 3u : 2u;   // stages
+        pf.smem_bytes = (size_t)pf.n_loads * slab + 64;
+        return pf;
+      }
+    }
     {
       // GATHER: all inputs point-major, only 16-byte units, at most half of the input bytes touched, records >= 1 KB
       bool all_p = n_inputs > 0;
@@ -1060,7 +1081,57 @@ struct spn_net {
         a << "in" << i.in << " + (" << pv << " * " << n.st.size() << "ull + " << i.flat << "ull) * " << w;
       return a.str();
     };
-    if (pf.mode == PF_GATHER) {
+    if (pf.mode == PF_TMA) {
+      const unsigned stages = pf.n_loads;
+      std::vector<size_t> rec(n_inputs), off(n_inputs);
+      size_t slab = 0;
+      for (uint32_t in = 0; in < n_inputs; ++in) {
+        const Node& nd = nodes[input_nodes[(size_t)in]];
+        rec[in] = nd.st.size() * (nd.dtype == SPN_C64 ? 16 : 8);
+        off[in] = slab;
+        slab += rec[in] * (size_t)kBlock;
+      }
+      o << "  extern __shared__ __align__(128) unsigned char tsm[];   // [" << stages << " stages][" << slab << " B: one slab per input], then the mbarriers\n";
+      o << "  unsigned long long* const bars = reinterpret_cast<unsigned long long*>(tsm + " << stages * slab << "u);\n";
+      o << "  const ull n_tiles = (n_points + " << kBlock - 1 << "ull) / " << kBlock << "ull;\n";
+      o << "  if (threadIdx.x == 0) {\n    for (unsigned s = 0; s < " << stages << "u; ++s)\n"
+           "      asm volatile(\"mbarrier.init.shared::cta.b64 [%0], 1;\" :: \"r\"((unsigned)__cvta_generic_to_shared(bars + s)) : \"memory\");\n"
+           "    asm volatile(\"fence.mbarrier_init.release.cluster;\" ::: \"memory\");\n  }\n  __syncthreads();\n";
+      o << "  auto issue = [&](ull tile, unsigned stage) {   // thread 0: arm the stage's barrier, launch one bulk copy per input\n";
+      o << "    const ull t0 = tile * " << kBlock << "ull;\n";
+      o << "    const unsigned np = (unsigned)(n_points - t0 < " << kBlock << "ull ? n_points - t0 : " << kBlock << "ull);\n";
+      o << "    const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + stage);\n";
+      size_t per_point = 0;
+      for (uint32_t in = 0; in < n_inputs; ++in) per_point += rec[in];
+      o << "    asm volatile(\"fence.proxy.async.shared::cta;\" ::: \"memory\");\n";
+      o << "    asm volatile(\"mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\" :: \"r\"(bar), \"r\"(np * " << per_point << "u) : \"memory\");\n";
+      for (uint32_t in = 0; in < n_inputs; ++in)
+        o << "    asm volatile(\"cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\" :: "
+             "\"r\"((unsigned)__cvta_generic_to_shared(tsm + stage * " << slab << "u + " << off[in] << "u)), \"l\"(reinterpret_cast<const unsigned char*>(in"
+          << in << ") + t0 * " << rec[in] << "ull), \"r\"(np * " << rec[in] << "u), \"r\"(bar) : \"memory\");\n";
+      o << "  };\n";
+      o << "  if (threadIdx.x == 0)\n    for (unsigned d = 0; d + 1 < " << stages << "u; ++d)\n"
+           "      if (blockIdx.x + (ull)d * gridDim.x < n_tiles) issue(blockIdx.x + (ull)d * gridDim.x, d);\n";
+      o << "  unsigned phases = 0;\n";
+      o << "  for (ull tile = blockIdx.x, it = 0; tile < n_tiles; tile += gridDim.x, ++it) {\n";
+      o << "    const unsigned stage = (unsigned)(it % " << stages << "ull);\n";
+      o << "    __syncthreads();   // every thread is done with the stage that is refilled now\n";
+      o << "    if (threadIdx.x == 0 && tile + " << (stages - 1) << "ull * gridDim.x < n_tiles) issue(tile + " << (stages - 1)
+        << "ull * gridDim.x, (unsigned)((it + " << (stages - 1) << "ull) % " << stages << "ull));\n";
+      o << "    {\n      const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + stage), ph = (phases >> stage) & 1u;\n";
+      o << "      unsigned done = 0;\n      while (!done)\n";
+      o << "        asm volatile(\"{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }\" : \"=r\"(done) : \"r\"(bar), \"r\"(ph) : \"memory\");\n";
+      o << "      phases ^= 1u << stage;\n    }\n";
+      o << "    const ull p = tile * " << kBlock << "ull + threadIdx.x;\n";
+      o << "    if (p < n_points) {\n";
+      for (const Ins& i : prog.ins) {
+        if (i.op != I_LOADC && i.op != I_LOADR) continue;
+        const size_t eb = i.op == I_LOADC ? 16 : 8;
+        o << "    const " << (i.op == I_LOADC ? "double2" : "double") << " l" << i.dst << " = *reinterpret_cast<const "
+          << (i.op == I_LOADC ? "double2" : "double") << "*>(tsm + stage * " << slab << "u + " << off[(size_t)i.in] << "u + threadIdx.x * "
+          << rec[(size_t)i.in] << "u + " << i.flat * eb << "u);\n";
+      }
+    } else if (pf.mode == PF_GATHER) {
       std::vector<RingUnit> units = ring_units(variant);
       // ascending addresses inside a record: neighbouring lanes fetch neighbouring sectors
       std::stable_sort(units.begin(), units.end(), [](const RingUnit& x, const RingUnit& y) {
@@ -1294,6 +1365,7 @@ struct spn_net {
       for (const Ins& i : prog.ins)
         if (i.op == I_LOADC || i.op == I_LOADR) o << "    l" << i.dst << " = n" << i.dst << ";\n";
     if (pf.mode == PF_GATHER) o << "    }\n    __syncwarp();   // the slab is re-used by the next iteration\n";
+    if (pf.mode == PF_TMA) o << "    }\n";
     if (pf.mode == PF_RING)  // refill the slot just consumed with the point kRingDepth iterations ahead
       o << "    if (p + " << kRingDepth << " * stride < n_points) issue(p + " << kRingDepth << " * stride, slot);\n"
            "    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");\n";

@@ -1365,3 +1365,39 @@ def test_execute_host_on_a_stepwise_network(ctx):
     step.execute_host_async(arrays, out=out2, chunk_points=700)
     step.host_wait()
     assert np.array_equal(out, out2)
+
+
+@pytest.mark.parametrize("name,n_points,scale,real", [("cfg2", 1000, 1.0, False), ("cfg2", 300_001, 1.0, False),
+                                                      ("cfg5", 70_003, 100.0, True), ("cfg5r", 70_003, 100.0, True)])
+def test_fused_tma_loader_equals_the_default_loader(ctx, monkeypatch, name, n_points, scale, real):
+    """SPN_LOAD_MODE=tma swaps the fused kernel's per-thread 256-bit loads for slabs moved by the TMA engine
+    (cp.async.bulk + mbarrier, 2-3 stages).  Only the loads change, so per-point results are bit-for-bit those of the
+    default kernel — on a ragged last slab and over many slabs per CTA — and the sums agree with the oracle."""
+    import torch
+
+    spec = workloads.WORKLOADS[name]()
+    arrays = workloads.synthetic_inputs(spec, n_points, 777, scale=scale, real=real)
+    if name == "cfg5r":
+        arrays = [np.ascontiguousarray(a.real) for a in arrays]
+
+    def run():
+        net = workloads.build_engine(spec, ctx, sp.FUSED)
+        inputs = []
+        for node, a, dt in zip([x for x in spec.nodes if x[0] == "batched"], arrays, spec.input_dtypes):
+            t = sp.BatchTensor.empty(ctx, node[1], n_points, dt)
+            t.upload(a)
+            inputs.append(t)
+        out = sp.BatchTensor.empty(ctx, net.result_slots, n_points)
+        s = torch.zeros(2 * net.result_size, dtype=torch.float64, device="cuda:0")
+        net.execute(inputs, out)
+        net.execute(inputs, None, sum_out_ptr=s.data_ptr())
+        ctx.synchronize()
+        src = net.prepare_variant("p" * net.n_inputs + "p")
+        return out.to_numpy().reshape(n_points, -1), s.cpu().numpy().view(np.complex128), src
+
+    want, want_sum, src0 = run()
+    monkeypatch.setenv("SPN_LOAD_MODE", "tma")
+    got, got_sum, src1 = run()
+    assert "cp.async.bulk" in src1 and "mbarrier.try_wait" in src1 and "cp.async.bulk" not in src0
+    assert np.array_equal(got.view(np.float64), want.view(np.float64))
+    assert rel_err(got_sum, want_sum) <= 1e-12
