@@ -25,7 +25,7 @@ from ._capi import SLOT_DTYPE, ContractPlan, SpensoError, build_library, check, 
 __all__ = [
     "Representation", "Euclidean", "Minkowski", "Lorentz", "Bispinor", "SpinFundamental", "ColorAdjoint",
     "ColorFundamental", "ColorSextet", "Slot", "slots", "symbol_slot", "Context", "DenseTensor", "SparseTensor", "BatchTensor",
-    "Network", "NetExpr", "PeerComm", "SpensoError", "canonicalize", "plan_contract", "build_library", "library_tensor",
+    "Network", "NetExpr", "PeerComm", "SpensoError", "canonicalize", "plan_contract", "contract_cuda_source", "build_library", "library_tensor",
     "F64", "C64", "POINT_MAJOR", "COMPONENT_MAJOR", "FUSED", "STEPWISE", "AUTO",
 ]
 
@@ -119,6 +119,31 @@ def plan_contract(a, b) -> ContractPlan:
     p = ContractPlan()
     check(lib().spn_plan_contract(ptr(a), len(a), ptr(b), len(b), C.byref(p)))
     return p
+
+
+def contract_cuda_source(a, b, dtype_a: int = 1, layout_a: int = 0, dtype_b: int = 1, layout_b: int = 0,
+                         sparse_entries: Optional[dict] = None, sparse_first: bool = True) -> str:
+    """CUDA source of the kernel specialised for a.contract(b) (host only; compiled with NVRTC on the way).  "" = the
+    contraction takes a generic kernel.  Two batched tensors by default; with sparse_entries ({index tuple in the
+    caller's slot order: value}) `a` is a SHARED SPARSE tensor with those stored entries and `b` the batched partner
+    (sparse_first=False: b.contract(a))."""
+    a, b = slots(a), slots(b)
+    ca = canonicalize(a) if len(a) else (a, [], -1, -1)
+    cb = canonicalize(b)[0] if len(b) else b
+    if sparse_entries is None:
+        r = lib().spn_plan_contract_cuda_source(ptr(ca[0]), len(a), dtype_a, layout_a, ptr(cb), len(b), dtype_b, layout_b)
+    else:
+        st = _row_major_strides([int(d) for d in ca[0]["dim"]])
+        flat = np.zeros(len(sparse_entries), dtype=np.uint64)
+        vals = np.zeros(len(sparse_entries), dtype=np.complex128)
+        for k, (idx, v) in enumerate(sparse_entries.items()):
+            flat[k] = sum(int(idx[int(p)]) * s_ for p, s_ in zip(ca[1], st))
+            vals[k] = v
+        r = lib().spn_plan_contract_sparse_cuda_source(ptr(ca[0]), len(a), ptr(flat), ptr(vals), len(flat), ptr(cb), len(b),
+                                                       dtype_b, layout_b, 1 if sparse_first else 0)
+    if r is None:
+        raise SpensoError(1, lib().spn_last_error().decode(errors="replace"))
+    return r.decode()
 
 
 def _row_major_strides(shape: Sequence[int]):

@@ -62,6 +62,7 @@ SYMBOLS = {
     "spn_ctx_sm_count": (_I, [_P]),
     "spn_ctx_plan_cache_stats": (_I, [_P, _P, _P, _P]),
     "spn_plan_contract_cuda_source": (C.c_char_p, [_P, _U32, _I, _I, _P, _U32, _I, _I]),
+    "spn_plan_contract_sparse_cuda_source": (C.c_char_p, [_P, _U32, _P, _P, _U64, _P, _U32, _I, _I, _I]),
     "spn_tensor_batched": (_I, [_P, _P, _U32, _U64, _I, _I, C.POINTER(_P)]),
     "spn_tensor_batched_wrap": (_I, [_P, _P, _U32, _U64, _I, _I, _P, C.POINTER(_P)]),
     "spn_tensor_shared_dense": (_I, [_P, _P, _U32, _P, C.POINTER(_P)]),

@@ -696,6 +696,25 @@ const char* spn_plan_contract_cuda_source(const spn_slot* a, uint32_t na, int dt
   }
 }
 
+const char* spn_plan_contract_sparse_cuda_source(const spn_slot* sparse, uint32_t n_sparse, const uint64_t* flat,
+                                                 const double* values, uint64_t n_entries, const spn_slot* batched,
+                                                 uint32_t n_batched, int dtype, int layout, int sparse_first) {
+  static thread_local std::string src;
+  try {
+    Structure ss = structure_of_canonical(sparse, n_sparse);
+    std::map<uint64_t, double2> entries;
+    for (uint64_t i = 0; i < n_entries; ++i) {
+      if (flat[i] >= ss.size()) throw Error(SPN_ERR_INVALID, "sparse entry outside the tensor");
+      entries[flat[i]] = make_double2(values[2 * i], values[2 * i + 1]);
+    }
+    src = pair_jit_source_sparse(ss, entries, structure_of_canonical(batched, n_batched), dtype, layout, sparse_first != 0);
+    return src.c_str();
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
 int spn_ctx_create(int device, spn_ctx** out) {
   API_TRY
   int count = 0;

@@ -17,6 +17,7 @@ struct JitKernel {
   cudaKernel_t kernel = nullptr;
   int blocks_per_sm = 0;
   int block = 0;          // threads per CTA this kernel was generated for (0: the caller's default)
+  bool flat = false;      // launched with one point per thread (hardware-scheduled CTAs) instead of one persistent wave
   int num_regs = 0;
   size_t smem_bytes = 0;  // dynamic shared memory (prefetch ring)
   ~JitKernel() {

@@ -917,7 +917,20 @@ struct spn_net {
     return sp;
   }
 
-  int variant_block(const std::string& variant) const { return plan_prefetch(variant).mode == PF_GATHER ? kGatherBlock : kBlock; }
+  // Kernels that stream (no prefetch ring) and store a result per point are launched FLAT: CTAs of kFlatBlock threads, one
+  // point per thread, as many CTAs as that takes.  Small hardware-scheduled CTAs drift out of step, so the loads of
+  // one overlap the stores of another; a persistent grid of 256-thread CTAs moves in lockstep.  Measured on every such
+  // workload (profiles/r02_net_grid.txt): cfg2 2.395 -> 2.460e10 evals/s, cfg2 component-major 2.475 -> 2.530, cfg2m
+  // 1.908 -> 1.939, cfg3 8.01 -> 8.27e8 (component-major 6.25 -> 6.33e9).  Kernels that fold a Monte-Carlo sum or run
+  // a prefetch ring keep the persistent 256-thread CTAs (see kBlock).  SPN_NET_PERSISTENT=1 / SPN_BLOCK=n for A/B runs.
+  static constexpr int kFlatBlock = 64;
+  bool variant_flat(const std::string& variant) const {
+    return variant.back() != 's' && plan_prefetch(variant).mode == PF_NONE && !getenv("SPN_NET_PERSISTENT");
+  }
+  int variant_block(const std::string& variant) const {
+    if (plan_prefetch(variant).mode == PF_GATHER) return kGatherBlock;
+    return (variant_flat(variant) && !getenv("SPN_BLOCK")) ? kFlatBlock : kBlock;
+  }
 
   std::string gen_source(const std::string& variant, const std::string& kname) const {
     const int kBlock = variant_block(variant);   // shadows the member: threads per CTA of THIS variant
@@ -1416,6 +1429,7 @@ struct spn_net {
     k->source = gen_source(variant, k->name);
     k->smem_bytes = plan_prefetch(variant).smem_bytes;
     k->block = variant_block(variant);
+    k->flat = variant_flat(variant);
     // occupancy experiments: SPN_PAD_SMEM_KB adds unused dynamic shared memory (fewer CTAs per SM, grid follows)
     if (const char* e = getenv("SPN_PAD_SMEM_KB")) k->smem_bytes += (size_t)atoi(e) * 1024;
     jit_compile(*k);
@@ -2244,7 +2258,7 @@ static void execute_host_impl(spn_net* net, const void* const* host_inputs, uint
     double* out_ptr = host_out ? static_cast<double*>(P.out[s]) : nullptr;
     unsigned long long ocs = chunk_points, np = cnt;
     double2* partial = host_sum ? P.partial[s] : nullptr;
-    const unsigned grid = (unsigned)std::min<uint64_t>((cnt + kblock - 1) / kblock, cap);
+    const unsigned grid = (unsigned)std::min<uint64_t>((cnt + kblock - 1) / kblock, k.flat ? 0x7fffffffull : cap);
     std::vector<void*> args;
     for (uint32_t i = 0; i < n_inputs; ++i) {
       args.push_back(&in_ptr[i]);
@@ -2415,8 +2429,8 @@ int spn_net_execute(spn_net* net, const spn_tensor* const* inputs, uint32_t n_in
     return SPN_OK;
   }
   const uint64_t need = (n_points + kblock - 1) / kblock;
-  const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;
-  const unsigned grid = (unsigned)std::min<uint64_t>(need, cap);
+  const uint64_t cap = (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm;   // persistent kernels: one wave
+  const unsigned grid = (unsigned)std::min<uint64_t>(need, k.flat ? 0x7fffffffull : cap);
 
   std::vector<const double*> in_ptr(n_inputs);
   std::vector<unsigned long long> in_cs(n_inputs);

@@ -8,11 +8,14 @@
 // cache lines (one sector each); beyond S = 64 B that runs into the L1 tag rate and the kernels of round 1 stalled at
 // 0.75-0.87 of the HBM roofline.  So point-major operands and results are STAGED: every warp owns slabs of 32
 // consecutive points; it copies the slab — a contiguous 32*S byte range — global -> shared with 16-byte cp.async
-// (LDGSTS; consecutive lanes = consecutive addresses, i.e. full lines), two slabs deep, into a padded [point][unit]
-// layout (row stride odd in 16-byte units => the thread-=-point reads that follow are bank-conflict free); results go
-// registers -> padded shared slab -> contiguous 16-byte global stores.  No block barrier: a warp only touches its
-// own slabs (__syncwarp).  Component-major operands are already coalesced thread = point and are read directly; a
-// shared dense operand is read with uniform (broadcast) loads; a shared sparse operand is literals in the code.
+// (LDGSTS; consecutive lanes = consecutive addresses, i.e. full lines) into a padded [point][unit] layout (row stride
+// odd in 16-byte units => the thread-=-point reads that follow are bank-conflict free); results go registers -> padded
+// shared slab -> contiguous 16-byte global stores.  No block barrier: a warp only touches its own slabs (__syncwarp).
+// A CTA is ONE warp with ONE slab and the grid has as many CTAs as there are slabs: the hardware scheduler keeps the
+// resident warps out of step with each other, which is what overlaps the load phase of one with the store phase of
+// another (a persistent grid of 4-warp CTAs — round 2's first version, still behind SPN_PAIR_PERSISTENT=1 — measured
+// 10-22 % slower on every shape).  Component-major operands are already coalesced thread = point and are read
+// directly; a shared dense operand is read with uniform (broadcast) loads; a shared sparse operand is literals in the code.
 //
 // The arithmetic is the reference's, operation for operation (singlecontract.rs:25-196, multicontract.rs:25-200,
 // exteriorproduct.rs:19-153; complex product algebra/complex/mul.rs:16-21; f64 upgraded to (x, 0.0),
@@ -32,8 +35,13 @@ namespace spn {
 
 namespace {
 
-const int kPairBlock = getenv("SPN_PAIR_BLOCK") ? atoi(getenv("SPN_PAIR_BLOCK")) : 256;  // direct kernels: threads per CTA
-const int kSlabWarps = getenv("SPN_PAIR_SLAB_WARPS") ? atoi(getenv("SPN_PAIR_SLAB_WARPS")) : 4;  // staged kernels: warps per CTA
+// direct kernels: threads per CTA.  Small, for the same reason: the threads of a CTA run load phase / store phase in
+// step, and only CTAs out of step overlap the two (component-major 768-byte points: 5.94 TB/s at 64 threads, 4.72 at 256).
+const int kPairBlock = getenv("SPN_PAIR_BLOCK") ? atoi(getenv("SPN_PAIR_BLOCK")) : 64;
+// staged kernels: warps per CTA.  One: a CTA is a warp with its slab — nothing is shared between warps, so there is
+// nothing to gain from larger CTAs, and single-warp CTAs drift apart in time (loads of one overlap stores of another)
+// where the 4 warps of one CTA start together: 1 344-byte points 6.83 vs 5.26 TB/s (profiles/r02_pairwise_grid.txt).
+const int kSlabWarps = getenv("SPN_PAIR_SLAB_WARPS") ? atoi(getenv("SPN_PAIR_SLAB_WARPS")) : 1;
 
 struct Operand {
   const spn_tensor* t;
@@ -456,13 +464,53 @@ std::string pair_jit_source(const Structure& sa, int dtype_a, int layout_a, cons
   return g.source;
 }
 
+// The same inspection for a SHARED SPARSE operand (its stored entries become part of the code) against a batched one.
+std::string pair_jit_source_sparse(const Structure& ss, const std::map<uint64_t, double2>& entries, const Structure& sd,
+                                   int dtype_d, int layout_d, bool sparse_first) {
+  spn_tensor s, d, r;
+  s.st = ss;
+  s.storage = SPN_STORAGE_SHARED_SPARSE;
+  s.dtype = SPN_C64;
+  s.layout = SPN_POINT_MAJOR;
+  s.n_points = 0;
+  s.entries = entries;
+  s.owns = false;
+  auto fake = [](spn_tensor& t, const Structure& st, int dtype, int layout) {
+    t.st = st;
+    t.storage = SPN_STORAGE_BATCHED;
+    t.dtype = dtype;
+    t.layout = layout;
+    t.n_points = 4096;
+    t.dptr = reinterpret_cast<void*>(uintptr_t(1) << 20);  // never dereferenced: alignment only
+    t.owns = false;
+  };
+  fake(d, sd, dtype_d, layout_d);
+  const spn_tensor* a = sparse_first ? &s : &d;
+  const spn_tensor* b = sparse_first ? &d : &s;
+  spn_contract_plan plan = plan_contract(a->st, b->st);
+  KTables kt = build_k_tables(plan, false);
+  if (!pair_jit_applicable(plan, kt, a, b, true, 4096)) return std::string();
+  fake(r, structure_of_plan_result(plan), SPN_C64, layout_d);
+  JitKernel k;
+  k.name = "spn_pair_contract_inspect";
+  Generated g = generate(plan, kt, a, b, &r, k.name, true);
+  k.source = g.source;
+  jit_compile(k);
+  return g.source;
+}
+
 void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const spn_tensor* b, spn_tensor* res,
                      uint64_t n_points) {
   JitKernel& k = *pj.k;
   // direct kernels: one thread per point; staged kernels: one warp per slab of 32 points
   const uint64_t need = pj.slab ? ((n_points + 31) / 32 + (uint64_t)(pj.block / 32) - 1) / (uint64_t)(pj.block / 32)
                                 : (n_points + (uint64_t)pj.block - 1) / (uint64_t)pj.block;
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm));
+  // Hardware-scheduled grid: one slab per warp (one point per thread), as many CTAs as that takes.  The kernels keep
+  // their grid-stride loop, but a persistent launch — SMs x resident CTAs, every warp walking its slabs in lockstep with
+  // all others — costs 10-22 % on these streams (profiles/r02_pairwise_grid.txt, tools/probes/write_stream_probe.cu: a
+  // plain fill drops from 6.87 to 5.93 TB/s when it is made persistent).  SPN_PAIR_PERSISTENT=1 restores it for A/B runs.
+  const uint64_t cap = getenv("SPN_PAIR_PERSISTENT") ? (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm : 0x7fffffffull;
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, cap));
   const double* pa = static_cast<const double*>(a->dptr);
   const double* pb = static_cast<const double*>(b->dptr);
   double* pc = static_cast<double*>(res->dptr);

@@ -199,6 +199,8 @@ PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTable
 void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const spn_tensor* b, spn_tensor* res,
                      uint64_t n_points);
 std::string pair_jit_source(const Structure& sa, int dtype_a, int layout_a, const Structure& sb, int dtype_b, int layout_b);
+std::string pair_jit_source_sparse(const Structure& ss, const std::map<uint64_t, double2>& entries, const Structure& sd,
+                                   int dtype_d, int layout_d, bool sparse_first);
 
 // comm.cu: fold the per-CTA partials (or take inout as the local sum when partial == nullptr) and exchange with
 // the peers in one launch on the context's stream

@@ -390,3 +390,23 @@ def test_symbolic_abstract_indices_are_interned_and_ordered_last():
     assert p.n_common == 1 and p.order_out == 4 and p.k_metric[0] == 1          # the Minkowski index nu is contracted
     om = O.merge(a, b)
     assert bytes(p.out_slots)[:16 * 4] == om["slots"].tobytes()
+
+
+def test_sparse_operand_kernel_source_inspection():
+    """Host-only inspection of the specialised pairwise kernels (source generation + NVRTC, no device): a shared sparse
+    operand contributes its stored entries as literals (gamma^mu p_mu: 16 products, not 64); point-major operands and
+    results are staged in warp-owned slabs; a component-major partner is read directly."""
+    b = lambda a: sp.Bispinor.new_slot(4, a)
+    m = lambda a: sp.Minkowski.new_slot(4, a)
+    ent = {(0, 2, 0): 1, (1, 3, 0): 1, (2, 0, 0): 1, (3, 1, 0): 1, (0, 3, 1): 1, (1, 2, 1): 1, (2, 1, 1): -1, (3, 0, 1): -1,
+           (0, 3, 2): -1j, (1, 2, 2): 1j, (2, 1, 2): 1j, (3, 0, 2): -1j, (0, 2, 3): 1, (1, 3, 3): -1, (2, 0, 3): -1, (3, 1, 3): 1}
+    for first in (True, False):
+        src = sp.contract_cuda_source([b(1), b(2), m(3)], [m(3)], sparse_entries=ent, sparse_first=first)
+        assert src.count("cmul_rn(") == 16 + 1 and "warp-owned slabs" in src and "sC[15] = r15;" in src
+        assert src.count("__dsub_rn(r") == 2 * 12           # the three spatial directions subtract (Minkowski metric)
+    src = sp.contract_cuda_source([b(1), b(2), m(3)], [m(3)], sparse_entries=ent, layout_b=sp.COMPONENT_MAJOR)
+    assert src and "warp-owned slabs" not in src and "csB + p" in src
+    # a result too large for registers takes the generic kernels
+    assert sp.contract_cuda_source([b(1), b(2), m(3)], [b(4), b(5), m(6), m(7)], sparse_entries=ent) == ""
+    # two batched tensors: the inspection entry point of the dense kernels
+    assert "warp-owned slabs" in sp.contract_cuda_source([b(1), b(2)], [b(2), b(3)])

@@ -1246,8 +1246,9 @@ def test_execute_host_async_keeps_order_and_results(ctx, name, scale, real):
 
 @pytest.mark.parametrize("seed", range(4))
 def test_slab_staged_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
-    """The specialised pairwise kernels in their three memory paths — warp-owned cp.async slabs (default), direct
-    thread = point loads (SPN_PAIR_NO_SLAB) and TMA bulk copies (SPN_LOAD_MODE=tma) — against the generic kernel
+    """The specialised pairwise kernels in their three memory paths — warp-owned cp.async slabs (default; also launched
+    as a persistent grid, SPN_PAIR_PERSISTENT), direct thread = point loads (SPN_PAIR_NO_SLAB) and TMA bulk copies
+    (SPN_LOAD_MODE=tma) — against the generic kernel
     (SPN_NO_PAIR_JIT) on the same operands: identical bits, for a ragged point count (a partial last slab), c64 and f64
     operands, both layouts, dense and shared-sparse partners."""
     import os
@@ -1277,8 +1278,8 @@ def test_slab_staged_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
             tb = mk(cb, dtb)
         results = {}
         for name, env in (("generic", {"SPN_NO_PAIR_JIT": "1"}), ("slab", {}), ("direct", {"SPN_PAIR_NO_SLAB": "1"}),
-                          ("tma", {"SPN_LOAD_MODE": "tma"})):
-            for k in ("SPN_NO_PAIR_JIT", "SPN_PAIR_NO_SLAB", "SPN_LOAD_MODE"):
+                          ("tma", {"SPN_LOAD_MODE": "tma"}), ("persistent", {"SPN_PAIR_PERSISTENT": "1"})):
+            for k in ("SPN_NO_PAIR_JIT", "SPN_PAIR_NO_SLAB", "SPN_LOAD_MODE", "SPN_PAIR_PERSISTENT"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             try:
@@ -1291,7 +1292,7 @@ def test_slab_staged_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
                     os.environ.pop(k, None)
         if results is None:
             continue
-        for name in ("slab", "direct", "tma"):
+        for name in ("slab", "direct", "tma", "persistent"):
             assert np.array_equal(results[name], results["generic"]), f"case {it}: {name} differs from the generic kernel"
         done += 1
     assert done >= 4
@@ -1401,3 +1402,67 @@ def test_fused_tma_loader_equals_the_default_loader(ctx, monkeypatch, name, n_po
     assert "cp.async.bulk" in src1 and "mbarrier.try_wait" in src1 and "cp.async.bulk" not in src0
     assert np.array_equal(got.view(np.float64), want.view(np.float64))
     assert rel_err(got_sum, want_sum) <= 1e-12
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_sparse_times_small_batched_kernels_bit_for_bit(ctx, seed):
+    """Shared sparse x small batched operand (gamma^mu p_mu and relatives — a write stream: the result is larger than the
+    batched operand).  The specialised kernel — hardware-scheduled single-warp CTAs by default, the persistent grid of
+    SPN_PAIR_PERSISTENT=1 — gives bit-for-bit the generic kernel's results (SPN_NO_PAIR_JIT) and the oracle's: with the
+    sparse tensor on either side, c64 and f64 partners, 2..128 result elements, 1-4 stored products per element, metric
+    signs, and a ragged last slab."""
+    import os
+
+    rng = np.random.default_rng(4200 + seed)
+    b = lambda a: sp.Bispinor.new_slot(4, a)
+    m = lambda a: sp.Minkowski.new_slot(4, a)
+    e3 = lambda a: sp.Euclidean.new_slot(2, a)
+    gamma = {(0, 2, 0): 1, (1, 3, 0): 1, (2, 0, 0): 1, (3, 1, 0): 1, (0, 3, 1): 1, (1, 2, 1): 1, (2, 1, 1): -1, (3, 0, 1): -1,
+             (0, 3, 2): -1j, (1, 2, 2): 1j, (2, 1, 2): 1j, (3, 0, 2): -1j, (0, 2, 3): 1, (1, 3, 3): -1, (2, 0, 3): -1, (3, 1, 3): 1}
+    n_points = 4099
+
+    def random_entries(dims, fill):
+        ent = {}
+        for idx in np.ndindex(*dims):
+            if rng.random() < fill:
+                ent[tuple(int(i) for i in idx)] = complex(rng.uniform(-1, 1), rng.uniform(-1, 1))
+        return ent or {tuple(0 for _ in dims): 1.0}
+
+    cases = [
+        ([b(1), b(2), m(3)], gamma, [m(3)]),                                       # 16 elements, 2 products each or none
+        ([b(1), b(2), m(3)], random_entries((4, 4, 4), 0.7), [m(3)]),                # up to 4 products (Minkowski signs)
+        ([b(1), m(3)], random_entries((4, 4), 0.5), [m(3)]),                         # 4 elements
+        ([e3(1), m(3)], random_entries((2, 4), 0.6), [m(3)]),                        # 2 elements
+        ([b(1), b(2), m(3), m(4)], random_entries((4, 4, 4, 4), 0.15), [m(4)]),      # 64 elements
+        ([b(1), b(2), m(3)], random_entries((4, 4, 4), 0.3), [b(2), m(3), e3(5)]),   # 2 contracted indices, 8 elements
+        ([b(1), b(2)], random_entries((4, 4), 0.4), [b(5), e3(6)]),                  # exterior product, 128 elements
+    ]
+    for it, (ssl, ent, dsl) in enumerate(cases):
+        for dt in (sp.C64, sp.F64):
+            for sparse_first in (True, False):
+                cd = O.order_structure(sp.slots(dsl))[0]
+                shape = [n_points] + [int(d) for d in cd["dim"]]
+                data = rng.uniform(-1, 1, size=shape) if dt == sp.F64 else _cases.random_complex(rng, shape)
+                td = sp.BatchTensor.empty(ctx, cd, n_points, dt)
+                td.upload(np.ascontiguousarray(data).reshape(n_points, -1))
+                ts = sp.SparseTensor.from_entries(ctx, ssl, ent)
+                assert sp.contract_cuda_source(ssl, cd, sparse_entries=ent, dtype_b=dt, sparse_first=sparse_first)
+                results = {}
+                for name, env in (("generic", {"SPN_NO_PAIR_JIT": "1"}), ("flat", {}), ("persistent", {"SPN_PAIR_PERSISTENT": "1"})):
+                    for k in ("SPN_NO_PAIR_JIT", "SPN_PAIR_PERSISTENT"):
+                        os.environ.pop(k, None)
+                    os.environ.update(env)
+                    try:
+                        r = ts.contract(td) if sparse_first else td.contract(ts)
+                        results[name] = r.to_numpy()
+                    finally:
+                        for k in env:
+                            os.environ.pop(k, None)
+                assert np.array_equal(results["flat"], results["generic"]), f"case {it}: specialised kernel differs from generic"
+                assert np.array_equal(results["persistent"], results["generic"]), f"case {it}: persistent launch differs"
+                if it < 2 and dt == sp.C64:   # and the oracle, on the physics case
+                    oa = O.OTensor.sparse(sp.slots(ssl), ent)
+                    pts = range(0, n_points, 997)
+                    od = [O.OTensor.dense(cd, data[p], canonicalize=False) for p in pts]
+                    want = np.stack([(oa.contract(x) if sparse_first else x.contract(oa)).to_dense() for x in od])
+                    assert np.array_equal(results["flat"].reshape(n_points, -1)[::997], want.reshape(len(want), -1))

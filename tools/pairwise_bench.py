@@ -60,6 +60,11 @@ cases.append(("dense[bis,bis] x dense[bis] -> [bis]              (K1)", lambda: 
 cases.append(("dense[bis,bis] + dense[bis,bis]              (add)", lambda: M1 + M1, 3 * 16 * 16))
 W, sw = rand_batch([b(1), b(2)])
 cases.append(("dense[bis,bis] x dense[bis,bis] -> scalar (multi, K5)", lambda: M1.contract(W), (s1 + sw + 1) * 16))
+M1c, _ = rand_batch([b(1), b(2)], sp.COMPONENT_MAJOR)
+M2c, _ = rand_batch([b(2), b(3)], sp.COMPONENT_MAJOR)
+cases.append(("component-major dense[bis,bis] x dense[bis,bis] -> [bis,bis]", lambda: M1c.contract(M2c), (s1 + s2 + 16) * 16))
+Pc, _ = rand_batch([m(3)], sp.COMPONENT_MAJOR)
+cases.append(("component-major sparse gamma x dense[mink] -> [bis,bis]", lambda: G.contract(Pc), (sp_ + 16) * 16))
 # control: what this box's HBM gives a plain torch kernel of the same shape as the element-wise add (2 reads + 1 write)
 xa = torch.rand(n * 32, dtype=torch.float64, device="cuda")
 xb = torch.rand(n * 32, dtype=torch.float64, device="cuda")
