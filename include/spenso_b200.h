@@ -114,8 +114,8 @@ const char* spn_plan_contract_cuda_source(const spn_slot* a, uint32_t na, int dt
                                           uint32_t nb, int dtype_b, int layout_b);
 
 /* The same for a SHARED SPARSE tensor (n_entries stored values: flat index, (re, im) pairs) against a batched one;
- * sparse_first != 0: the sparse tensor is the receiver a of a.contract(b).  gamma^mu p_mu takes a kernel whose lanes
- * map to the units of the result. */
+ * sparse_first != 0: the sparse tensor is the receiver a of a.contract(b).  The stored entries appear as literals in
+ * the code. */
 const char* spn_plan_contract_sparse_cuda_source(const spn_slot* sparse, uint32_t n_sparse, const uint64_t* flat,
                                                  const double* values, uint64_t n_entries, const spn_slot* batched,
                                                  uint32_t n_batched, int dtype, int layout, int sparse_first);

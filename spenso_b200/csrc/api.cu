@@ -388,6 +388,7 @@ static void contract_key(std::string& key, const spn_ctx* ctx, const spn_tensor*
   key.push_back(lm ? lm[0] : '-');
   key.push_back(getenv("SPN_NO_PAIR_JIT") ? 'g' : 'j');
   key.push_back(getenv("SPN_PAIR_NO_SLAB") ? 'd' : 's');
+  key.push_back(getenv("SPN_PAIR_NO_ROWS") ? 'g' : 'r');
 }
 
 static std::shared_ptr<ContractEntry> build_entry(spn_ctx* ctx, const spn_tensor* a, const spn_tensor* b,

@@ -96,13 +96,234 @@ std::string addr(const Operand& o, uint64_t f) {
 
 struct Generated {
   std::string source;
+  uint32_t rows = 1;   // row-parallel kernels: threads per point
+  uint32_t points_per_cta = 0;   // row-parallel kernels: whole points per CTA
   bool slab = false;
   size_t smem_bytes = 0;
   int block = 0;
 };
 
+// ---- row-parallel kernels: per-point tensors too large for one thread's registers ---------------------------------
+// dense[coad^3] x dense[coad^2] -> [coad^3] is a 64x8 by 8x8 product per point: 576 operand components, 512 results, 4 096
+// products.  The generic kernel (one thread per result element, offsets from tables) re-reads every operand element 8-64
+// times through L1 and reaches 1.1 TB/s.  Here the free indices of ONE batched operand X become a thread dimension:
+// thread = (point, row i of X), a CTA = the rows of whole points (64 threads or one point, whichever is more), launched
+// flat.  A thread keeps its row of X — the n_k contracted components at literal offsets from a per-row base, 256-bit
+// loads — in registers, walks the free components j of the other operand Y and writes result[i, j].  Y: a batched one
+// is staged once per CTA in shared memory (every row of a point reads all of it: a broadcast; read through L1 instead
+// the rows ran into each other's misses — L1 hit rate 38 %, FP64 pipe 41 % busy — 1.12 ms against 0.86 ms staged); a
+// shared dense one is read through L1 at literal offsets; a shared sparse one is its stored entries as literals, and
+// only the components of X that meet one are loaded.  The sums are the reference's (k order, from zero, "-=" on a
+// negative metric, no FMA): bit-for-bit the generic kernels.  Measured at 2^18 points (profiles/r02_pairwise_rows.txt):
+// 4.01 ms -> 0.86 ms (5.3 TB/s) for the product above, 0.85 -> 0.29 ms for dense[coad^3] x sparse f.  A prefetch of the
+// rows 256-8192 points ahead into L2 was tried and dropped (+3 % before Y was staged, -7 % after).
+struct RowSplit {
+  bool ok = false;
+  bool rows_from_a = true;
+  uint32_t n_rows = 0, n_cols = 0;
+  std::vector<uint64_t> row_x, row_c;   // per row: element offset inside X's record / inside the result record
+  std::vector<uint64_t> col_y, col_c;   // per column: element offset inside Y's record / inside the result record
+};
+
+bool register_form_fits(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b) {
+  const uint64_t loaded = (a->sparse() ? 0 : a->size()) + (b->sparse() ? 0 : b->size());
+  const uint64_t products = plan.size_out * (uint64_t)kt.off_a.size();
+  // everything lives in registers: at most ~80 complex operand components and a few thousand products
+  return !(loaded > 80 || plan.size_out > 256 || products > 4096 || products == 0);
+}
+
+RowSplit row_split(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b) {
+  RowSplit rs;
+  if (getenv("SPN_PAIR_NO_ROWS")) return rs;
+  auto can_be_x = [](const spn_tensor* t) { return t->batched() && t->layout == SPN_POINT_MAJOR && ((uintptr_t)t->dptr % 16) == 0; };
+  auto can_be_y = [](const spn_tensor* t) { return !t->batched() || (t->layout == SPN_POINT_MAJOR && ((uintptr_t)t->dptr % 16) == 0); };
+  uint64_t free_a = 1, free_b = 1;
+  for (uint32_t r = 0; r < plan.order_out; ++r) (plan.partition[r] ? free_a : free_b) *= plan.out_dim[r];
+  const bool a_x = can_be_x(a) && can_be_y(b), b_x = can_be_x(b) && can_be_y(a);
+  if (!a_x && !b_x) return rs;
+  rs.rows_from_a = a_x && (!b_x || free_a >= free_b);
+  const uint64_t n_rows = rs.rows_from_a ? free_a : free_b, n_cols = rs.rows_from_a ? free_b : free_a;
+  const uint64_t n_k = kt.off_a.size();
+  if (n_rows < 2 || n_rows > 4096 || n_cols > 256 || n_k == 0 || n_k > 64 || n_cols * n_k > 1024) return rs;
+  if (plan.size_a > (1u << 20) || plan.size_b > (1u << 20) || plan.size_out > (1u << 20)) return rs;
+  rs.n_rows = (uint32_t)n_rows;
+  rs.n_cols = (uint32_t)n_cols;
+  // result record: row-major over out_dim
+  std::vector<uint64_t> ostride(plan.order_out, 1);
+  for (uint32_t r = plan.order_out; r-- > 1;) ostride[r - 1] = ostride[r] * plan.out_dim[r];
+  std::vector<uint32_t> ix(plan.order_out, 0);
+  for (uint64_t e = 0; e < plan.size_out; ++e) {
+    uint64_t ox = 0, oy = 0, cx = 0, cy = 0;
+    bool x_zero = true, y_zero = true;
+    for (uint32_t r = 0; r < plan.order_out; ++r) {
+      const bool from_x = (plan.partition[r] != 0) == rs.rows_from_a;
+      const uint64_t so = ix[r] * (rs.rows_from_a ? plan.out_stride_a[r] : plan.out_stride_b[r]);
+      const uint64_t sy = ix[r] * (rs.rows_from_a ? plan.out_stride_b[r] : plan.out_stride_a[r]);
+      if (from_x) { ox += so; cx += ix[r] * ostride[r]; x_zero = x_zero && ix[r] == 0; }
+      else { oy += sy; cy += ix[r] * ostride[r]; y_zero = y_zero && ix[r] == 0; }
+    }
+    if (y_zero) { rs.row_x.push_back(ox); rs.row_c.push_back(cx); }   // enumerated with the other side at zero
+    if (x_zero) { rs.col_y.push_back(oy); rs.col_c.push_back(cy); }
+    for (uint32_t r = plan.order_out; r-- > 0;) {
+      if (++ix[r] < plan.out_dim[r]) break;
+      ix[r] = 0;
+    }
+  }
+  rs.ok = rs.row_x.size() == n_rows && rs.col_y.size() == n_cols;
+  return rs;
+}
+
+Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
+                        const spn_tensor* b, const spn_tensor* res, const std::string& kname) {
+  const spn_tensor* X = rs.rows_from_a ? a : b;
+  const spn_tensor* Y = rs.rows_from_a ? b : a;
+  const char xn = rs.rows_from_a ? 'A' : 'B', yn = rs.rows_from_a ? 'B' : 'A';
+  const std::vector<long long>& kx = rs.rows_from_a ? kt.off_a : kt.off_b;
+  const std::vector<long long>& ky = rs.rows_from_a ? kt.off_b : kt.off_a;
+  const bool xc = X->dtype == SPN_C64, yc = Y->dtype == SPN_C64, oc = res->dtype == SPN_C64;
+  Generated gen;
+  // a CTA covers whole points: P of them if the rows of P points fill 64 threads, else one (threads rounded up to a warp)
+  const uint32_t P = rs.n_rows >= 64 ? 1u : 64u / rs.n_rows;
+  gen.block = (int)(((uint64_t)P * rs.n_rows + 31) / 32 * 32);
+  gen.rows = rs.n_rows;
+  gen.points_per_cta = P;
+  // a batched Y is staged once per CTA in shared memory: every row-thread of a point reads all of it (a broadcast), and
+  // through L1 those reads met each other's misses (ncu: L1 hit rate 38 %, long_scoreboard 9 cycles per issue, FP64 pipe 41 %)
+  const bool y_smem = Y->batched() && (Y->size() * (uint64_t)(yc ? 16 : 8)) % 16 == 0 && !getenv("SPN_PAIR_ROWS_NO_SMEM");
+  const uint64_t y_units = y_smem ? (Y->size() * (uint64_t)(yc ? 16 : 8) + 15) / 16 : 0;   // 16-byte units per point
+  const uint64_t y_row = y_units | 1ull;   // odd stride: the points of one warp sit in different banks
+  if (y_smem) gen.smem_bytes = (size_t)(P * y_row * 16);
+  std::ostringstream o;
+  o << "// generated by spenso_b200 (pairwise_jit.cu): one pairwise contraction, thread = (point, row of " << xn << "), reference rounding\n";
+  o << "// " << rs.n_rows << " rows x " << rs.n_cols << " columns x " << kx.size() << " contracted components per point, " << P
+    << " point(s) per CTA\n";
+  o << "typedef unsigned long long ull;\n";
+  o << "__device__ __forceinline__ double2 cmul_rn(double2 a, double2 b) {\n"
+       "  return make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));\n}\n";
+  o << "__device__ __forceinline__ void ld32(const double* p, double2& a, double2& b) {\n"
+       "  asm(\"ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];\" : \"=d\"(a.x), \"=d\"(a.y), \"=d\"(b.x), \"=d\"(b.y) : \"l\"(p));\n}\n";
+  // no "memory" clobber: nothing reads the result, and the loads of the next columns may move above the store
+  o << "__device__ __forceinline__ void st32(double* p, double2 a, double2 b) {\n"
+       "  asm volatile(\"st.global.v4.f64 [%0], {%1,%2,%3,%4};\" :: \"l\"(p), \"d\"(a.x), \"d\"(a.y), \"d\"(b.x), \"d\"(b.y));\n}\n";
+  o << "__device__ const unsigned kRowX[" << rs.n_rows << "] = {";
+  for (uint64_t v : rs.row_x) o << v << "u, ";
+  o << "};\n__device__ const unsigned kRowC[" << rs.n_rows << "] = {";
+  for (uint64_t v : rs.row_c) o << v << "u, ";
+  o << "};\n";
+  o << "extern \"C\" __global__ void __launch_bounds__(" << gen.block << ") " << kname
+    << "(const double* __restrict__ A, ull csA, const double* __restrict__ B, ull csB, double* __restrict__ C, ull csC, ull n_points) {\n";
+  o << "  const ull p0 = (ull)blockIdx.x * " << P << "ull;   // first point of this CTA\n";
+  o << "  const unsigned np = (unsigned)(n_points - p0 < " << P << "ull ? n_points - p0 : " << P << "ull);\n";
+  o << "  const unsigned pl = threadIdx.x / " << rs.n_rows << "u, i = threadIdx.x % " << rs.n_rows << "u;\n";
+  o << "  const bool live = pl < np;   // a thread of the last CTA's padding, or of the warp round-up, only helps staging\n";
+  o << "  const ull p = p0 + (live ? pl : 0u);\n";
+  o << "  const double* const X = " << xn << " + (p * " << X->size() << "ull + kRowX[i]) * " << (xc ? 2 : 1) << "ull;\n";
+  std::ostringstream stage;
+  if (y_smem) {
+    stage << "  extern __shared__ __align__(16) double2 ys[];   // [point][" << y_row << " units]\n";
+    stage << "  {\n    const double2* src = reinterpret_cast<const double2*>(" << yn << ") + p0 * " << y_units << "ull;   // the CTA's points: one contiguous range\n";
+    stage << "    for (unsigned g = threadIdx.x; g < np * " << y_units << "u; g += " << gen.block << "u)\n";
+    if (y_row == y_units)
+      stage << "      ys[g] = __ldg(src + g);\n";
+    else
+      stage << "      ys[g + g / " << y_units << "u] = __ldg(src + g);\n";
+    stage << "  }\n  __syncthreads();\n";
+    stage << "  if (!live) return;\n";
+    stage << "  const double* const Y = reinterpret_cast<const double*>(ys + pl * " << y_row << "u);\n";
+  } else {
+    stage << "  if (!live) return;\n";
+    if (Y->batched())
+      stage << "  const double* const Y = " << yn << " + p * " << Y->size() * (yc ? 2 : 1) << "ull;\n";
+    else if (!Y->sparse())
+      stage << "  const double* const Y = " << yn << ";\n";
+  }
+  o << "  double* const O = C + (p * " << plan.size_out << "ull + kRowC[i]) * " << (oc ? 2 : 1) << "ull;\n";
+  // which (j, k) products exist (a sparse Y contributes its stored entries only), and which components of the row they use
+  auto y_entry = [&](uint32_t j, size_t k) -> const double2* {
+    if (!Y->sparse()) return nullptr;
+    auto it = Y->entries.find(rs.col_y[j] + (uint64_t)ky[k]);
+    return it == Y->entries.end() ? nullptr : &it->second;
+  };
+  std::vector<char> k_used(kx.size(), 0);
+  for (uint32_t j = 0; j < rs.n_cols; ++j)
+    for (size_t k = 0; k < kx.size(); ++k)
+      if (!Y->sparse() || y_entry(j, k)) k_used[k] = 1;
+  // the row of X: 256-bit loads where two used neighbours share a 32-byte sector (every row base and the record even)
+  bool even_rows = xc && X->size() % 2 == 0 && ((uintptr_t)X->dptr % 32) == 0 && jit_has_256bit_loads();
+  for (uint64_t v : rs.row_x) even_rows = even_rows && v % 2 == 0;
+  std::map<long long, size_t> k_of_off;
+  for (size_t k = 0; k < kx.size(); ++k)
+    if (k_used[k]) k_of_off[kx[k]] = k;
+  std::vector<char> loaded(kx.size(), 0);
+  for (size_t k = 0; k < kx.size(); ++k) {
+    if (!k_used[k] || loaded[k]) continue;
+    const long long off = kx[k];
+    auto mate = k_of_off.find(off ^ 1ll);
+    if (even_rows && mate != k_of_off.end() && !loaded[mate->second] && mate->second != k) {
+      const size_t lo = (off & 1ll) ? mate->second : k, hi = (off & 1ll) ? k : mate->second;
+      o << "  double2 x" << lo << ", x" << hi << "; ld32(X + " << (off & ~1ll) * 2 << "ull, x" << lo << ", x" << hi << ");\n";
+      loaded[lo] = loaded[hi] = 1;
+    } else {
+      if (xc)
+        o << "  const double2 x" << k << " = __ldg(reinterpret_cast<const double2*>(X + " << off * 2 << "ull));\n";
+      else
+        o << "  const double2 x" << k << " = make_double2(__ldg(X + " << off << "ull), 0.0);\n";
+      loaded[k] = 1;
+    }
+  }
+  o << stage.str();   // the row's loads are in flight while the CTA stages Y
+  bool even_out = oc && plan.size_out % 2 == 0 && ((uintptr_t)res->dptr % 32) == 0;
+  for (uint64_t v : rs.row_c) even_out = even_out && v % 2 == 0;
+  std::string pending;
+  uint64_t pending_c = 0;
+  auto flush = [&]() {
+    if (pending.empty()) return;
+    o << "  *reinterpret_cast<double2*>(O + " << pending_c * 2 << "ull) = " << pending << ";\n";
+    pending.clear();
+  };
+  for (uint32_t j = 0; j < rs.n_cols; ++j) {
+    o << "  double2 r" << j << " = make_double2(0.0, 0.0);\n";
+    for (size_t k = 0; k < kx.size(); ++k) {
+      std::string yv;
+      if (Y->sparse()) {
+        const double2* v = y_entry(j, k);
+        if (!v) continue;   // the sparse fibre holds no entry here
+        yv = "make_double2(" + lit(v->x) + ", " + lit(v->y) + ")";
+      } else {
+        const uint64_t f = rs.col_y[j] + (uint64_t)ky[k];
+        if (y_smem)
+          yv = yc ? "*reinterpret_cast<const double2*>(Y + " + std::to_string(f * 2) + "u)" : "make_double2(Y[" + std::to_string(f) + "u], 0.0)";
+        else
+          yv = yc ? "__ldg(reinterpret_cast<const double2*>(Y + " + std::to_string(f * 2) + "ull))"
+                  : "make_double2(__ldg(Y + " + std::to_string(f) + "ull), 0.0)";
+      }
+      const std::string xv = "x" + std::to_string(k);
+      o << "  { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : yv) << ", " << (rs.rows_from_a ? yv : xv) << "); r" << j << ".x = "
+        << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(r" << j << ".x, t.x); r" << j << ".y = "
+        << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(r" << j << ".y, t.y); }\n";
+    }
+    const uint64_t c = rs.col_c[j];
+    if (!oc) {
+      o << "  O[" << c << "ull] = r" << j << ".x;\n";
+    } else if (even_out && !pending.empty() && c == pending_c + 1 && pending_c % 2 == 0) {
+      o << "  st32(O + " << pending_c * 2 << "ull, " << pending << ", r" << j << ");\n";
+      pending.clear();
+    } else {
+      flush();
+      pending = "r" + std::to_string(j);
+      pending_c = c;
+      if (!even_out) flush();
+    }
+  }
+  flush();
+  o << "}\n";
+  gen.source = o.str();
+  return gen;
+}
+
 Generated generate(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b,
                    const spn_tensor* res, const std::string& kname, bool wide_stores) {
+  if (!register_form_fits(plan, kt, a, b)) return generate_rows(row_split(plan, kt, a, b), plan, kt, a, b, res, kname);
   const bool wide_loads = !getenv("SPN_NO_WIDE_LOADS");
   Generated gen;
   Staging sa = a->sparse() ? Staging() : staging_of(a, true), sb = b->sparse() ? Staging() : staging_of(b, true), sc = staging_of(res, false);
@@ -388,10 +609,9 @@ bool pair_jit_applicable(const spn_contract_plan& plan, const KTables& kt, const
   // specialising costs one NVRTC compile (~0.3 s, cached on disk): only worth it for batches that amortise it
   if (!res_batched || n_points < 2048) return false;
   if (a->sparse() && b->sparse()) return false;
-  const uint64_t loaded = (a->sparse() ? 0 : a->size()) + (b->sparse() ? 0 : b->size());
-  const uint64_t products = plan.size_out * (uint64_t)kt.off_a.size();
-  // everything lives in registers: at most ~80 complex operand components and a few thousand products
-  return !(loaded > 80 || plan.size_out > 256 || products > 4096 || products == 0);
+  if (register_form_fits(plan, kt, a, b)) return true;
+  // too large for one thread: one thread per (point, row of a batched operand) if the shape allows
+  return plan.size_out * (uint64_t)kt.off_a.size() != 0 && row_split(plan, kt, a, b).ok;
 }
 
 PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a,
@@ -407,6 +627,7 @@ PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTable
   }
   key.push_back(wide ? 'w' : 'n');
   key.push_back(tma_mode() ? 'T' : 'L');
+  key.push_back(getenv("SPN_PAIR_NO_ROWS") ? 'g' : (getenv("SPN_PAIR_ROWS_NO_SMEM") ? 'l' : 'r'));
   key.append(reinterpret_cast<const char*>(kt.off_a.data()), kt.off_a.size() * sizeof(long long));
   key.append(reinterpret_cast<const char*>(kt.off_b.data()), kt.off_b.size() * sizeof(long long));
   key.append(reinterpret_cast<const char*>(kt.sign.data()), kt.sign.size());
@@ -433,6 +654,8 @@ PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTable
   pj.k = k;
   pj.block = g.block;
   pj.slab = g.slab;
+  pj.rows = g.rows;
+  pj.points_per_cta = g.points_per_cta;
   ctx->pair_kernels.emplace(h, pj);
   return pj;
 }
@@ -503,8 +726,8 @@ void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const
                      uint64_t n_points) {
   JitKernel& k = *pj.k;
   // direct kernels: one thread per point; staged kernels: one warp per slab of 32 points
-  const uint64_t need = pj.slab ? ((n_points + 31) / 32 + (uint64_t)(pj.block / 32) - 1) / (uint64_t)(pj.block / 32)
-                                : (n_points + (uint64_t)pj.block - 1) / (uint64_t)pj.block;
+  const uint64_t need = pj.points_per_cta ? (n_points + pj.points_per_cta - 1) / pj.points_per_cta : pj.slab ? ((n_points + 31) / 32 + (uint64_t)(pj.block / 32) - 1) / (uint64_t)(pj.block / 32)
+                                : (n_points * (uint64_t)pj.rows + (uint64_t)pj.block - 1) / (uint64_t)pj.block;
   // Hardware-scheduled grid: one slab per warp (one point per thread), as many CTAs as that takes.  The kernels keep
   // their grid-stride loop, but a persistent launch — SMs x resident CTAs, every warp walking its slabs in lockstep with
   // all others — costs 10-22 % on these streams (profiles/r02_pairwise_grid.txt, tools/probes/write_stream_probe.cu: a

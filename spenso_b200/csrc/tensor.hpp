@@ -23,6 +23,8 @@ struct PairJit {
   std::shared_ptr<JitKernel> k;
   int block = 0;      // threads per CTA
   bool slab = false;  // staged: one warp per slab of 32 points (else one thread per point)
+  uint32_t rows = 1;  // row-parallel kernels: threads per point (no grid-stride loop)
+  uint32_t points_per_cta = 0;  // row-parallel kernels: whole points per CTA (the grid is ceil(n_points / this))
 };
 }
 

@@ -406,7 +406,27 @@ def test_sparse_operand_kernel_source_inspection():
         assert src.count("__dsub_rn(r") == 2 * 12           # the three spatial directions subtract (Minkowski metric)
     src = sp.contract_cuda_source([b(1), b(2), m(3)], [m(3)], sparse_entries=ent, layout_b=sp.COMPONENT_MAJOR)
     assert src and "warp-owned slabs" not in src and "csB + p" in src
-    # a result too large for registers takes the generic kernels
-    assert sp.contract_cuda_source([b(1), b(2), m(3)], [b(4), b(5), m(6), m(7)], sparse_entries=ent) == ""
+    # an exterior product with a 256-component partner is row-parallel; 32 768 rows are left to the generic kernels
+    assert "thread = (point, row of" in sp.contract_cuda_source([b(1), b(2), m(3)], [b(4), b(5), m(6), m(7)], sparse_entries=ent)
+    c = lambda a: sp.ColorAdjoint.new_slot(8, a)
+    assert sp.contract_cuda_source([b(1), b(2), m(3)], [c(4), c(5), c(6), c(7), c(8)], sparse_entries=ent) == ""
     # two batched tensors: the inspection entry point of the dense kernels
     assert "warp-owned slabs" in sp.contract_cuda_source([b(1), b(2)], [b(2), b(3)])
+
+
+def test_row_parallel_kernel_source_inspection():
+    """Per-point tensors beyond one thread's registers (colour algebra) get the row-parallel specialised kernel: thread =
+    (point, row of one batched operand), a batched partner staged in shared memory, a sparse partner as literals.
+    Host-only: source generation + NVRTC."""
+    c = lambda a: sp.ColorAdjoint.new_slot(8, a)
+    b = lambda a: sp.Bispinor.new_slot(4, a)
+    src = sp.contract_cuda_source([c(1), c(2), c(3)], [c(3), c(4)])
+    assert "thread = (point, row of A)" in src and "64 rows x 8 columns x 8 contracted" in src
+    assert "__shared__" in src and src.count("cmul_rn(") == 64 + 1 and src.count("ld32(X") == 4 and src.count("st32(O") == 4
+    src = sp.contract_cuda_source([c(3), c(4)], [c(1), c(2), c(3)])
+    assert "thread = (point, row of B)" in src                   # the rows come from the operand with more free components
+    ent = {(1, 2, 3): 1.0, (2, 1, 3): -1.0, (4, 5, 6): 0.5j}
+    src = sp.contract_cuda_source([c(2), c(3), c(4)], [c(1), c(2), c(3)], sparse_entries=ent, sparse_first=False)
+    assert "thread = (point, row of A)" in src and src.count("cmul_rn(") == 3 + 1 and "__shared__" not in src
+    # small tensors keep the thread = point kernel
+    assert "thread = (point" not in sp.contract_cuda_source([b(1), b(2)], [b(2), b(3)])

@@ -1466,3 +1466,81 @@ def test_sparse_times_small_batched_kernels_bit_for_bit(ctx, seed):
                     od = [O.OTensor.dense(cd, data[p], canonicalize=False) for p in pts]
                     want = np.stack([(oa.contract(x) if sparse_first else x.contract(oa)).to_dense() for x in od])
                     assert np.array_equal(results["flat"].reshape(n_points, -1)[::997], want.reshape(len(want), -1))
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_row_parallel_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
+    """Per-point tensors too large for one thread's registers (colour algebra: dense[coad^3] x dense[coad^2], x sparse f)
+    take the row-parallel specialised kernel: thread = (point, row of one batched operand).  Same sums as the reference
+    (k order, from zero, no FMA), so bit-for-bit the generic / CSR kernels (SPN_PAIR_NO_ROWS=1) — rows taken from either
+    operand, f64 and c64, Minkowski signs over two contracted indices, interleaved result order, a shared dense or a
+    shared sparse partner — and the oracle."""
+    import os
+
+    rng = np.random.default_rng(7100 + seed)
+    c = lambda a: sp.ColorAdjoint.new_slot(8, a)
+    m = lambda a: sp.Minkowski.new_slot(4, a)
+    b = lambda a: sp.Bispinor.new_slot(4, a)
+    n_points = 2300
+
+    def batch(sl, dt):
+        canon = O.order_structure(sp.slots(sl))[0]
+        shape = [n_points] + [int(d) for d in canon["dim"]]
+        data = rng.uniform(-1, 1, size=shape) if dt == sp.F64 else _cases.random_complex(rng, shape)
+        t = sp.BatchTensor.empty(ctx, canon, n_points, dt)
+        t.upload(np.ascontiguousarray(data).reshape(n_points, -1))
+        return t, canon, data
+
+    def sparse(sl, fill):
+        dims = [s.dim for s in sl]
+        ent = {}
+        for idx in np.ndindex(*dims):
+            if rng.random() < fill:
+                ent[tuple(int(i) for i in idx)] = complex(rng.uniform(-1, 1), rng.uniform(-1, 1))
+        return sp.SparseTensor.from_entries(ctx, sl, ent), ent
+
+    def shared_dense(sl):
+        dims = [s.dim for s in sl]
+        data = _cases.random_complex(rng, dims)
+        return sp.DenseTensor.from_data(ctx, sl, data), data
+
+    cases = []   # (a, b, oracle pair or None, expects the row-parallel source)
+    A, ca, da = batch([c(1), c(2), c(3)], sp.C64)
+    B, cb, db = batch([c(3), c(4)], sp.C64)
+    cases.append((A, B, (ca, da, cb, db), sp.contract_cuda_source(ca, cb)))
+    cases.append((B, A, (cb, db, ca, da), sp.contract_cuda_source(cb, ca)))
+    Ar, car, _ = batch([c(1), c(2), c(3)], sp.F64)
+    cases.append((Ar, B, None, sp.contract_cuda_source(car, cb, dtype_a=sp.F64)))
+    Br, cbr, _ = batch([c(3), c(4)], sp.F64)
+    cases.append((Ar, Br, None, sp.contract_cuda_source(car, cbr, dtype_a=sp.F64, dtype_b=sp.F64)))
+    F, fent = sparse([c(2), c(3), c(4)], 0.1)
+    cases.append((A, F, None, sp.contract_cuda_source([c(2), c(3), c(4)], ca, sparse_entries=fent, sparse_first=False)))
+    cases.append((F, A, None, sp.contract_cuda_source([c(2), c(3), c(4)], ca, sparse_entries=fent, sparse_first=True)))
+    M1, cm1, _ = batch([m(1), m(2), m(3), b(4), b(6)], sp.C64)
+    M2, cm2, _ = batch([m(2), m(3), b(5)], sp.C64)
+    cases.append((M1, M2, None, sp.contract_cuda_source(cm1, cm2)))
+    I1, ci1, _ = batch([c(1), c(3), c(5)], sp.C64)
+    I2, ci2, _ = batch([c(2), c(3), c(4)], sp.C64)
+    cases.append((I1, I2, None, sp.contract_cuda_source(ci1, ci2)))
+    S, _ = shared_dense([c(3), c(4)])
+    cases.append((A, S, None, None))
+    cases.append((S, A, None, None))
+    for it, (ta, tb, orc, src) in enumerate(cases):
+        if src is not None:
+            assert "thread = (point, row of" in src, f"case {it} does not take the row-parallel kernel"
+        results = {}
+        for name, env in (("rows", {}), ("generic", {"SPN_PAIR_NO_ROWS": "1"})):
+            os.environ.pop("SPN_PAIR_NO_ROWS", None)
+            os.environ.update(env)
+            try:
+                results[name] = ta.contract(tb).to_numpy()
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        assert np.array_equal(results["rows"], results["generic"]), f"case {it}: row-parallel kernel differs from the generic one"
+        if orc is not None:
+            (c1, d1, c2, d2) = orc
+            pts = range(0, n_points, 571)
+            want = np.stack([O.OTensor.dense(c1, d1[p], canonicalize=False).contract(O.OTensor.dense(c2, d2[p], canonicalize=False)).to_dense()
+                             for p in pts])
+            assert np.array_equal(results["rows"].reshape(n_points, -1)[::571], want.reshape(len(want), -1))

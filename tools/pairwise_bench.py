@@ -93,10 +93,10 @@ co = lambda a: sp.ColorAdjoint.new_slot(8, a)
 n_keep0, n = n, min(n, 1 << 18)
 D3, sd3 = rand_batch([co(1), co(2), co(3)])
 D2, sd2 = rand_batch([co(3), co(4)])
-cases.append(("dense[coad^3] x dense[coad^2] -> [coad^3]  (generic dense)", lambda: D3.contract(D2), (sd3 + sd2 + 512) * 16))
+cases.append(("dense[coad^3] x dense[coad^2] -> [coad^3]  (row-parallel)", lambda: D3.contract(D2), (sd3 + sd2 + 512) * 16))
 from spenso_b200 import workloads  # noqa: E402
 F = sp.SparseTensor.from_entries(ctx, [co(1), co(2), co(4)], workloads.su3_f())
-cases.append(("dense[coad^3] x sparse f (shared) -> [coad^2]  (CSR gather)", lambda: D3.contract(F), (sd3 + 64) * 16))
+cases.append(("dense[coad^3] x sparse f (shared) -> [coad^2]  (row-parallel)", lambda: D3.contract(F), (sd3 + 64) * 16))
 for name, fn, bytes_pp in cases:
     ms, r = timeit(fn)
     print(f"{name:62s} {ms*1e3:8.1f} us  {bytes_pp*n/ms/1e6:7.0f} GB/s  ({bytes_pp} B/point)", flush=True)

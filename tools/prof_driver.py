@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Launch ONE of the engine's kernels a few times — the command `ncu` wraps (tools/profile_r02.sh).
-usage: prof_driver.py cfg2|cfg5|cfg5r|cfg3p|cfg3c|pair1|pair3|zgemm|dgemm|mixed|exchange [n_points]"""
+usage: prof_driver.py cfg2|cfg5|cfg5r|cfg3p|cfg3c|pair1|pair3|rows|zgemm|dgemm|mixed|exchange [n_points]"""
 import os
 import sys
 
@@ -65,6 +65,13 @@ elif what in ("pair1", "pair3"):
         ent = {(0, 2, 0): 1, (1, 3, 0): 1, (2, 0, 0): 1, (3, 1, 0): 1, (0, 3, 1): 1, (1, 2, 1): 1, (2, 1, 1): -1, (3, 0, 1): -1,
                (0, 3, 2): -1j, (1, 2, 2): 1j, (2, 1, 2): 1j, (3, 0, 2): -1j, (0, 2, 3): 1, (1, 3, 3): -1, (2, 0, 3): -1, (3, 1, 3): 1}
         A, B = sp.SparseTensor.from_entries(ctx, [b(1), b(2), m(3)], ent), rand_batch([m(3)], n)
+    for _ in range(ITERS):
+        r = A.contract(B)
+    torch.cuda.synchronize()
+elif what == "rows":
+    n = n or 1 << 18
+    c = lambda a: sp.ColorAdjoint.new_slot(8, a)
+    A, B = rand_batch([c(1), c(2), c(3)], n), rand_batch([c(3), c(4)], n)
     for _ in range(ITERS):
         r = A.contract(B)
     torch.cuda.synchronize()
