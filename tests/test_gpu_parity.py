@@ -1544,3 +1544,63 @@ def test_row_parallel_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
             want = np.stack([O.OTensor.dense(c1, d1[p], canonicalize=False).contract(O.OTensor.dense(c2, d2[p], canonicalize=False)).to_dense()
                              for p in pts])
             assert np.array_equal(results["rows"].reshape(n_points, -1)[::571], want.reshape(len(want), -1))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_specialised_kernels_on_random_medium_pairs_bit_for_bit(ctx, seed):
+    """Random pairs of up to 6 indices per tensor (up to 4 096 components per point): whichever specialised form the
+    dispatcher picks — registers, warp slabs, row-parallel — gives the bits of the generic kernels (SPN_NO_PAIR_JIT)."""
+    import os
+
+    rng = np.random.default_rng(8800 + seed)
+    n_points, done, rows_seen = 2111, 0, 0
+    for it in range(40):
+        a, b = _cases.random_pair(rng, max_free=4, max_common=2)
+        ca = O.order_structure(a)[0] if len(a) else a
+        cb = O.order_structure(b)[0] if len(b) else b
+        size_a = int(np.prod([int(d) for d in ca["dim"]])) if len(ca) else 1
+        size_b = int(np.prod([int(d) for d in cb["dim"]])) if len(cb) else 1
+        if size_a * size_b > 1 << 16 or max(size_a, size_b) < 48:
+            continue
+        dta = sp.F64 if it % 4 == 1 else sp.C64
+        dtb = sp.F64 if it % 4 in (1, 3) else sp.C64
+
+        def mk(c, dt):
+            shape = [n_points] + [int(d) for d in c["dim"]]
+            data = rng.uniform(-1, 1, size=shape) if dt == sp.F64 else _cases.random_complex(rng, shape)
+            t = sp.BatchTensor.empty(ctx, c, n_points, dt)
+            t.upload(np.ascontiguousarray(data).reshape(n_points, -1))
+            return t
+
+        ta = mk(ca, dta)
+        ent = None
+        if it % 5 == 4 and len(cb):
+            ent = _cases.random_sparse_entries(rng, [int(d) for d in cb["dim"]], density=0.1)
+            tb = sp.SparseTensor.from_entries(ctx, cb, ent)
+        else:
+            tb = mk(cb, dtb)
+        try:
+            src = (sp.contract_cuda_source(cb, ca, sparse_entries=ent, dtype_b=dta, sparse_first=False) if ent is not None
+                   else sp.contract_cuda_source(ca, cb, dtype_a=dta, dtype_b=dtb))
+        except sp.SpensoError:
+            continue
+        rows_seen += "thread = (point, row of" in src
+        results = {}
+        for name, env in (("generic", {"SPN_NO_PAIR_JIT": "1"}), ("specialised", {})):
+            os.environ.pop("SPN_NO_PAIR_JIT", None)
+            os.environ.update(env)
+            try:
+                results[name] = ta.contract(tb).to_numpy()
+            except sp.SpensoError:
+                results = None
+                break
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        if results is None:
+            continue
+        assert np.array_equal(results["specialised"], results["generic"]), f"case {it} differs from the generic kernel"
+        done += 1
+        if done >= 10:
+            break
+    assert done >= 5 and rows_seen >= 2
