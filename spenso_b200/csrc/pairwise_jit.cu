@@ -733,7 +733,9 @@ void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const
   // all others — costs 10-22 % on these streams (profiles/r02_pairwise_grid.txt, tools/probes/write_stream_probe.cu: a
   // plain fill drops from 6.87 to 5.93 TB/s when it is made persistent).  SPN_PAIR_PERSISTENT=1 restores it for A/B runs.
   const uint64_t cap = getenv("SPN_PAIR_PERSISTENT") ? (uint64_t)ctx->sm_count * (uint64_t)k.blocks_per_sm : 0x7fffffffull;
-  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, cap));
+  if (pj.points_per_cta && need > 0x7fffffffull)   // the row-parallel kernels have no grid-stride loop
+    throw Error(SPN_ERR_INVALID, "batch too large for one launch of the row-parallel kernel");
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, pj.points_per_cta ? 0x7fffffffull : cap));
   const double* pa = static_cast<const double*>(a->dptr);
   const double* pb = static_cast<const double*>(b->dptr);
   double* pc = static_cast<double*>(res->dptr);
