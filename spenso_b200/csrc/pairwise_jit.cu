@@ -114,9 +114,11 @@ struct Generated {
 // the rows ran into each other's misses — L1 hit rate 38 %, FP64 pipe 41 % busy — 1.12 ms against 0.86 ms staged); a
 // shared dense one is read through L1 at literal offsets; a shared sparse one is its stored entries as literals, and
 // only the components of X that meet one are loaded.  The sums are the reference's (k order, from zero, "-=" on a
-// negative metric, no FMA): bit-for-bit the generic kernels.  Measured at 2^18 points (profiles/r02_pairwise_rows.txt):
-// 4.01 ms -> 0.86 ms (5.3 TB/s) for the product above, 0.85 -> 0.29 ms for dense[coad^3] x sparse f.  A prefetch of the
-// rows 256-8192 points ahead into L2 was tried and dropped (+3 % before Y was staged, -7 % after).
+// negative metric, no FMA): bit-for-bit the generic kernels.  A thread takes two neighbouring rows (register tiling: one
+// read of Y's component, two products; 856 -> 820 us, four rows: 928).  Measured at 2^18 points
+// (profiles/r02_pairwise_rows.txt): 4.01 ms -> 0.82 ms (5.6 TB/s) for the product above, 0.85 -> 0.29 ms for
+// dense[coad^3] x sparse f.  A prefetch of the rows 256-8192 points ahead into L2 was tried and dropped (+3 % before Y
+// was staged, -7 % after).
 struct RowSplit {
   bool ok = false;
   bool rows_from_a = true;
@@ -182,10 +184,16 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   const std::vector<long long>& ky = rs.rows_from_a ? kt.off_b : kt.off_a;
   const bool xc = X->dtype == SPN_C64, yc = Y->dtype == SPN_C64, oc = res->dtype == SPN_C64;
   Generated gen;
-  // a CTA covers whole points: P of them if the rows of P points fill 64 threads, else one (threads rounded up to a warp)
-  const uint32_t P = rs.n_rows >= 64 ? 1u : 64u / rs.n_rows;
-  gen.block = (int)(((uint64_t)P * rs.n_rows + 31) / 32 * 32);
-  gen.rows = rs.n_rows;
+  // register tiling: a thread takes R neighbouring rows, so every component of Y it reads serves R products
+  // (SPN_PAIR_ROWS_PER_THREAD=1|2|4 for A/B runs)
+  uint32_t R = getenv("SPN_PAIR_ROWS_PER_THREAD") ? (uint32_t)atoi(getenv("SPN_PAIR_ROWS_PER_THREAD")) : 2u;
+  while (R > 1 && (rs.n_rows % R != 0 || rs.n_rows / R < 2 || (uint64_t)R * kx.size() > 48 || (uint64_t)R * rs.n_cols * kx.size() > 1536)) R /= 2;
+  if (R == 0) R = 1;
+  const uint32_t T = rs.n_rows / R;   // threads per point
+  // a CTA covers whole points: P of them if their threads fill 64, else one (threads rounded up to a warp)
+  const uint32_t P = T >= 64 ? 1u : 64u / T;
+  gen.block = (int)(((uint64_t)P * T + 31) / 32 * 32);
+  gen.rows = T;
   gen.points_per_cta = P;
   // a batched Y is staged once per CTA in shared memory: every row-thread of a point reads all of it (a broadcast), and
   // through L1 those reads met each other's misses (ncu: L1 hit rate 38 %, long_scoreboard 9 cycles per issue, FP64 pipe 41 %)
@@ -195,8 +203,8 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   if (y_smem) gen.smem_bytes = (size_t)(P * y_row * 16);
   std::ostringstream o;
   o << "// generated by spenso_b200 (pairwise_jit.cu): one pairwise contraction, thread = (point, row of " << xn << "), reference rounding\n";
-  o << "// " << rs.n_rows << " rows x " << rs.n_cols << " columns x " << kx.size() << " contracted components per point, " << P
-    << " point(s) per CTA\n";
+  o << "// " << rs.n_rows << " rows x " << rs.n_cols << " columns x " << kx.size() << " contracted components per point, " << R
+    << " row(s) per thread, " << P << " point(s) per CTA\n";
   o << "typedef unsigned long long ull;\n";
   o << "__device__ __forceinline__ double2 cmul_rn(double2 a, double2 b) {\n"
        "  return make_double2(__dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x)));\n}\n";
@@ -214,10 +222,11 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
     << "(const double* __restrict__ A, ull csA, const double* __restrict__ B, ull csB, double* __restrict__ C, ull csC, ull n_points) {\n";
   o << "  const ull p0 = (ull)blockIdx.x * " << P << "ull;   // first point of this CTA\n";
   o << "  const unsigned np = (unsigned)(n_points - p0 < " << P << "ull ? n_points - p0 : " << P << "ull);\n";
-  o << "  const unsigned pl = threadIdx.x / " << rs.n_rows << "u, i = threadIdx.x % " << rs.n_rows << "u;\n";
+  o << "  const unsigned pl = threadIdx.x / " << T << "u, i = (threadIdx.x % " << T << "u) * " << R << "u;   // first of this thread's rows\n";
   o << "  const bool live = pl < np;   // a thread of the last CTA's padding, or of the warp round-up, only helps staging\n";
   o << "  const ull p = p0 + (live ? pl : 0u);\n";
-  o << "  const double* const X = " << xn << " + (p * " << X->size() << "ull + kRowX[i]) * " << (xc ? 2 : 1) << "ull;\n";
+  for (uint32_t r = 0; r < R; ++r)
+    o << "  const double* const X" << r << " = " << xn << " + (p * " << X->size() << "ull + kRowX[i + " << r << "u]) * " << (xc ? 2 : 1) << "ull;\n";
   std::ostringstream stage;
   if (y_smem) {
     stage << "  extern __shared__ __align__(16) double2 ys[];   // [point][" << y_row << " units]\n";
@@ -237,7 +246,8 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
     else if (!Y->sparse())
       stage << "  const double* const Y = " << yn << ";\n";
   }
-  o << "  double* const O = C + (p * " << plan.size_out << "ull + kRowC[i]) * " << (oc ? 2 : 1) << "ull;\n";
+  for (uint32_t r = 0; r < R; ++r)
+    o << "  double* const O" << r << " = C + (p * " << plan.size_out << "ull + kRowC[i + " << r << "u]) * " << (oc ? 2 : 1) << "ull;\n";
   // which (j, k) products exist (a sparse Y contributes its stored entries only), and which components of the row they use
   auto y_entry = [&](uint32_t j, size_t k) -> const double2* {
     if (!Y->sparse()) return nullptr;
@@ -254,35 +264,38 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   std::map<long long, size_t> k_of_off;
   for (size_t k = 0; k < kx.size(); ++k)
     if (k_used[k]) k_of_off[kx[k]] = k;
-  std::vector<char> loaded(kx.size(), 0);
-  for (size_t k = 0; k < kx.size(); ++k) {
-    if (!k_used[k] || loaded[k]) continue;
-    const long long off = kx[k];
-    auto mate = k_of_off.find(off ^ 1ll);
-    if (even_rows && mate != k_of_off.end() && !loaded[mate->second] && mate->second != k) {
-      const size_t lo = (off & 1ll) ? mate->second : k, hi = (off & 1ll) ? k : mate->second;
-      o << "  double2 x" << lo << ", x" << hi << "; ld32(X + " << (off & ~1ll) * 2 << "ull, x" << lo << ", x" << hi << ");\n";
-      loaded[lo] = loaded[hi] = 1;
-    } else {
-      if (xc)
-        o << "  const double2 x" << k << " = __ldg(reinterpret_cast<const double2*>(X + " << off * 2 << "ull));\n";
-      else
-        o << "  const double2 x" << k << " = make_double2(__ldg(X + " << off << "ull), 0.0);\n";
-      loaded[k] = 1;
+  for (uint32_t r = 0; r < R; ++r) {
+    std::vector<char> loaded(kx.size(), 0);
+    const std::string xr = "x" + std::to_string(r) + "_", Xr = "X" + std::to_string(r);
+    for (size_t k = 0; k < kx.size(); ++k) {
+      if (!k_used[k] || loaded[k]) continue;
+      const long long off = kx[k];
+      auto mate = k_of_off.find(off ^ 1ll);
+      if (even_rows && mate != k_of_off.end() && !loaded[mate->second] && mate->second != k) {
+        const size_t lo = (off & 1ll) ? mate->second : k, hi = (off & 1ll) ? k : mate->second;
+        o << "  double2 " << xr << lo << ", " << xr << hi << "; ld32(" << Xr << " + " << (off & ~1ll) * 2 << "ull, " << xr << lo << ", " << xr << hi << ");\n";
+        loaded[lo] = loaded[hi] = 1;
+      } else {
+        if (xc)
+          o << "  const double2 " << xr << k << " = __ldg(reinterpret_cast<const double2*>(" << Xr << " + " << off * 2 << "ull));\n";
+        else
+          o << "  const double2 " << xr << k << " = make_double2(__ldg(" << Xr << " + " << off << "ull), 0.0);\n";
+        loaded[k] = 1;
+      }
     }
   }
   o << stage.str();   // the row's loads are in flight while the CTA stages Y
   bool even_out = oc && plan.size_out % 2 == 0 && ((uintptr_t)res->dptr % 32) == 0;
   for (uint64_t v : rs.row_c) even_out = even_out && v % 2 == 0;
-  std::string pending;
-  uint64_t pending_c = 0;
-  auto flush = [&]() {
-    if (pending.empty()) return;
-    o << "  *reinterpret_cast<double2*>(O + " << pending_c * 2 << "ull) = " << pending << ";\n";
-    pending.clear();
+  std::vector<std::string> pending(R);
+  std::vector<uint64_t> pending_c(R, 0);
+  auto flush = [&](uint32_t r) {
+    if (pending[r].empty()) return;
+    o << "  *reinterpret_cast<double2*>(O" << r << " + " << pending_c[r] * 2 << "ull) = " << pending[r] << ";\n";
+    pending[r].clear();
   };
   for (uint32_t j = 0; j < rs.n_cols; ++j) {
-    o << "  double2 r" << j << " = make_double2(0.0, 0.0);\n";
+    for (uint32_t r = 0; r < R; ++r) o << "  double2 r" << r << "_" << j << " = make_double2(0.0, 0.0);\n";
     for (size_t k = 0; k < kx.size(); ++k) {
       std::string yv;
       if (Y->sparse()) {
@@ -297,25 +310,32 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
           yv = yc ? "__ldg(reinterpret_cast<const double2*>(Y + " + std::to_string(f * 2) + "ull))"
                   : "make_double2(__ldg(Y + " + std::to_string(f) + "ull), 0.0)";
       }
-      const std::string xv = "x" + std::to_string(k);
-      o << "  { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : yv) << ", " << (rs.rows_from_a ? yv : xv) << "); r" << j << ".x = "
-        << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(r" << j << ".x, t.x); r" << j << ".y = "
-        << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(r" << j << ".y, t.y); }\n";
+      o << "  { const double2 y = " << yv << ";\n";
+      for (uint32_t r = 0; r < R; ++r) {
+        const std::string xv = "x" + std::to_string(r) + "_" + std::to_string(k), acc = "r" + std::to_string(r) + "_" + std::to_string(j);
+        o << "    { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : "y") << ", " << (rs.rows_from_a ? "y" : xv) << "); " << acc << ".x = "
+          << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(" << acc << ".x, t.x); " << acc << ".y = "
+          << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(" << acc << ".y, t.y); }\n";
+      }
+      o << "  }\n";
     }
     const uint64_t c = rs.col_c[j];
-    if (!oc) {
-      o << "  O[" << c << "ull] = r" << j << ".x;\n";
-    } else if (even_out && !pending.empty() && c == pending_c + 1 && pending_c % 2 == 0) {
-      o << "  st32(O + " << pending_c * 2 << "ull, " << pending << ", r" << j << ");\n";
-      pending.clear();
-    } else {
-      flush();
-      pending = "r" + std::to_string(j);
-      pending_c = c;
-      if (!even_out) flush();
+    for (uint32_t r = 0; r < R; ++r) {
+      const std::string acc = "r" + std::to_string(r) + "_" + std::to_string(j);
+      if (!oc) {
+        o << "  O" << r << "[" << c << "ull] = " << acc << ".x;\n";
+      } else if (even_out && !pending[r].empty() && c == pending_c[r] + 1 && pending_c[r] % 2 == 0) {
+        o << "  st32(O" << r << " + " << pending_c[r] * 2 << "ull, " << pending[r] << ", " << acc << ");\n";
+        pending[r].clear();
+      } else {
+        flush(r);
+        pending[r] = acc;
+        pending_c[r] = c;
+        if (!even_out) flush(r);
+      }
     }
   }
-  flush();
+  for (uint32_t r = 0; r < R; ++r) flush(r);
   o << "}\n";
   gen.source = o.str();
   return gen;
@@ -628,6 +648,7 @@ PairJit pair_jit_build(spn_ctx* ctx, const spn_contract_plan& plan, const KTable
   key.push_back(wide ? 'w' : 'n');
   key.push_back(tma_mode() ? 'T' : 'L');
   key.push_back(getenv("SPN_PAIR_NO_ROWS") ? 'g' : (getenv("SPN_PAIR_ROWS_NO_SMEM") ? 'l' : 'r'));
+  if (const char* e = getenv("SPN_PAIR_ROWS_PER_THREAD")) key += e;
   key.append(reinterpret_cast<const char*>(kt.off_a.data()), kt.off_a.size() * sizeof(long long));
   key.append(reinterpret_cast<const char*>(kt.off_b.data()), kt.off_b.size() * sizeof(long long));
   key.append(reinterpret_cast<const char*>(kt.sign.data()), kt.sign.size());

@@ -421,8 +421,10 @@ def test_row_parallel_kernel_source_inspection():
     c = lambda a: sp.ColorAdjoint.new_slot(8, a)
     b = lambda a: sp.Bispinor.new_slot(4, a)
     src = sp.contract_cuda_source([c(1), c(2), c(3)], [c(3), c(4)])
-    assert "thread = (point, row of A)" in src and "64 rows x 8 columns x 8 contracted" in src
-    assert "__shared__" in src and src.count("cmul_rn(") == 64 + 1 and src.count("ld32(X") == 4 and src.count("st32(O") == 4
+    assert "thread = (point, row of A)" in src and "64 rows x 8 columns x 8 contracted" in src and "2 row(s) per thread" in src
+    # two rows per thread: every component of the staged partner serves two products
+    assert "__shared__" in src and src.count("cmul_rn(") == 2 * 64 + 1 and src.count("ld32(X") == 2 * 4 and src.count("st32(O") == 2 * 4
+    assert src.count("const double2 y = ") == 64
     src = sp.contract_cuda_source([c(3), c(4)], [c(1), c(2), c(3)])
     assert "thread = (point, row of B)" in src                   # the rows come from the operand with more free components
     ent = {(1, 2, 3): 1.0, (2, 1, 3): -1.0, (4, 5, 6): 0.5j}
