@@ -40,7 +40,10 @@ def kernels_of(path):
 
 def demangle(name):
     try:
-        return subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip().split("(")[0]
+        full = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
+        full = full.replace("(anonymous namespace)::", "")
+        m = re.match(r"(?:void\s+)?([\w:]+)(<[^(]*>)?\(", full)      # kernel name + template arguments, no parameter list
+        return (m.group(1) + (m.group(2) or "")) if m else full
     except Exception:
         return name
 
