@@ -746,9 +746,15 @@ std::string pair_jit_source_sparse(const Structure& ss, const std::map<uint64_t,
 void pair_jit_launch(spn_ctx* ctx, const PairJit& pj, const spn_tensor* a, const spn_tensor* b, spn_tensor* res,
                      uint64_t n_points) {
   JitKernel& k = *pj.k;
-  // direct kernels: one thread per point; staged kernels: one warp per slab of 32 points
-  const uint64_t need = pj.points_per_cta ? (n_points + pj.points_per_cta - 1) / pj.points_per_cta : pj.slab ? ((n_points + 31) / 32 + (uint64_t)(pj.block / 32) - 1) / (uint64_t)(pj.block / 32)
-                                : (n_points * (uint64_t)pj.rows + (uint64_t)pj.block - 1) / (uint64_t)pj.block;
+  // CTAs that cover the batch — row-parallel kernels: whole points per CTA; staged kernels: one warp per slab of 32
+  // points; direct kernels: one thread per point
+  uint64_t need;
+  if (pj.points_per_cta)
+    need = (n_points + pj.points_per_cta - 1) / pj.points_per_cta;
+  else if (pj.slab)
+    need = ((n_points + 31) / 32 + (uint64_t)(pj.block / 32) - 1) / (uint64_t)(pj.block / 32);
+  else
+    need = (n_points + (uint64_t)pj.block - 1) / (uint64_t)pj.block;
   // Hardware-scheduled grid: one slab per warp (one point per thread), as many CTAs as that takes.  The kernels keep
   // their grid-stride loop, but a persistent launch — SMs x resident CTAs, every warp walking its slabs in lockstep with
   // all others — costs 10-22 % on these streams (profiles/r02_pairwise_grid.txt, tools/probes/write_stream_probe.cu: a
