@@ -1604,3 +1604,32 @@ def test_specialised_kernels_on_random_medium_pairs_bit_for_bit(ctx, seed):
         if done >= 10:
             break
     assert done >= 5 and rows_seen >= 2
+
+
+@pytest.mark.parametrize("name,n_points", [("cfg2", 300_001), ("cfg3", 20_011)])
+def test_fused_flat_and_persistent_launches_agree(ctx, monkeypatch, name, n_points):
+    """Streaming fused kernels that store a result per point are launched flat (64-thread CTAs, one point per thread);
+    SPN_NET_PERSISTENT=1 keeps the persistent wave of 256-thread CTAs.  Same arithmetic per point: identical bits, also
+    on a point range that starts inside the batch and ends on a ragged CTA."""
+    spec = workloads.WORKLOADS[name]()
+    arrays = workloads.synthetic_inputs(spec, n_points, 4242)
+
+    def run():
+        net = workloads.build_engine(spec, ctx, sp.FUSED)
+        inputs = []
+        for node, a, dt in zip([x for x in spec.nodes if x[0] == "batched"], arrays, spec.input_dtypes):
+            t = sp.BatchTensor.empty(ctx, node[1], n_points, dt)
+            t.upload(a)
+            inputs.append(t)
+        out = sp.BatchTensor.empty(ctx, net.result_slots, n_points)
+        out.upload(np.zeros((n_points, net.result_size), dtype=complex))
+        net.execute(inputs, out, first_point=37, n_points=n_points - 100)
+        ctx.synchronize()
+        return out.to_numpy().reshape(n_points, -1), net.prepare_variant("p" * net.n_inputs + "p")
+
+    flat, src_flat = run()
+    monkeypatch.setenv("SPN_NET_PERSISTENT", "1")
+    pers, src_pers = run()
+    assert "__launch_bounds__(64" in src_flat and "__launch_bounds__(256" in src_pers
+    assert np.array_equal(flat.view(np.float64), pers.view(np.float64))
+    assert not flat[:37].any() and not flat[n_points - 63:].any() and flat[37:n_points - 63].any()
