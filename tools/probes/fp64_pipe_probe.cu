@@ -5,12 +5,16 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 
-template <int ILP, int MIX>   // MIX 0: DFMA only; 1: DMUL + DADD alternating; 2: DFMA with one integer op between
+template <int ILP, int MIX>   // MIX 0: DFMA only; 1: DMUL + DADD alternating; 2: DFMA with one integer op between;
+                              // 3: DFMA whose three operands are three different live registers (the shape of real code)
 __global__ void __launch_bounds__(256) k(double* out, double a, double b, int iters) {
   double x[ILP];
 #pragma unroll
   for (int i = 0; i < ILP; ++i) x[i] = threadIdx.x * 1e-3 + i;
   unsigned n = threadIdx.x;
+  double y[ILP], z[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) { y[i] = 1.0 + a * (i + 1) * 1e-9 + threadIdx.x * 1e-12; z[i] = b * (i + 1); }
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
@@ -19,12 +23,16 @@ __global__ void __launch_bounds__(256) k(double* out, double a, double b, int it
         if (MIX == 0) x[i] = fma(x[i], a, b);
         if (MIX == 1) x[i] = (r & 1) ? __dmul_rn(x[i], a) : __dadd_rn(x[i], b);
         if (MIX == 2) { x[i] = fma(x[i], a, b); n = n * 1664525u + 1013904223u; }
+        if (MIX == 3) x[i] = fma(x[i], y[(i + r) % ILP], z[(i + 2 * r + 1) % ILP]);
       }
     }
   }
   double s = 0;
 #pragma unroll
   for (int i = 0; i < ILP; ++i) s += x[i];
+  if (MIX == 3)
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += y[i] + z[i];
   if (s == 12345.678 || n == 7u) out[0] = s;   // keep the chains alive
 }
 
@@ -61,6 +69,8 @@ int main() {
     run<16, 0>("DFMA", w, 256, sms, clk);
     run<8, 1>("DMUL/DADD", w, 256, sms, clk);
     run<8, 2>("DFMA + IMAD", w, 256, sms, clk);
+    run<8, 3>("DFMA 3 live operands", w, 256, sms, clk);
+    run<16, 3>("DFMA 3 live operands", w, 256, sms, clk);
   }
   return 0;
 }
