@@ -134,6 +134,14 @@ bool register_form_fits(const spn_contract_plan& plan, const KTables& kt, const 
   return !(loaded > 80 || plan.size_out > 256 || products > 4096 || products == 0);
 }
 
+// register tiling: a thread takes R neighbouring rows, so every component of Y it reads serves R products
+// (SPN_PAIR_ROWS_PER_THREAD=1|2|4 for A/B runs)
+uint32_t rows_per_thread(uint64_t n_rows, uint64_t n_cols, uint64_t n_k) {
+  uint32_t R = getenv("SPN_PAIR_ROWS_PER_THREAD") ? (uint32_t)atoi(getenv("SPN_PAIR_ROWS_PER_THREAD")) : 2u;
+  while (R > 1 && (n_rows % R != 0 || n_rows / R < 2 || (uint64_t)R * n_k > 48 || (uint64_t)R * n_cols * n_k > 1536)) R /= 2;
+  return R == 0 ? 1u : R;
+}
+
 RowSplit row_split(const spn_contract_plan& plan, const KTables& kt, const spn_tensor* a, const spn_tensor* b) {
   RowSplit rs;
   if (getenv("SPN_PAIR_NO_ROWS")) return rs;
@@ -146,7 +154,8 @@ RowSplit row_split(const spn_contract_plan& plan, const KTables& kt, const spn_t
   rs.rows_from_a = a_x && (!b_x || free_a >= free_b);
   const uint64_t n_rows = rs.rows_from_a ? free_a : free_b, n_cols = rs.rows_from_a ? free_b : free_a;
   const uint64_t n_k = kt.off_a.size();
-  if (n_rows < 2 || n_rows > 4096 || n_cols > 256 || n_k == 0 || n_k > 64 || n_cols * n_k > 1024) return rs;
+  if (n_rows < 2 || n_cols > 256 || n_k == 0 || n_k > 64 || n_cols * n_k > 1024) return rs;
+  if (n_rows / rows_per_thread(n_rows, n_cols, n_k) > 256) return rs;   // a point's threads fit one CTA of <= 256 threads
   if (plan.size_a > (1u << 20) || plan.size_b > (1u << 20) || plan.size_out > (1u << 20)) return rs;
   rs.n_rows = (uint32_t)n_rows;
   rs.n_cols = (uint32_t)n_cols;
@@ -184,11 +193,7 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   const std::vector<long long>& ky = rs.rows_from_a ? kt.off_b : kt.off_a;
   const bool xc = X->dtype == SPN_C64, yc = Y->dtype == SPN_C64, oc = res->dtype == SPN_C64;
   Generated gen;
-  // register tiling: a thread takes R neighbouring rows, so every component of Y it reads serves R products
-  // (SPN_PAIR_ROWS_PER_THREAD=1|2|4 for A/B runs)
-  uint32_t R = getenv("SPN_PAIR_ROWS_PER_THREAD") ? (uint32_t)atoi(getenv("SPN_PAIR_ROWS_PER_THREAD")) : 2u;
-  while (R > 1 && (rs.n_rows % R != 0 || rs.n_rows / R < 2 || (uint64_t)R * kx.size() > 48 || (uint64_t)R * rs.n_cols * kx.size() > 1536)) R /= 2;
-  if (R == 0) R = 1;
+  const uint32_t R = rows_per_thread(rs.n_rows, rs.n_cols, kx.size());
   const uint32_t T = rs.n_rows / R;   // threads per point
   // a CTA covers whole points: P of them if their threads fill 64, else one (threads rounded up to a warp)
   const uint32_t P = T >= 64 ? 1u : 64u / T;

@@ -1522,6 +1522,8 @@ def test_row_parallel_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
     I1, ci1, _ = batch([c(1), c(3), c(5)], sp.C64)
     I2, ci2, _ = batch([c(2), c(3), c(4)], sp.C64)
     cases.append((I1, I2, None, sp.contract_cuda_source(ci1, ci2)))
+    A4, ca4, _ = batch([c(1), c(2), c(3), c(5)], sp.C64)          # 512 rows: one point per 256-thread CTA
+    cases.append((A4, B, None, sp.contract_cuda_source(ca4, cb)))
     S, _ = shared_dense([c(3), c(4)])
     cases.append((A, S, None, None))
     cases.append((S, A, None, None))
