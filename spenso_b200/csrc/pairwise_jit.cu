@@ -155,7 +155,7 @@ RowSplit row_split(const spn_contract_plan& plan, const KTables& kt, const spn_t
   const uint64_t n_rows = rs.rows_from_a ? free_a : free_b, n_cols = rs.rows_from_a ? free_b : free_a;
   const uint64_t n_k = kt.off_a.size();
   if (n_rows < 2 || n_cols > 256 || n_k == 0 || n_k > 64 || n_cols * n_k > 1024) return rs;
-  if (n_rows / rows_per_thread(n_rows, n_cols, n_k) > 256) return rs;   // a point's threads fit one CTA of <= 256 threads
+  if (n_rows > (1u << 16)) return rs;   // per-row offset tables
   if (plan.size_a > (1u << 20) || plan.size_b > (1u << 20) || plan.size_out > (1u << 20)) return rs;
   rs.n_rows = (uint32_t)n_rows;
   rs.n_cols = (uint32_t)n_cols;
@@ -194,7 +194,9 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   const bool xc = X->dtype == SPN_C64, yc = Y->dtype == SPN_C64, oc = res->dtype == SPN_C64;
   Generated gen;
   const uint32_t R = rows_per_thread(rs.n_rows, rs.n_cols, kx.size());
-  const uint32_t T = rs.n_rows / R;   // threads per point
+  // threads per point: one per R rows, at most 256 — a point with more rows is walked in passes of 256 R rows
+  const uint32_t T = std::min<uint32_t>(rs.n_rows / R, 256u);
+  const bool passes = (uint64_t)T * R < rs.n_rows;
   // a CTA covers whole points: P of them if their threads fill 64, else one (threads rounded up to a warp)
   const uint32_t P = T >= 64 ? 1u : 64u / T;
   gen.block = (int)(((uint64_t)P * T + 31) / 32 * 32);
@@ -227,11 +229,13 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
     << "(const double* __restrict__ A, ull csA, const double* __restrict__ B, ull csB, double* __restrict__ C, ull csC, ull n_points) {\n";
   o << "  const ull p0 = (ull)blockIdx.x * " << P << "ull;   // first point of this CTA\n";
   o << "  const unsigned np = (unsigned)(n_points - p0 < " << P << "ull ? n_points - p0 : " << P << "ull);\n";
-  o << "  const unsigned pl = threadIdx.x / " << T << "u, i = (threadIdx.x % " << T << "u) * " << R << "u;   // first of this thread's rows\n";
+  o << "  const unsigned pl = threadIdx.x / " << T << "u, " << (passes ? "i0" : "i") << " = (threadIdx.x % " << T << "u) * " << R
+    << "u;   // first of this thread's rows\n";
   o << "  const bool live = pl < np;   // a thread of the last CTA's padding, or of the warp round-up, only helps staging\n";
   o << "  const ull p = p0 + (live ? pl : 0u);\n";
+  std::ostringstream body;   // everything that depends on the row: emitted once, or inside the loop over passes
   for (uint32_t r = 0; r < R; ++r)
-    o << "  const double* const X" << r << " = " << xn << " + (p * " << X->size() << "ull + kRowX[i + " << r << "u]) * " << (xc ? 2 : 1) << "ull;\n";
+    body << "  const double* const X" << r << " = " << xn << " + (p * " << X->size() << "ull + kRowX[i + " << r << "u]) * " << (xc ? 2 : 1) << "ull;\n";
   std::ostringstream stage;
   if (y_smem) {
     stage << "  extern __shared__ __align__(16) double2 ys[];   // [point][" << y_row << " units]\n";
@@ -252,7 +256,7 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
       stage << "  const double* const Y = " << yn << ";\n";
   }
   for (uint32_t r = 0; r < R; ++r)
-    o << "  double* const O" << r << " = C + (p * " << plan.size_out << "ull + kRowC[i + " << r << "u]) * " << (oc ? 2 : 1) << "ull;\n";
+    body << "  double* const O" << r << " = C + (p * " << plan.size_out << "ull + kRowC[i + " << r << "u]) * " << (oc ? 2 : 1) << "ull;\n";
   // which (j, k) products exist (a sparse Y contributes its stored entries only), and which components of the row they use
   auto y_entry = [&](uint32_t j, size_t k) -> const double2* {
     if (!Y->sparse()) return nullptr;
@@ -263,6 +267,8 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   for (uint32_t j = 0; j < rs.n_cols; ++j)
     for (size_t k = 0; k < kx.size(); ++k)
       if (!Y->sparse() || y_entry(j, k)) k_used[k] = 1;
+  std::ostringstream loads, compute;
+  std::ostringstream* out = &loads;
   // the row of X: 256-bit loads where two used neighbours share a 32-byte sector (every row base and the record even)
   bool even_rows = xc && X->size() % 2 == 0 && ((uintptr_t)X->dptr % 32) == 0 && jit_has_256bit_loads();
   for (uint64_t v : rs.row_x) even_rows = even_rows && v % 2 == 0;
@@ -278,29 +284,29 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
       auto mate = k_of_off.find(off ^ 1ll);
       if (even_rows && mate != k_of_off.end() && !loaded[mate->second] && mate->second != k) {
         const size_t lo = (off & 1ll) ? mate->second : k, hi = (off & 1ll) ? k : mate->second;
-        o << "  double2 " << xr << lo << ", " << xr << hi << "; ld32(" << Xr << " + " << (off & ~1ll) * 2 << "ull, " << xr << lo << ", " << xr << hi << ");\n";
+        (*out) << "  double2 " << xr << lo << ", " << xr << hi << "; ld32(" << Xr << " + " << (off & ~1ll) * 2 << "ull, " << xr << lo << ", " << xr << hi << ");\n";
         loaded[lo] = loaded[hi] = 1;
       } else {
         if (xc)
-          o << "  const double2 " << xr << k << " = __ldg(reinterpret_cast<const double2*>(" << Xr << " + " << off * 2 << "ull));\n";
+          (*out) << "  const double2 " << xr << k << " = __ldg(reinterpret_cast<const double2*>(" << Xr << " + " << off * 2 << "ull));\n";
         else
-          o << "  const double2 " << xr << k << " = make_double2(__ldg(" << Xr << " + " << off << "ull), 0.0);\n";
+          (*out) << "  const double2 " << xr << k << " = make_double2(__ldg(" << Xr << " + " << off << "ull), 0.0);\n";
         loaded[k] = 1;
       }
     }
   }
-  o << stage.str();   // the row's loads are in flight while the CTA stages Y
+  out = &compute;
   bool even_out = oc && plan.size_out % 2 == 0 && ((uintptr_t)res->dptr % 32) == 0;
   for (uint64_t v : rs.row_c) even_out = even_out && v % 2 == 0;
   std::vector<std::string> pending(R);
   std::vector<uint64_t> pending_c(R, 0);
   auto flush = [&](uint32_t r) {
     if (pending[r].empty()) return;
-    o << "  *reinterpret_cast<double2*>(O" << r << " + " << pending_c[r] * 2 << "ull) = " << pending[r] << ";\n";
+    (*out) << "  *reinterpret_cast<double2*>(O" << r << " + " << pending_c[r] * 2 << "ull) = " << pending[r] << ";\n";
     pending[r].clear();
   };
   for (uint32_t j = 0; j < rs.n_cols; ++j) {
-    for (uint32_t r = 0; r < R; ++r) o << "  double2 r" << r << "_" << j << " = make_double2(0.0, 0.0);\n";
+    for (uint32_t r = 0; r < R; ++r) (*out) << "  double2 r" << r << "_" << j << " = make_double2(0.0, 0.0);\n";
     for (size_t k = 0; k < kx.size(); ++k) {
       std::string yv;
       if (Y->sparse()) {
@@ -315,22 +321,22 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
           yv = yc ? "__ldg(reinterpret_cast<const double2*>(Y + " + std::to_string(f * 2) + "ull))"
                   : "make_double2(__ldg(Y + " + std::to_string(f) + "ull), 0.0)";
       }
-      o << "  { const double2 y = " << yv << ";\n";
+      (*out) << "  { const double2 y = " << yv << ";\n";
       for (uint32_t r = 0; r < R; ++r) {
         const std::string xv = "x" + std::to_string(r) + "_" + std::to_string(k), acc = "r" + std::to_string(r) + "_" + std::to_string(j);
-        o << "    { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : "y") << ", " << (rs.rows_from_a ? "y" : xv) << "); " << acc << ".x = "
+        (*out) << "    { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : "y") << ", " << (rs.rows_from_a ? "y" : xv) << "); " << acc << ".x = "
           << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(" << acc << ".x, t.x); " << acc << ".y = "
           << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(" << acc << ".y, t.y); }\n";
       }
-      o << "  }\n";
+      (*out) << "  }\n";
     }
     const uint64_t c = rs.col_c[j];
     for (uint32_t r = 0; r < R; ++r) {
       const std::string acc = "r" + std::to_string(r) + "_" + std::to_string(j);
       if (!oc) {
-        o << "  O" << r << "[" << c << "ull] = " << acc << ".x;\n";
+        (*out) << "  O" << r << "[" << c << "ull] = " << acc << ".x;\n";
       } else if (even_out && !pending[r].empty() && c == pending_c[r] + 1 && pending_c[r] % 2 == 0) {
-        o << "  st32(O" << r << " + " << pending_c[r] * 2 << "ull, " << pending[r] << ", " << acc << ");\n";
+        (*out) << "  st32(O" << r << " + " << pending_c[r] * 2 << "ull, " << pending[r] << ", " << acc << ");\n";
         pending[r].clear();
       } else {
         flush(r);
@@ -341,6 +347,13 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
     }
   }
   for (uint32_t r = 0; r < R; ++r) flush(r);
+  if (!passes) {
+    o << body.str() << loads.str() << stage.str() << compute.str();   // the row's loads are in flight while the CTA stages Y
+  } else {
+    o << stage.str();
+    o << "  for (unsigned i = i0; i < " << rs.n_rows << "u; i += " << (uint64_t)T * R << "u) {   // passes over the rows of the point\n";
+    o << body.str() << loads.str() << compute.str() << "  }\n";
+  }
   o << "}\n";
   gen.source = o.str();
   return gen;

@@ -1524,6 +1524,11 @@ def test_row_parallel_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
     cases.append((I1, I2, None, sp.contract_cuda_source(ci1, ci2)))
     A4, ca4, _ = batch([c(1), c(2), c(3), c(5)], sp.C64)          # 512 rows: one point per 256-thread CTA
     cases.append((A4, B, None, sp.contract_cuda_source(ca4, cb)))
+    A5, ca5, _ = batch([sp.Euclidean.new_slot(3, 7), c(2), c(3), c(5), c(6)], sp.C64)   # 1 536 rows: three passes of 512
+    B5, cb5, _ = batch([c(3), c(4)], sp.C64)
+    src5 = sp.contract_cuda_source(ca5, cb5)
+    assert "passes over the rows" in src5
+    cases.append((A5, B5, None, src5))
     S, _ = shared_dense([c(3), c(4)])
     cases.append((A, S, None, None))
     cases.append((S, A, None, None))
