@@ -118,11 +118,13 @@ struct Generated {
 // read of Y's component, two products; 856 -> 820 us, four rows: 928).  Measured at 2^18 points
 // (profiles/r02_pairwise_rows.txt): 4.01 ms -> 0.82 ms (5.6 TB/s) for the product above, 0.85 -> 0.29 ms for
 // dense[coad^3] x sparse f.  A prefetch of the rows 256-8192 points ahead into L2 was tried and dropped (+3 % before Y
-// was staged, -7 % after).
+// was staged, -7 % after).  Rows too long for registers against few columns (full contractions to a scalar / vector) are
+// streamed: a loop over k, offsets in constant tables, one accumulator per column (1.05 -> 0.96 ms for coad^3 . coad^3).
 struct RowSplit {
   bool ok = false;
   bool rows_from_a = true;
   uint32_t n_rows = 0, n_cols = 0;
+  bool k_outer = false;                 // the row does not fit registers: walk k outside, keep one accumulator per column
   std::vector<uint64_t> row_x, row_c;   // per row: element offset inside X's record / inside the result record
   std::vector<uint64_t> col_y, col_c;   // per column: element offset inside Y's record / inside the result record
 };
@@ -136,8 +138,12 @@ bool register_form_fits(const spn_contract_plan& plan, const KTables& kt, const 
 
 // register tiling: a thread takes R neighbouring rows, so every component of Y it reads serves R products
 // (SPN_PAIR_ROWS_PER_THREAD=1|2|4 for A/B runs)
-uint32_t rows_per_thread(uint64_t n_rows, uint64_t n_cols, uint64_t n_k) {
+uint32_t rows_per_thread(uint64_t n_rows, uint64_t n_cols, uint64_t n_k, bool k_outer) {
   uint32_t R = getenv("SPN_PAIR_ROWS_PER_THREAD") ? (uint32_t)atoi(getenv("SPN_PAIR_ROWS_PER_THREAD")) : 2u;
+  if (k_outer) {   // registers hold R x n_cols accumulators
+    while (R > 1 && (n_rows % R != 0 || (uint64_t)R * n_cols > 32 || (uint64_t)R * n_cols * n_k > 4096)) R /= 2;
+    return R == 0 ? 1u : R;
+  }
   while (R > 1 && (n_rows % R != 0 || n_rows / R < 2 || (uint64_t)R * n_k > 48 || (uint64_t)R * n_cols * n_k > 1536)) R /= 2;
   return R == 0 ? 1u : R;
 }
@@ -154,8 +160,12 @@ RowSplit row_split(const spn_contract_plan& plan, const KTables& kt, const spn_t
   rs.rows_from_a = a_x && (!b_x || free_a >= free_b);
   const uint64_t n_rows = rs.rows_from_a ? free_a : free_b, n_cols = rs.rows_from_a ? free_b : free_a;
   const uint64_t n_k = kt.off_a.size();
-  if (n_rows < 2 || n_cols > 256 || n_k == 0 || n_k > 64 || n_cols * n_k > 1024) return rs;
-  if (n_rows > (1u << 16)) return rs;   // per-row offset tables
+  if (n_rows < 1 || n_rows > (1u << 16) || n_cols > 256 || n_k == 0) return rs;   // (per-row offset tables)
+  const bool row_in_regs = n_rows >= 2 && n_k <= 64 && n_cols * n_k <= 1024;
+  // long rows against few columns (full contractions to a scalar or a vector): the components of the row are used once
+  // per column, so they are streamed — k outside, one accumulator per column; every accumulator still sums k in order
+  rs.k_outer = !row_in_regs && n_cols <= 16 && n_k <= 4096 && !a->sparse() && !b->sparse();
+  if (!row_in_regs && !rs.k_outer) return rs;
   if (plan.size_a > (1u << 20) || plan.size_b > (1u << 20) || plan.size_out > (1u << 20)) return rs;
   rs.n_rows = (uint32_t)n_rows;
   rs.n_cols = (uint32_t)n_cols;
@@ -193,7 +203,7 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   const std::vector<long long>& ky = rs.rows_from_a ? kt.off_b : kt.off_a;
   const bool xc = X->dtype == SPN_C64, yc = Y->dtype == SPN_C64, oc = res->dtype == SPN_C64;
   Generated gen;
-  const uint32_t R = rows_per_thread(rs.n_rows, rs.n_cols, kx.size());
+  const uint32_t R = rows_per_thread(rs.n_rows, rs.n_cols, kx.size(), rs.k_outer);
   // threads per point: one per R rows, at most 256 — a point with more rows is walked in passes of 256 R rows
   const uint32_t T = std::min<uint32_t>(rs.n_rows / R, 256u);
   const bool passes = (uint64_t)T * R < rs.n_rows;
@@ -204,9 +214,12 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   gen.points_per_cta = P;
   // a batched Y is staged once per CTA in shared memory: every row-thread of a point reads all of it (a broadcast), and
   // through L1 those reads met each other's misses (ncu: L1 hit rate 38 %, long_scoreboard 9 cycles per issue, FP64 pipe 41 %)
-  const bool y_smem = Y->batched() && (Y->size() * (uint64_t)(yc ? 16 : 8)) % 16 == 0 && !getenv("SPN_PAIR_ROWS_NO_SMEM");
+  bool y_smem = Y->batched() && (Y->size() * (uint64_t)(yc ? 16 : 8)) % 16 == 0 && !getenv("SPN_PAIR_ROWS_NO_SMEM");
   const uint64_t y_units = y_smem ? (Y->size() * (uint64_t)(yc ? 16 : 8) + 15) / 16 : 0;   // 16-byte units per point
   const uint64_t y_row = y_units | 1ull;   // odd stride: the points of one warp sit in different banks
+  // (few threads per point and a large partner — a full contraction of two large tensors — would need hundreds of KB:
+  // there every thread streams its own record of Y like its row of X)
+  if (y_smem && P * y_row * 16 > 64 * 1024) y_smem = false;
   if (y_smem) gen.smem_bytes = (size_t)(P * y_row * 16);
   std::ostringstream o;
   o << "// generated by spenso_b200 (pairwise_jit.cu): one pairwise contraction, thread = (point, row of " << xn << "), reference rounding\n";
@@ -225,6 +238,15 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   o << "};\n__device__ const unsigned kRowC[" << rs.n_rows << "] = {";
   for (uint64_t v : rs.row_c) o << v << "u, ";
   o << "};\n";
+  if (rs.k_outer) {
+    o << "__constant__ unsigned kTabX[" << kx.size() << "] = {";
+    for (long long v : kx) o << v << "u, ";
+    o << "};\n__constant__ unsigned kTabY[" << ky.size() << "] = {";
+    for (long long v : ky) o << v << "u, ";
+    o << "};\n__constant__ unsigned char kTabNeg[" << kt.sign.size() << "] = {";
+    for (unsigned char v : kt.sign) o << (v ? 1 : 0) << ", ";
+    o << "};\n";
+  }
   o << "extern \"C\" __global__ void __launch_bounds__(" << gen.block << ") " << kname
     << "(const double* __restrict__ A, ull csA, const double* __restrict__ B, ull csB, double* __restrict__ C, ull csC, ull n_points) {\n";
   o << "  const ull p0 = (ull)blockIdx.x * " << P << "ull;   // first point of this CTA\n";
@@ -275,7 +297,7 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
   std::map<long long, size_t> k_of_off;
   for (size_t k = 0; k < kx.size(); ++k)
     if (k_used[k]) k_of_off[kx[k]] = k;
-  for (uint32_t r = 0; r < R; ++r) {
+  for (uint32_t r = 0; r < R && !rs.k_outer; ++r) {
     std::vector<char> loaded(kx.size(), 0);
     const std::string xr = "x" + std::to_string(r) + "_", Xr = "X" + std::to_string(r);
     for (size_t k = 0; k < kx.size(); ++k) {
@@ -305,9 +327,59 @@ Generated generate_rows(const RowSplit& rs, const spn_contract_plan& plan, const
     (*out) << "  *reinterpret_cast<double2*>(O" << r << " + " << pending_c[r] * 2 << "ull) = " << pending[r] << ";\n";
     pending[r].clear();
   };
+  auto y_value = [&](uint32_t j, size_t k) -> std::string {   // "" = the sparse fibre holds no entry here
+    if (Y->sparse()) {
+      const double2* v = y_entry(j, k);
+      return v ? "make_double2(" + lit(v->x) + ", " + lit(v->y) + ")" : std::string();
+    }
+    const uint64_t f = rs.col_y[j] + (uint64_t)ky[k];
+    if (y_smem)
+      return yc ? "*reinterpret_cast<const double2*>(Y + " + std::to_string(f * 2) + "u)" : "make_double2(Y[" + std::to_string(f) + "u], 0.0)";
+    return yc ? "__ldg(reinterpret_cast<const double2*>(Y + " + std::to_string(f * 2) + "ull))"
+              : "make_double2(__ldg(Y + " + std::to_string(f) + "ull), 0.0)";
+  };
+  auto product = [&](const std::string& xv, uint32_t r, uint32_t j, size_t k) {
+    const std::string acc = "r" + std::to_string(r) + "_" + std::to_string(j);
+    (*out) << "    { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : "y") << ", " << (rs.rows_from_a ? "y" : xv) << "); " << acc << ".x = "
+           << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(" << acc << ".x, t.x); " << acc << ".y = "
+           << (kt.sign[k] ? "__dsub_rn" : "__dadd_rn") << "(" << acc << ".y, t.y); }\n";
+  };
+  if (rs.k_outer) {
+    // A real loop over k with the offsets in constant tables (uniform across the warp): straight-line code lets ptxas hoist
+    // every load of a 512-component row above the sequential accumulation chain and spill 24 KB per thread.
+    for (uint32_t j = 0; j < rs.n_cols; ++j)
+      for (uint32_t r = 0; r < R; ++r) (*out) << "  double2 r" << r << "_" << j << " = make_double2(0.0, 0.0);\n";
+    (*out) << "#pragma unroll 4\n  for (unsigned k = 0; k < " << kx.size() << "u; ++k) {\n";
+    (*out) << "    const unsigned ox = kTabX[k], oy = kTabY[k];\n    const bool neg = kTabNeg[k] != 0;\n";
+    for (uint32_t r = 0; r < R; ++r) {
+      if (xc)
+        (*out) << "    const double2 x" << r << " = __ldg(reinterpret_cast<const double2*>(X" << r << ") + ox);\n";
+      else
+        (*out) << "    const double2 x" << r << " = make_double2(__ldg(X" << r << " + ox), 0.0);\n";
+    }
+    for (uint32_t j = 0; j < rs.n_cols; ++j) {
+      const uint64_t f = rs.col_y[j];
+      std::string yv;
+      if (y_smem)
+        yv = yc ? "reinterpret_cast<const double2*>(Y)[" + std::to_string(f) + "u + oy]" : "make_double2(Y[" + std::to_string(f) + "u + oy], 0.0)";
+      else
+        yv = yc ? "__ldg(reinterpret_cast<const double2*>(Y) + " + std::to_string(f) + "u + oy)"
+                : "make_double2(__ldg(Y + " + std::to_string(f) + "u + oy), 0.0)";
+      (*out) << "    { const double2 y = " << yv << ";\n";
+      for (uint32_t r = 0; r < R; ++r) {
+        const std::string xv = "x" + std::to_string(r), acc = "r" + std::to_string(r) + "_" + std::to_string(j);
+        // "-=" where the metric is negative: r - t and r + (-t) are the same IEEE operation
+        (*out) << "      { const double2 t = cmul_rn(" << (rs.rows_from_a ? xv : "y") << ", " << (rs.rows_from_a ? "y" : xv) << "); " << acc
+               << ".x = __dadd_rn(" << acc << ".x, neg ? -t.x : t.x); " << acc << ".y = __dadd_rn(" << acc << ".y, neg ? -t.y : t.y); }\n";
+      }
+      (*out) << "    }\n";
+    }
+    (*out) << "  }\n";
+  }
   for (uint32_t j = 0; j < rs.n_cols; ++j) {
-    for (uint32_t r = 0; r < R; ++r) (*out) << "  double2 r" << r << "_" << j << " = make_double2(0.0, 0.0);\n";
-    for (size_t k = 0; k < kx.size(); ++k) {
+    if (!rs.k_outer)
+      for (uint32_t r = 0; r < R; ++r) (*out) << "  double2 r" << r << "_" << j << " = make_double2(0.0, 0.0);\n";
+    for (size_t k = 0; k < kx.size() && !rs.k_outer; ++k) {
       std::string yv;
       if (Y->sparse()) {
         const double2* v = y_entry(j, k);

@@ -1529,6 +1529,18 @@ def test_row_parallel_kernels_equal_the_generic_kernels_bit_for_bit(ctx, seed):
     src5 = sp.contract_cuda_source(ca5, cb5)
     assert "passes over the rows" in src5
     cases.append((A5, B5, None, src5))
+    # rows too long for registers, few columns: streamed over k (full contractions to a scalar / a vector)
+    A2, ca2, da2 = batch([c(1), c(2), c(3)], sp.C64)
+    cases.append((A, A2, (ca, da, ca2, da2), sp.contract_cuda_source(ca, ca2)))                 # 512 products -> scalar
+    A6, ca6, _ = batch([c(1), c(2), c(3), c(4)], sp.C64)
+    B6, cb6, _ = batch([c(2), c(3), c(4)], sp.F64)
+    cases.append((A6, B6, None, sp.contract_cuda_source(ca6, cb6, dtype_b=sp.F64)))               # 8 rows x 512, c64 x f64
+    cases.append((B6, A6, None, sp.contract_cuda_source(cb6, ca6, dtype_a=sp.F64)))
+    M7, cm7, _ = batch([m(1), m(2), m(3), m(4), b(5)], sp.C64)
+    M8, cm8, _ = batch([m(1), m(2), m(3), m(4)], sp.C64)
+    src78 = sp.contract_cuda_source(cm7, cm8)
+    assert "kTabNeg" in src78
+    cases.append((M7, M8, None, src78))                                                           # 256 signed products per row
     S, _ = shared_dense([c(3), c(4)])
     cases.append((A, S, None, None))
     cases.append((S, A, None, None))

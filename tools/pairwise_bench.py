@@ -96,6 +96,8 @@ D2, sd2 = rand_batch([co(3), co(4)])
 cases.append(("dense[coad^3] x dense[coad^2] -> [coad^3]  (row-parallel)", lambda: D3.contract(D2), (sd3 + sd2 + 512) * 16))
 from spenso_b200 import workloads  # noqa: E402
 F = sp.SparseTensor.from_entries(ctx, [co(1), co(2), co(4)], workloads.su3_f())
+D3b, _ = rand_batch([co(1), co(2), co(3)])
+cases.append(("dense[coad^3] . dense[coad^3] -> scalar  (streamed rows)", lambda: D3.contract(D3b), (2 * sd3 + 1) * 16))
 cases.append(("dense[coad^3] x sparse f (shared) -> [coad^2]  (row-parallel)", lambda: D3.contract(F), (sd3 + 64) * 16))
 for name, fn, bytes_pp in cases:
     ms, r = timeit(fn)
