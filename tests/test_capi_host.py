@@ -430,5 +430,8 @@ def test_row_parallel_kernel_source_inspection():
     ent = {(1, 2, 3): 1.0, (2, 1, 3): -1.0, (4, 5, 6): 0.5j}
     src = sp.contract_cuda_source([c(2), c(3), c(4)], [c(1), c(2), c(3)], sparse_entries=ent, sparse_first=False)
     assert "thread = (point, row of A)" in src and src.count("cmul_rn(") == 3 + 1 and "__shared__" not in src
+    # a full contraction of two 512-component tensors: the row is streamed (loop over k, offsets in constant tables)
+    src = sp.contract_cuda_source([c(1), c(2), c(3)], [c(1), c(2), c(3)])
+    assert "1 rows x 1 columns x 512 contracted" in src and "kTabX[512]" in src and "for (unsigned k = 0; k < 512u; ++k)" in src
     # small tensors keep the thread = point kernel
     assert "thread = (point" not in sp.contract_cuda_source([b(1), b(2)], [b(2), b(3)])
